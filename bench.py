@@ -1,0 +1,482 @@
+#!/usr/bin/env python
+"""bench.py -- BPR triplet-updates/s (and ranked users/s) on B200 vs the reference CPU path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): synthetic 1M users x 100K items x 100M interactions,
+BPR k=64, one B200.  A "step" is one BPR epoch = nnz sampled triplets (what one call of the
+reference's BPR._fit_sgd does, cornac/models/bpr/recom_bpr.pyx:208-269).  For N > 1 every
+rank holds its own 1M-user / 100M-interaction shard (weak scaling), the 100K-item matrix is
+replicated and the item deltas are all-reduced once per epoch inside the timed region.
+
+value  = non-skipped triplet updates per second, inputs resident in HBM (CUDA events, max
+         over ranks);
+e2e    = the same through the host-buffer entry the plug-in's fit() uses
+         (engine.bpr_train_host): pinned-host CSR + factors -> H2D -> one epoch -> D2H;
+roofline / cpu_baseline / rank (ranked users/s) are reported alongside.
+--impl reference times the reference's own Cython/OpenMP kernel (oracle/_ref) on the host
+cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(n_users=1_000_000, n_items=100_000, nnz=100_000_000, k=64, lr=0.05, reg=0.01, use_bias=True)
+RANK_WORKLOAD = dict(n_q=4096, topk=100)          # secondary metric: ranked users/s on the same model
+CPU_SAMPLE = dict(n_users=100_000, nnz_target=10_000_000)   # bounded sample for the CPU legs (same k, same items)
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# --------------------------------------------------------------------------------------
+# synthetic data (torch on the GPU is used as a fast array library here; not product code)
+def synth_interactions(n_users, n_items, nnz, seed, device):
+    """Unique (u, i) pairs: user activity ~ log-normal (mean degree nnz/n_users), item
+    popularity ~ Zipf(1.0); returns CSR (indptr int32, indices int32) on `device`."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    w_u = torch.exp(torch.randn(n_users, generator=g, device=device, dtype=torch.float64))
+    cdf_u = torch.cumsum(w_u / w_u.sum(), 0)
+    w_i = 1.0 / torch.arange(1, n_items + 1, device=device, dtype=torch.float64)
+    perm = torch.randperm(n_items, generator=g, device=device)          # popular ids spread over the id range
+    cdf_i = torch.cumsum(w_i / w_i.sum(), 0)
+    keys = torch.empty(0, dtype=torch.int64, device=device)
+    need = nnz
+    while need > 0:
+        m = int(need * 1.25) + 1024
+        u = torch.searchsorted(cdf_u, torch.rand(m, generator=g, device=device, dtype=torch.float64)).clamp_(max=n_users - 1)
+        i = perm[torch.searchsorted(cdf_i, torch.rand(m, generator=g, device=device, dtype=torch.float64)).clamp_(max=n_items - 1)]
+        keys = torch.unique(torch.cat([keys, u * n_items + i]))
+        del u, i
+        need = nnz - keys.numel()
+    if keys.numel() > nnz:
+        drop = torch.randperm(keys.numel(), generator=g, device=device)[: keys.numel() - nnz]
+        mask = torch.ones(keys.numel(), dtype=torch.bool, device=device)
+        mask[drop] = False
+        keys = keys[mask]
+    u = keys // n_items
+    indices = (keys % n_items).to(torch.int32)
+    counts = torch.bincount(u, minlength=n_users)
+    indptr = torch.zeros(n_users + 1, dtype=torch.int64, device=device)
+    indptr[1:] = torch.cumsum(counts, 0)
+    return indptr.to(torch.int32), indices.contiguous()
+
+
+def init_factors(n_users, n_items, k, seed, device):
+    """(U[0,1) - 0.5) / k like BPR._init (recom_bpr.pyx:145-152)."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    U = (torch.rand((n_users, k), generator=g, device=device) - 0.5) / k
+    V = (torch.rand((n_items, k), generator=g, device=device) - 0.5) / k
+    B = torch.zeros(n_items, device=device)
+    return U, V, B
+
+
+# --------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes(k, updates, skipped, mean_deg):
+    """3 rows read + 3 written (24k B) + 4 biases R/W (16 B) + indices/coo/indptr
+    (16 B) + 4*ceil(log2(deg+1)) B binary search per update; a skipped sample costs only the
+    sampling + search bytes."""
+    search = 4 * math.ceil(math.log2(mean_deg + 1))
+    return updates * (24 * k + 16 + 16 + search) + skipped * (16 + search)
+
+
+# --------------------------------------------------------------------------------------
+def reference_fit_sgd_runner(indptr, indices, n_items, k, lr, reg, n_threads):
+    """Returns (run_epoch() -> (correct, skipped), kind, cores).  Uses the UNMODIFIED compiled
+    reference (oracle/_ref: cornac.models.bpr.recom_bpr.BPR._fit_sgd + RNGVector) when it is
+    importable, else the oracle's OpenMP port."""
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    n_users = len(indptr) - 1
+    rng = np.random.RandomState(1)
+    U = ((rng.uniform(0, 1, (n_users, k)).astype(np.float32) - 0.5) / k)
+    V = ((rng.uniform(0, 1, (n_items, k)).astype(np.float32) - 0.5) / k)
+    B = np.zeros(n_items, np.float32)
+    user_ids = np.repeat(np.arange(n_users), np.diff(indptr)).astype(np.int32)
+    try:
+        if ref not in sys.path:
+            sys.path.insert(0, ref)
+        import multiprocessing
+        from cornac.models.bpr.recom_bpr import BPR as RefBPR, RNGVector
+        n_threads = n_threads or multiprocessing.cpu_count()
+        m = RefBPR(k=k, learning_rate=lr, lambda_reg=reg, use_bias=True)
+        rp = RNGVector(n_threads, len(user_ids) - 1, 11)
+        rn = RNGVector(n_threads, n_items - 1, 12)
+        neg = np.arange(n_items, dtype=np.int32)
+
+        def run():
+            return m._fit_sgd(rp, rn, n_threads, user_ids, indices, neg, indptr, U, V, B)
+        return run, "reference", n_threads
+    except Exception as e:   # reference install absent: the oracle port, all threads
+        log("[bench] reference install not importable (%s); using the oracle OpenMP port" % (e,))
+        from oracle import oracle as O
+        n_threads = n_threads or O.n_threads()
+        state = {"e": 0}
+
+        def run():
+            state["e"] += 1
+            return O.bpr_epoch_omp(indptr, indices, n_items, U, V, B, lr, reg, True, n_threads, seed=state["e"])
+        return run, "port", n_threads
+
+
+def cpu_sample_csr(indptr_host, indices_host):
+    """Bounded sample of the workload for the CPU legs: the first users of the same synthetic
+    matrix (same k, same 100K items, ~1/10 of the interactions)."""
+    n_u = CPU_SAMPLE["n_users"]
+    n_u = min(n_u, len(indptr_host) - 1)
+    end = int(indptr_host[n_u])
+    return np.ascontiguousarray(indptr_host[: n_u + 1]), np.ascontiguousarray(indices_host[:end])
+
+
+def time_cpu_epochs(run, nnz, min_seconds=8.0, max_epochs=6):
+    run()                                             # warm-up epoch (page-in, thread pool)
+    t_tot, upd, eps = 0.0, 0, 0
+    while t_tot < min_seconds and eps < max_epochs:
+        t0 = time.perf_counter()
+        c, s = run()
+        t_tot += time.perf_counter() - t0
+        upd += nnz - s
+        eps += 1
+    return upd / t_tot, t_tot, eps
+
+
+# --------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debug only; result then INVALID)")
+    ap.add_argument("--atomic", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-rank", action="store_true")
+    args = ap.parse_args()
+
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    W = dict(WORKLOAD)
+    if args.scale != 1.0:
+        W["n_users"] = max(1000, int(W["n_users"] * args.scale))
+        W["nnz"] = max(10000, int(W["nnz"] * args.scale))
+    k = W["k"]
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        return run_reference_arm(args, W)
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from cornac_b200 import engine
+    from cornac_b200.parallel import ItemReplicaSync
+
+    # ---- data: every rank builds its own user shard (weak scaling), items are shared
+    t0 = time.time()
+    indptr, indices = synth_interactions(W["n_users"], W["n_items"], W["nnz"], seed=1234 + rank, device=dev)
+    U, V, B = init_factors(W["n_users"], W["n_items"], k, seed=99, device=dev)     # V/B identical on all ranks
+    if world > 1:
+        dist.broadcast(V, 0); dist.broadcast(B, 0)
+    data = engine.BprData(indptr, indices)
+    nnz = data.nnz
+    mean_deg = nnz / W["n_users"]
+    torch.cuda.synchronize()
+    log("[bench] rank %d data ready in %.1fs: %d users x %d items x %d nnz" % (rank, time.time() - t0, W["n_users"], W["n_items"], nnz))
+    sync = ItemReplicaSync([V, B]) if world > 1 else None
+    stats = torch.zeros(2, dtype=torch.int64, device=dev)
+    key = 0xB200
+
+    def step(epoch):
+        engine.bpr_epoch(data, W["n_items"], U, V, B, W["lr"], W["reg"], W["use_bias"], key + rank, epoch, stats,
+                         atomic=bool(args.atomic))
+        if sync is not None:
+            sync.exchange()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for e in range(args.warmup):
+        step(e)
+    barrier()
+    stats.zero_()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kern_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    ev0.record()
+    for e in range(args.steps):
+        kern_ev[e][0].record()
+        engine.bpr_epoch(data, W["n_items"], U, V, B, W["lr"], W["reg"], W["use_bias"], key + rank, args.warmup + e,
+                         stats, atomic=bool(args.atomic))
+        kern_ev[e][1].record()
+        if sync is not None:
+            sync.exchange()
+    ev1.record()
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    ms_total = ev0.elapsed_time(ev1)
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kern_ev]))
+    correct, skipped = stats.cpu().tolist()
+    t = torch.tensor([ms_total, float(nnz * args.steps - skipped), float(skipped), kern_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms_total, updates, skipped_all, kern_ms = tmax[0].item(), tsum[1].item(), tsum[2].item(), tmax[3].item()
+    else:
+        updates, skipped_all = t[1].item(), t[2].item()
+    value = updates / (ms_total * 1e-3)
+
+    # ---- roofline of the dominant kernel (bpr_hogwild_kernel), this rank's launches
+    peak, peak_src = measured_peaks()
+    upd_per_launch = (nnz * args.steps - skipped) / args.steps
+    alg_bytes = algorithmic_bytes(k, upd_per_launch, skipped / args.steps, mean_deg)
+    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "bpr_hogwild_dram_bytes.json")
+    if os.path.exists(prof):
+        try:
+            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"kernel": "bpr_hogwild_kernel<G=16,NPL=1,VEC,S=2>", "bound": "hbm", "achieved": round(achieved, 1),
+                "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
+                "peak_source": peak_src, "algorithmic_bytes_per_update": 24 * k + 32 + 4 * math.ceil(math.log2(mean_deg + 1)),
+                "kernel_ms": round(kern_ms, 3)}
+
+    # ---- e2e: host buffers through the plug-in's training entry, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, W, engine, indptr, indices, dev, world, rank)
+
+    # ---- secondary metric: ranked users/s (score + exclusion + top-k) on the trained model
+    rank_metric = None
+    if not args.no_rank and rank == 0:
+        rank_metric = run_rank(W, engine, data, U, V, B, dev)
+
+    # ---- CPU baseline on rank 0, N = 1 only
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ip, ix = cpu_sample_csr(indptr.cpu().numpy(), indices.cpu().numpy())
+        run, kind, cores = reference_fit_sgd_runner(ip, ix, W["n_items"], k, W["lr"], W["reg"], 0)
+        v, secs, eps = time_cpu_epochs(run, len(ix))
+        cpu_baseline = {"value": round(v, 1), "unit": "triplet-updates/s", "cores": cores, "kind": kind,
+                        "sample": "first %d users of the same matrix: %d interactions, %d items, k=%d, %d epoch(s) in %.1fs"
+                                  % (len(ip) - 1, len(ix), W["n_items"], k, eps, secs)}
+
+    if rank == 0:
+        out = {
+            "metric": "BPR triplet-updates/sec", "value": round(value, 1), "unit": "updates/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE.json configs[1]: %d users x %d items x %d interactions per GPU, BPR k=%d, "
+                                   "lr=%g reg=%g use_bias; user activity log-normal, item popularity Zipf(1.0), unique pairs"
+                                   % (W["n_users"], W["n_items"], nnz, k, W["lr"], W["reg"]),
+                       "step": "one epoch = nnz sampled triplets (Hogwild, on-device Philox sampling)",
+                       "l2": "working set (U 256 MB + CSR 800 MB per GPU) exceeds the 126 MB L2; no flush needed",
+                       "parallelism": "users sharded x%d, items replicated, 1 all-reduce of item deltas per epoch" % world,
+                       "scatter": "red.global.add.v4.f32" if args.atomic else "st.global.cg.v4.f32 (Hogwild)"},
+            "samples_per_s": round((nnz * args.steps * world) / (ms_total * 1e-3), 1),
+            "skipped_frac": round(skipped_all / (nnz * args.steps * world), 5),
+            "gpu_launches": args.steps * (1 + (2 * 2 if world > 1 else 0)),
+            "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "rank": rank_metric,
+        }
+        if args.scale != 1.0:
+            out["INVALID"] = "scaled-down debug run (--scale %g)" % args.scale
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def run_e2e(args, W, engine, indptr, indices, dev, world, rank):
+    import torch
+    import torch.distributed as dist
+    k = W["k"]
+    pin = lambda t: t.cpu().pin_memory()
+    h_indptr, h_indices = pin(indptr), pin(indices)
+    U, V, B = init_factors(W["n_users"], W["n_items"], k, seed=7, device=dev)
+    hU, hV, hB = pin(U), pin(V), pin(B)
+    del U, V, B
+    torch.cuda.empty_cache()
+    nnz = h_indices.numel()
+    h2d = sum(t.numel() * t.element_size() for t in (h_indptr, h_indices, hU, hV, hB))
+    d2h = sum(t.numel() * t.element_size() for t in (hU, hV, hB)) + 16
+    steps = max(2, min(args.steps, 3))
+
+    def one(e):
+        hist, _ = engine.bpr_train_host(h_indptr.numpy(), h_indices.numpy(), W["n_items"], hU.numpy(), hV.numpy(),
+                                        hB.numpy(), W["lr"], W["reg"], W["use_bias"], 1, key=77 + e + rank,
+                                        atomic=bool(args.atomic), on_epoch=lambda *a: None)
+        return hist[0]
+
+    one(0)                                             # warm-up (allocator, pinned staging)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    upd = 0
+    for e in range(steps):
+        c, s = one(1 + e)
+        upd += nnz - s
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt, float(upd)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tm = t.clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ts = t.clone(); dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+        dt, upd = tm[0].item(), ts[1].item()
+    return {"value": round(upd / dt, 1), "unit": "updates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "steps": steps, "ms_per_step": round(dt / steps * 1e3, 2),
+            "path": "engine.bpr_train_host (the call BPR.fit makes): pinned host CSR + U/V/B -> H2D -> 1 epoch -> D2H U/V/B + stats"}
+
+
+def run_rank(W, engine, data, U, V, B, dev):
+    """ranked users/s: score + exclusion of train positives + top-100 for a batch of users."""
+    import torch
+    from cornac_b200._lib import check, current_stream, load, ptr
+    L = load()
+    n_q, topk, k = RANK_WORKLOAD["n_q"], RANK_WORKLOAD["topk"], W["k"]
+    n_q = min(n_q, W["n_users"])
+    uidx = torch.arange(n_q, device=dev, dtype=torch.int64)
+    ex_ptr = data.indptr[: n_q + 1].to(torch.int64).contiguous()
+    ids = torch.empty((n_q, topk), dtype=torch.int32, device=dev)
+    sc = torch.empty((n_q, topk), dtype=torch.float32, device=dev)
+    nb = int(L.b200_rank_topk_workspace_bytes(n_q, W["n_items"], k, topk))
+    ws = torch.empty(max(nb, 16), dtype=torch.uint8, device=dev)
+
+    def go():
+        check(L.b200_rank_topk(ptr(U), ptr(uidx), n_q, ptr(V), W["n_items"], k, ptr(B), None, ptr(ex_ptr), ptr(data.indices),
+                               topk, ptr(ids), ptr(sc), ptr(ws), nb, current_stream()), "b200_rank_topk")
+    go()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        go()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    return {"metric": "ranked users/sec", "value": round(n_q / (ms * 1e-3), 1), "unit": "users/s",
+            "config": "%d users x %d items k=%d top-%d, train positives excluded" % (n_q, W["n_items"], k, topk),
+            "ms": round(ms, 3), "tflops": round(2.0 * k * W["n_items"] * n_q / (ms * 1e-3) / 1e12, 2)}
+
+
+def run_reference_arm(args, W):
+    """--impl reference: the reference's own CPU kernel on a bounded sample of the workload."""
+    import torch
+    k = W["k"]
+    if torch.cuda.is_available():
+        indptr, indices = synth_interactions(W["n_users"], W["n_items"], W["nnz"], seed=1234, device=torch.device("cuda", 0))
+        ip, ix = cpu_sample_csr(indptr.cpu().numpy(), indices.cpu().numpy())
+        del indptr, indices
+    else:   # no GPU: generate the sample directly at sample size
+        frac = CPU_SAMPLE["n_users"] / W["n_users"]
+        ipt, ixt = synth_interactions(CPU_SAMPLE["n_users"], W["n_items"], int(W["nnz"] * frac), seed=1234, device=torch.device("cpu"))
+        ip, ix = ipt.numpy(), ixt.numpy()
+    run, kind, cores = reference_fit_sgd_runner(ip, ix, W["n_items"], k, W["lr"], W["reg"], 0)
+    nnz = len(ix)
+    for _ in range(max(1, min(args.warmup, 2))):
+        run()
+    t0 = time.perf_counter()
+    upd = 0
+    steps = args.steps
+    for _ in range(steps):
+        c, s = run()
+        upd += nnz - s
+    dt = time.perf_counter() - t0
+    v = upd / dt
+    sample = "first %d users of the configs[1] matrix: %d interactions, %d items, k=%d" % (len(ip) - 1, nnz, W["n_items"], k)
+    out = {"impl": "reference", "metric": "BPR triplet-updates/sec", "value": round(v, 1), "unit": "updates/s",
+           "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": round(dt / steps * 1e3, 2),
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "BASELINE.json configs[1] (1M x 100K x 100M, BPR k=64), each step = one _fit_sgd epoch "
+                                  "over a bounded sample: " + sample},
+           "cpu_baseline": {"value": round(v, 1), "unit": "updates/s", "cores": cores, "kind": kind, "sample": sample},
+           "e2e": {"value": round(v, 1), "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

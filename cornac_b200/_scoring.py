@@ -1,0 +1,127 @@
+"""Device-resident scoring/ranking shared by the BPR and MF plug-ins.
+
+Implements the `score()` / `rank()` half of the cornac.models.Recommender contract
+(reference: cornac/models/recommender.py:423-441, 476-530) on the GPU, plus the batched
+`rank_batch()` that the reference lacks (it ranks one user per Python call).
+"""
+import numpy as np
+import torch
+
+from . import engine
+from ._lib import B200Error
+
+
+class DeviceScoringMixin:
+    """Expects the subclass to provide `_b200_host_params()` returning
+    (U, V, item_base, user_off_vector_or_None, n_score_items) as numpy arrays."""
+
+    _B200_IGNORED = ("_b200_dev",)
+
+    def _b200_register_ignored(self):
+        for a in self._B200_IGNORED:
+            if a not in self.ignored_attrs:
+                self.ignored_attrs.append(a)
+        self._b200_dev = None
+
+    # ---- device cache --------------------------------------------------------------
+    def _b200_invalidate(self):
+        self._b200_dev = None
+
+    def _b200_device(self):
+        dev = getattr(self, "_b200_dev", None)
+        if dev is None:
+            engine.require_cuda()
+            U, V, item_base, user_off, n_items = self._b200_host_params()
+            dev = dict(
+                U=engine.to_device(U, torch.float32),
+                V=engine.to_device(V, torch.float32),
+                item_base=None if item_base is None else engine.to_device(item_base, torch.float32),
+                user_off=None if user_off is None else engine.to_device(user_off, torch.float32),
+                n_items=int(n_items),
+            )
+            self._b200_dev = dev
+        return dev
+
+    def _b200_adopt_device(self, U, V, item_base, user_off, n_items):
+        """Keep the freshly trained device tensors as the scoring cache (no re-upload)."""
+        self._b200_dev = dict(U=U, V=V, item_base=item_base, user_off=user_off, n_items=int(n_items))
+
+    # ---- scores --------------------------------------------------------------------
+    def _b200_scores_dev(self, user_indices):
+        """[n_q, n_items] device scores for known users."""
+        d = self._b200_device()
+        uidx = torch.as_tensor(np.asarray(user_indices, dtype=np.int64)).cuda()
+        uoff = None if d["user_off"] is None else d["user_off"][uidx].contiguous()
+        return engine.score_batch(d["U"], d["V"], user_idx=uidx, item_base=d["item_base"], user_off=uoff,
+                                  n_items=d["n_items"])
+
+    # ---- batched rank (the throughput path) ----------------------------------------
+    def rank_batch(self, user_indices, k, exclude=None):
+        """Top-k item ids and scores for many users at once.
+
+        user_indices : int array [n_q]
+        exclude      : optional scipy CSR matrix (rows = user index) whose stored columns
+                       are removed from each user's candidates (e.g. train_set.csr_matrix)
+        Returns (ids int32 [n_q, k] (-1 padded), scores float32 [n_q, k]) as numpy arrays,
+        ordered by (score desc, item id asc).
+        """
+        from ._lib import check, ptr, current_stream, load
+        d = self._b200_device()
+        L = load()
+        user_indices = np.asarray(user_indices, dtype=np.int64)
+        n_q = len(user_indices)
+        uidx = torch.from_numpy(user_indices).cuda()
+        uoff = None if d["user_off"] is None else d["user_off"][uidx].contiguous()
+        ex_ptr = ex_idx = None
+        if exclude is not None:
+            sub = exclude[user_indices] if n_q != exclude.shape[0] or not np.array_equal(
+                user_indices, np.arange(exclude.shape[0])) else exclude
+            sub = sub.tocsr()
+            sub.sort_indices()
+            ex_ptr = engine.to_device(sub.indptr.astype(np.int64), torch.int64)
+            ex_idx = engine.to_device(sub.indices.astype(np.int32), torch.int32)
+            if ex_idx.numel() == 0:
+                ex_idx = torch.zeros(1, dtype=torch.int32, device="cuda")
+        n_items, kdim = d["n_items"], d["V"].shape[1]
+        ids = torch.empty((n_q, k), dtype=torch.int32, device="cuda")
+        sc = torch.empty((n_q, k), dtype=torch.float32, device="cuda")
+        ws_bytes = int(L.b200_rank_topk_workspace_bytes(n_q, n_items, kdim, int(k)))
+        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device="cuda")
+        check(L.b200_rank_topk(ptr(d["U"]), ptr(uidx), n_q, ptr(d["V"]), n_items, kdim, ptr(d["item_base"]), ptr(uoff),
+                               ptr(ex_ptr), ptr(ex_idx), int(k), ptr(ids), ptr(sc), ptr(ws), ws_bytes,
+                               current_stream()), "b200_rank_topk")
+        return ids.cpu().numpy(), sc.cpu().numpy()
+
+    # ---- Recommender.rank ------------------------------------------------------------
+    def _b200_rank(self, all_scores_dev, item_indices, k):
+        """Reference semantics of Recommender.rank (recommender.py:513-530) given the
+        device score vector [1, total]: returns (ranked_items, item_scores)."""
+        total = all_scores_dev.shape[1]
+        all_item_scores = all_scores_dev[0].cpu().numpy()
+        if item_indices is None:
+            item_indices = np.arange(self.num_items)
+            n_cand_all = self.num_items == total
+        else:
+            item_indices = np.asarray(item_indices)
+            n_cand_all = False
+        item_scores = all_item_scores[item_indices]
+        n_cand = len(item_indices)
+        if k == -1 or k >= n_cand or k > 4096:
+            # full ordering requested: not the hot path (MRR-style metrics); host sort with the
+            # same total order (score desc, id asc)
+            order = np.lexsort((item_indices, -item_scores.astype(np.float64)))
+            return item_indices[order], item_scores
+        if n_cand_all:
+            ex_ptr = ex_idx = None
+        else:
+            mask = np.ones(total, dtype=bool)
+            mask[item_indices] = False
+            excl = np.flatnonzero(mask).astype(np.int32)
+            ex_ptr = engine.to_device(np.array([0, len(excl)], dtype=np.int64), torch.int64, pinned=False)
+            ex_idx = engine.to_device(excl if len(excl) else np.zeros(1, np.int32), torch.int32, pinned=False)
+        ids, _ = engine.topk_rows(all_scores_dev, int(k), ex_ptr, ex_idx)
+        top = ids[0].cpu().numpy().astype(item_indices.dtype)
+        in_top = np.zeros(total, dtype=bool)
+        in_top[top] = True
+        rest = item_indices[~in_top[item_indices]]
+        return np.concatenate([top, rest]), item_scores

@@ -1,0 +1,234 @@
+"""Device-side engine: thin, typed Python wrappers over the C ABI.
+
+Everything here operates on torch CUDA tensors used as plain device buffers.  The
+functions mirror the reference kernels one to one (see include/b200cornac.h):
+    bpr_epoch / bpr_epoch_replay   <-> BPR._fit_sgd          (cornac/models/bpr/recom_bpr.pyx:208-269)
+    MTSampler                      <-> RNGVector             (cornac/models/bpr/recom_bpr.pyx:54-62)
+    mf_epoch                       <-> backend_cpu.fit_sgd   (cornac/models/mf/backend_cpu.pyx:58-83)
+    score_batch                    <-> fast_dot              (cornac/utils/fast_dot.pyx:40-43)
+    topk_rows / rank_topk          <-> Recommender.rank      (cornac/models/recommender.py:476-530)
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import B200Error, check, current_stream, ptr
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise B200Error("cornac_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return _lib.load()
+
+
+def _dev(t, dtype, name):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == dtype and t.is_contiguous()):
+        raise B200Error("%s must be a contiguous CUDA tensor of dtype %s" % (name, dtype))
+    return t
+
+
+def to_device(a, dtype=None, pinned=True):
+    """H2D copy of a numpy array (through pinned memory) -> CUDA tensor."""
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    if pinned:
+        t = t.pin_memory()
+    return t.cuda(non_blocking=True)
+
+
+class BprData:
+    """Device copy of train_set.matrix in the layout the BPR kernels read:
+    CSR (indptr int32 [n_users+1], sorted indices int32 [nnz]) + the COO row array
+    (BPR._prepare_data, recom_bpr.pyx:154-161)."""
+
+    def __init__(self, indptr, indices, coo_row=None):
+        self.indptr = _dev(indptr, torch.int32, "indptr")
+        self.indices = _dev(indices, torch.int32, "indices")
+        self.n_users = self.indptr.numel() - 1
+        self.nnz = self.indices.numel()
+        if coo_row is None:
+            counts = (self.indptr[1:] - self.indptr[:-1]).to(torch.int64)
+            coo_row = torch.repeat_interleave(
+                torch.arange(self.n_users, device=self.indptr.device, dtype=torch.int32), counts)
+        self.coo_row = _dev(coo_row, torch.int32, "coo_row")
+        if self.coo_row.numel() != self.nnz:
+            raise B200Error("coo_row length %d != nnz %d" % (self.coo_row.numel(), self.nnz))
+
+    @classmethod
+    def from_host(cls, indptr, indices):
+        if len(indices) >= 2 ** 31:
+            raise B200Error("nnz >= 2^31 per shard is not supported (int32 CSR offsets)")
+        return cls(to_device(np.asarray(indptr), torch.int32), to_device(np.asarray(indices), torch.int32))
+
+
+def bpr_epoch(data, n_neg, U, V, B, lr, reg, use_bias, seed, epoch, stats, n_samples=None,
+              sample_base=0, atomic=False, exact_exp=False):
+    """One Hogwild BPR epoch on the current stream; `stats` (int64[2] CUDA) accumulates
+    (correct, skipped)."""
+    L = require_cuda()
+    k = U.shape[1]
+    _dev(U, torch.float32, "U"), _dev(V, torch.float32, "V"), _dev(B, torch.float32, "B")
+    _dev(stats, torch.int64, "stats")
+    flags = (_lib.SGD_ATOMIC if atomic else 0) | (_lib.SGD_EXACT_EXP if exact_exp else 0)
+    n = data.nnz if n_samples is None else int(n_samples)
+    check(L.b200_bpr_epoch(ptr(data.indptr), ptr(data.indices), ptr(data.coo_row), data.nnz, int(n_neg), n,
+                           ptr(U), ptr(V), ptr(B), int(k), float(lr), float(reg), int(bool(use_bias)),
+                           int(seed) & (2 ** 64 - 1), int(epoch), int(sample_base), flags, ptr(stats),
+                           current_stream()), "b200_bpr_epoch")
+
+
+def bpr_draw_host(seed, epoch, n, nnz, n_neg, sample_base=0):
+    """The (i_index, j_id) stream that bpr_epoch(seed, epoch) consumes, computed on the host."""
+    L = _lib.load()
+    ii = np.empty(n, dtype=np.int64)
+    jj = np.empty(n, dtype=np.int32)
+    check(L.b200_bpr_draw_host(int(seed) & (2 ** 64 - 1), int(epoch), int(sample_base), int(n), int(nnz), int(n_neg),
+                               ii.ctypes.data, jj.ctypes.data), "b200_bpr_draw_host")
+    return ii, jj
+
+
+def bpr_epoch_replay(data, i_index, j_id, U, V, B, lr, reg, use_bias, stats):
+    """Serial-equivalent application of an explicit sample stream (parity mode)."""
+    L = require_cuda()
+    _dev(i_index, torch.int64, "i_index"), _dev(j_id, torch.int32, "j_id")
+    _dev(U, torch.float32, "U"), _dev(V, torch.float32, "V"), _dev(B, torch.float32, "B")
+    check(L.b200_bpr_epoch_replay(ptr(i_index), ptr(j_id), i_index.numel(), ptr(data.indptr), ptr(data.indices),
+                                  ptr(data.coo_row), ptr(U), ptr(V), ptr(B), int(U.shape[1]), float(lr), float(reg),
+                                  int(bool(use_bias)), ptr(_dev(stats, torch.int64, "stats")), current_stream()),
+          "b200_bpr_epoch_replay")
+
+
+def bpr_train_host(indptr, indices, n_neg, U, V, B, lr, reg, use_bias, max_iter, key=0, replay_seeds=None,
+                   atomic=False, on_epoch=None, keep_device=False):
+    """Host-buffer entry of BPR training (what BPR.fit calls): uploads the CSR matrix and the
+    factors, runs `max_iter` epochs, writes the trained factors back INTO the given numpy
+    arrays U, V, B (pinned staging both ways).
+
+    replay_seeds = (seed_pos, seed_neg): deterministic mode -- per epoch the two mt19937 streams
+    of the reference's RNGVector are drawn on the host and applied by the serial-equivalent
+    replay kernel.  Otherwise Hogwild epochs with the on-device Philox sampler keyed by `key`.
+    Returns (per-epoch (correct, skipped) list or [], device tensors (U, V, B) if keep_device)."""
+    require_cuda()
+    data = BprData.from_host(indptr, indices)
+    nnz = data.nnz
+    dU, dV, dB = to_device(U, torch.float32), to_device(V, torch.float32), to_device(B, torch.float32)
+    stats = torch.zeros(2, dtype=torch.int64, device="cuda")
+    lr, reg = float(np.float32(lr)), float(np.float32(reg))
+    history = []
+    if replay_seeds is not None:
+        g_pos, g_neg = MTSampler(replay_seeds[0]), MTSampler(replay_seeds[1])
+        h_i = torch.empty(nnz, dtype=torch.int64).pin_memory()
+        h_j = torch.empty(nnz, dtype=torch.int32).pin_memory()
+        for epoch in range(max_iter):
+            g_pos.fill(nnz - 1, nnz, out=h_i.numpy())
+            g_neg.fill(int(n_neg) - 1, nnz, out=h_j.numpy())
+            d_i, d_j = h_i.cuda(non_blocking=True), h_j.cuda(non_blocking=True)
+            stats.zero_()
+            bpr_epoch_replay(data, d_i, d_j, dU, dV, dB, lr, reg, use_bias, stats)
+            history.append(tuple(stats.cpu().tolist()))      # also fences the staging buffers
+            if on_epoch:
+                on_epoch(epoch, *history[-1])
+    else:
+        for epoch in range(max_iter):
+            stats.zero_()
+            bpr_epoch(data, n_neg, dU, dV, dB, lr, reg, use_bias, key, epoch, stats, atomic=atomic)
+            if on_epoch:
+                history.append(tuple(stats.cpu().tolist()))
+                on_epoch(epoch, *history[-1])
+    for host, dev in ((U, dU), (V, dV), (B, dB)):
+        _to_host_into(host, dev)
+    return history, ((dU, dV, dB) if keep_device else None)
+
+
+def _to_host_into(host, dev):
+    """D2H into an existing numpy array (through pinned staging when it is not pinned itself)."""
+    out = torch.from_numpy(host) if (host.flags["C_CONTIGUOUS"] and host.flags.writeable) else None
+    if out is not None and out.dtype == dev.dtype and tuple(out.shape) == tuple(dev.shape):
+        out.copy_(dev)
+        return host
+    raise B200Error("destination array must be a writable C-contiguous %s array of shape %s" % (dev.dtype, tuple(dev.shape)))
+
+
+class MTSampler:
+    """boost::random::mt19937 + uniform_int_distribution<long>(0, hi) on the host
+    (RNGVector of the reference, one thread)."""
+
+    def __init__(self, seed):
+        self._L = _lib.load()
+        self._h = self._L.b200_mt_sampler_create(int(seed) & 0xFFFFFFFF)
+        if not self._h:
+            raise B200Error("b200_mt_sampler_create failed")
+
+    def fill(self, hi, n, dtype=np.int64, out=None):
+        out = np.empty(n, dtype=dtype) if out is None else out
+        fn = self._L.b200_mt_sampler_fill_i64 if out.dtype == np.int64 else self._L.b200_mt_sampler_fill_i32
+        check(fn(self._h, int(hi), int(n), out.ctypes.data), "b200_mt_sampler_fill")
+        return out
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.b200_mt_sampler_destroy(self._h)
+            self._h = None
+
+
+def mf_epoch(rid, cid, val, U, V, Bu, Bi, lr, reg, mu, use_bias, loss, ordered=False, atomic=False):
+    """One MF epoch; `loss` (float32[1] CUDA) receives sum(err^2)."""
+    L = require_cuda()
+    if rid.dtype not in (torch.int32, torch.int64) or cid.dtype != rid.dtype:
+        raise B200Error("rid/cid must both be int32 or int64")
+    _dev(rid, rid.dtype, "rid"), _dev(cid, rid.dtype, "cid"), _dev(val, torch.float32, "val")
+    for n_, t_ in (("U", U), ("V", V), ("Bu", Bu), ("Bi", Bi), ("loss", loss)):
+        _dev(t_, torch.float32, n_)
+    check(L.b200_mf_epoch(ptr(rid), ptr(cid), ptr(val), val.numel(), int(rid.dtype == torch.int32),
+                          ptr(U), ptr(V), ptr(Bu), ptr(Bi), int(U.shape[1]), float(lr), float(reg), float(mu),
+                          int(bool(use_bias)), int(bool(ordered)), _lib.SGD_ATOMIC if atomic else 0, ptr(loss),
+                          current_stream()), "b200_mf_epoch")
+
+
+def score_batch(U, V, user_idx=None, item_base=None, user_off=None, n_items=None, out=None):
+    """out[q, i] = (item_base[i] + user_off[q]) + dot(U[user_idx[q]], V[i]) for i < n_items."""
+    L = require_cuda()
+    _dev(U, torch.float32, "U"), _dev(V, torch.float32, "V")
+    n_items = V.shape[0] if n_items is None else int(n_items)
+    n_q = U.shape[0] if user_idx is None else user_idx.numel()
+    if user_idx is not None:
+        _dev(user_idx, torch.int64, "user_idx")
+    if out is None:
+        out = torch.empty((n_q, n_items), dtype=torch.float32, device=U.device)
+    check(L.b200_score_batch(ptr(U), ptr(user_idx), n_q, ptr(V), n_items, int(V.shape[1]), ptr(item_base),
+                             ptr(user_off), ptr(_dev(out, torch.float32, "out")), current_stream()),
+          "b200_score_batch")
+    return out
+
+
+def topk_rows(scores, topk, excl_indptr=None, excl_indices=None):
+    """Exact top-k (score desc, id asc) of each row of `scores`, with per-row exclusions."""
+    L = require_cuda()
+    _dev(scores, torch.float32, "scores")
+    n_q, n_items = scores.shape
+    ids = torch.empty((n_q, topk), dtype=torch.int32, device=scores.device)
+    sc = torch.empty((n_q, topk), dtype=torch.float32, device=scores.device)
+    if excl_indptr is not None:
+        _dev(excl_indptr, torch.int64, "excl_indptr"), _dev(excl_indices, torch.int32, "excl_indices")
+    check(L.b200_topk_rows(ptr(scores), n_q, n_items, ptr(excl_indptr), ptr(excl_indices), int(topk), ptr(ids),
+                           ptr(sc), current_stream()), "b200_topk_rows")
+    return ids, sc
+
+
+def delta_make(x, snapshot, delta):
+    L = require_cuda()
+    check(L.b200_delta_make(ptr(x), ptr(snapshot), ptr(delta), x.numel(), current_stream()), "b200_delta_make")
+
+
+def delta_apply(x, snapshot, delta):
+    L = require_cuda()
+    check(L.b200_delta_apply(ptr(x), ptr(snapshot), ptr(delta), x.numel(), current_stream()), "b200_delta_apply")
+
+
+def device_info():
+    import ctypes
+    L = require_cuda()
+    a, b, c = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    check(L.b200_device_info(ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)), "b200_device_info")
+    return dict(sm_count=a.value, cc=(b.value, c.value))

@@ -1,0 +1,157 @@
+/*
+ * b200cornac.h -- C ABI of libb200cornac.so: the B200 (sm_100a) implementation of
+ * Cornac's embedding train-and-rank hot path (BPR / MF SGD, per-user score + rank).
+ *
+ * The reference has no C ABI for this path: its kernels are Cython `def`/`cpdef`
+ * functions taking typed memoryviews (paths relative to the reference root):
+ *     BPR._fit_sgd             cornac/models/bpr/recom_bpr.pyx:208-269
+ *     RNGVector                cornac/models/bpr/recom_bpr.pyx:54-62 (+ recom_bpr.pxd:26-41)
+ *     backend_cpu.fit_sgd      cornac/models/mf/backend_cpu.pyx:35-97
+ *     fast_dot                 cornac/utils/fast_dot.pyx:40-43
+ *     Recommender.rank         cornac/models/recommender.py:476-530
+ * Each entry point below names the reference interface it replaces.  The Python
+ * plug-in classes in cornac_b200/ (same constructor arguments as the reference's
+ * BPR / MF) call these through ctypes; see INTEGRATION.md for the binding.
+ *
+ * Conventions
+ *  - plain C types only; every pointer documented "device" is a CUDA device pointer
+ *    (row-major, contiguous), every pointer documented "host" is ordinary host memory;
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *  - calls are asynchronous on `stream` unless stated otherwise and never allocate
+ *    device memory; scratch comes in through explicit workspace arguments;
+ *  - return value: 0 = ok, otherwise a B200_ERR_* code; b200_last_error() returns the
+ *    message of the calling thread's last failure;
+ *  - there is NO CPU fallback anywhere in this library.
+ */
+#ifndef B200CORNAC_H_
+#define B200CORNAC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_API __attribute__((visibility("default")))
+
+#define B200_OK 0
+#define B200_ERR_INVALID 1   /* bad argument (message says which) */
+#define B200_ERR_CUDA 2      /* a CUDA runtime call or kernel launch failed */
+#define B200_ERR_UNSUPPORTED 3
+
+/* flags for the SGD epochs */
+#define B200_SGD_ATOMIC 1u   /* scatter with red.global.add.f32 (no lost updates) instead of plain stores */
+#define B200_SGD_EXACT_EXP 2u /* z = 1/(1+exp(double)) like the reference instead of the fast f32 path */
+
+B200_API const char* b200_last_error(void);
+B200_API int b200_abi_version(void);
+/* multiProcessorCount / compute capability of the current device (host call). */
+B200_API int b200_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------
+ * BPR, throughput mode.  Replaces one call of BPR._fit_sgd (recom_bpr.pyx:208-269) run
+ * Hogwild over all cores: `n_samples` triplets, each drawing i_index uniformly from
+ * [0, nnz) and j uniformly from [0, n_neg) ON DEVICE (Philox4x32-10 keyed by `seed`,
+ * counter = (sample_base + s, epoch)), skipping (not redrawing) a sample when user u
+ * already has item j (has_non_zero, recom_bpr.pyx:46-51,241-243), otherwise applying the
+ * update of recom_bpr.pyx:249-267 to U[u], V[i], V[j], B[i], B[j].
+ *   indptr  device int32[n_users+1], indices device int32[nnz]  (train_set.matrix, sorted rows)
+ *   coo_row device int32[nnz]   = user_ids of BPR._prepare_data (recom_bpr.pyx:154-161)
+ *   U device f32[*, k], V device f32[*, k], B device f32[*]
+ *   stats   device int64[2]: {correct, skipped} are ADDED to it (caller zeroes)           */
+B200_API int b200_bpr_epoch(const int32_t* indptr, const int32_t* indices, const int32_t* coo_row,
+                            int64_t nnz, int64_t n_neg, int64_t n_samples,
+                            float* U, float* V, float* B, int k,
+                            float lr, float reg, int use_bias,
+                            uint64_t seed, uint64_t epoch, uint64_t sample_base,
+                            unsigned flags, int64_t* stats, void* stream);
+
+/* The sample law of b200_bpr_epoch, evaluated on the HOST (no CUDA): writes, for
+ * s = 0..n-1, the i_index and j_id that sample `sample_base + s` of `epoch` draws.  Lets a
+ * caller replay / audit the exact stream the throughput kernel consumed.
+ *   out_i_index host int64[n], out_j_id host int32[n]                                      */
+B200_API int b200_bpr_draw_host(uint64_t seed, uint64_t epoch, uint64_t sample_base, int64_t n,
+                                int64_t nnz, int64_t n_neg, int64_t* out_i_index, int32_t* out_j_id);
+
+/* BPR, parity mode.  Applies an explicit sample stream (i_index[s], j_id[s]),
+ * s = 0..n_samples-1, with the SAME RESULT AS APPLYING IT SEQUENTIALLY in stream order,
+ * i.e. the seeded single-thread reference (recom_bpr.pyx:132-133).  The stream normally
+ * comes from b200_mt_sampler_* below.
+ *   i_index device int64[n_samples], j_id device int32[n_samples]                          */
+B200_API int b200_bpr_epoch_replay(const int64_t* i_index, const int32_t* j_id, int64_t n_samples,
+                                   const int32_t* indptr, const int32_t* indices, const int32_t* coo_row,
+                                   float* U, float* V, float* B, int k,
+                                   float lr, float reg, int use_bias,
+                                   int64_t* stats, void* stream);
+
+/* Host-side restatement of RNGVector (recom_bpr.pyx:54-62): boost::random::mt19937 seeded
+ * with `seed` + boost::random::uniform_int_distribution<long>(0, hi).  Pure host code, no
+ * CUDA.  `fill` writes n consecutive draws from [0, hi] INCLUSIVE into host memory.        */
+typedef struct b200_mt_sampler b200_mt_sampler;
+B200_API b200_mt_sampler* b200_mt_sampler_create(uint32_t seed);
+B200_API void b200_mt_sampler_destroy(b200_mt_sampler* s);
+B200_API int b200_mt_sampler_fill_i64(b200_mt_sampler* s, int64_t hi, int64_t n, int64_t* out_host);
+B200_API int b200_mt_sampler_fill_i32(b200_mt_sampler* s, int64_t hi, int64_t n, int32_t* out_host);
+
+/* ------------------------------------------------------------------------------------
+ * MF.  Replaces one epoch of backend_cpu.fit_sgd (mf/backend_cpu.pyx:58-83).
+ *   rid, cid device int64[n] (the reference's INT64_t layout) or int32[n] when ids_are_i32
+ *   val device f32[n]; U f32[num_users,k]; V f32[num_items,k]; Bu, Bi f32
+ *   ordered = 1: ratings are applied with the same result as the stored-order sequential
+ *                loop (seeded reference); ordered = 0: Hogwild over the whole GPU.
+ *   loss device f32[1]: receives sum(err^2) of the epoch (caller multiplies by 0.5,
+ *                backend_cpu.pyx:85); it is overwritten, not accumulated.                   */
+B200_API int b200_mf_epoch(const void* rid, const void* cid, const float* val, int64_t n, int ids_are_i32,
+                           float* U, float* V, float* Bu, float* Bi, int k,
+                           float lr, float reg, float mu, int use_bias, int ordered,
+                           unsigned flags, float* loss, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Scores.  Replaces `out = base; fast_dot(U[u], V, out)` (fast_dot.pyx:40-43 as used by
+ * BPR.score recom_bpr.pyx:290-293 and MF.score mf/recom_mf.py:272-278) for a BATCH of
+ * query users:  out[q, i] = (item_base[i] + user_off[q]) + dot(U[user_idx[q]], V[i]).
+ * The dot is accumulated in f64 in index order and rounded once to f32 (the defined
+ * summation order shared with the oracle), so results are reproducible bit-for-bit.
+ *   user_idx device int64[n_q] (NULL = rows 0..n_q-1 of U); item_base, user_off may be NULL
+ *   out device f32[n_q, n_items]                                                            */
+B200_API int b200_score_batch(const float* U, const int64_t* user_idx, int64_t n_q,
+                              const float* V, int64_t n_items, int k,
+                              const float* item_base, const float* user_off,
+                              float* out, void* stream);
+
+/* Top-k of precomputed score rows.  Replaces the argpartition/argsort of
+ * Recommender.rank (recommender.py:521-528) with a TOTAL order (score desc, id asc).
+ *   scores device f32[n_q, n_items]; excl_indptr device int64[n_q+1] / excl_indices device
+ *   int32 (sorted per row) list item ids removed from row q's candidates (NULL = none);
+ *   out_ids device int32[n_q, topk] (-1 padded), out_scores device f32[n_q, topk].         */
+B200_API int b200_topk_rows(const float* scores, int64_t n_q, int64_t n_items,
+                            const int64_t* excl_indptr, const int32_t* excl_indices,
+                            int topk, int32_t* out_ids, float* out_scores, void* stream);
+
+/* Fused rank: scores (as b200_score_batch) + exclusion + top-k (as b200_topk_rows) for a
+ * batch of users without materialising the [n_q, n_items] score matrix.  Tensor-core
+ * (tcgen05) candidate pass + exact f64 re-score of the candidates; ids and scores are
+ * identical to b200_score_batch followed by b200_topk_rows.
+ *   workspace: device scratch of b200_rank_topk_workspace_bytes(...) bytes.                */
+B200_API int64_t b200_rank_topk_workspace_bytes(int64_t n_q, int64_t n_items, int k, int topk);
+B200_API int b200_rank_topk(const float* U, const int64_t* user_idx, int64_t n_q,
+                            const float* V, int64_t n_items, int k,
+                            const float* item_base, const float* user_off,
+                            const int64_t* excl_indptr, const int32_t* excl_indices,
+                            int topk, int32_t* out_ids, float* out_scores,
+                            void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Multi-GPU item-factor exchange (no reference counterpart: the reference is a single
+ * process).  Each rank trains its user shard against a replica of V / B; at the epoch
+ * boundary   b200_delta_make:  delta[i] = x[i] - snapshot[i]
+ * the caller all-reduces (sum) `delta` over NCCL, then
+ *            b200_delta_apply: x[i] = snapshot[i] + delta[i];  snapshot[i] = x[i]
+ * so every replica ends the epoch with x_start + sum over ranks of the local changes.     */
+B200_API int b200_delta_make(const float* x, const float* snapshot, float* delta, int64_t n, void* stream);
+B200_API int b200_delta_apply(float* x, float* snapshot, const float* delta, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200CORNAC_H_ */

