@@ -24,7 +24,9 @@ SIGNATURES = {
     "b200_last_error": (_c.c_char_p, []),
     "b200_abi_version": (_int, []),
     "b200_device_info": (_int, [_vp, _vp, _vp]),
-    "b200_bpr_epoch": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _int, _f32, _f32, _int,
+    "b200_bpr_table_slots": (_i64, [_i64]),
+    "b200_bpr_prepare": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _i64, _vp]),
+    "b200_bpr_epoch": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _int, _f32, _f32, _int,
                               _u64, _u64, _u64, _c.c_uint, _vp, _vp]),
     "b200_bpr_draw_host": (_int, [_u64, _u64, _u64, _i64, _i64, _i64, _vp, _vp]),
     "b200_bpr_epoch_replay": (_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _int, _f32, _f32, _int,

@@ -12,14 +12,34 @@
 //     at a time in parallel (read-only data), the updates are applied strictly in order.
 //
 // HBM-bound integer/gather work: no tensor cores here by design.
+#include <stdlib.h>
+
 #include "sgd_common.cuh"
 
 namespace b200 {
 
+// Interaction store of the throughput kernel (built once per fit by b200_bpr_prepare):
+//   pairs  int2[nnz]   (u, i) of every interaction: ONE 8-byte gather yields the user and the
+//                      positive item of a sampled interaction (instead of coo_row[] + indices[]);
+//   table  u64[slots]  open-addressing set of the keys (u << 32 | i), 4-slot (32-byte) buckets at
+//                      load <= 0.5: has_non_zero(u, j) is ONE 32-byte gather that can be issued
+//                      together with the factor rows, instead of a ~log2(deg)-deep dependent
+//                      binary search.  Costs 8 + ~21 bytes of HBM per interaction -- cheap on a
+//                      180 GB part, and it removes ~7 serialized memory round trips per sample.
+constexpr unsigned long long TABLE_EMPTY = ~0ull;
+
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t x)
+{
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL;
+    x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL;
+    x ^= x >> 33;
+    return x;
+}
+
 struct BprParams {
-    const int32_t* __restrict__ indptr;
-    const int32_t* __restrict__ indices;
-    const int32_t* __restrict__ coo_row;
+    const int2* __restrict__ pairs;
+    const unsigned long long* __restrict__ table;   // 4 slots (32 B) per bucket
+    uint64_t bucket_mask;
     int64_t nnz;
     int64_t n_neg;
     int64_t n_samples;
@@ -43,8 +63,17 @@ __device__ __forceinline__ float bpr_z(float score)
     return __frcp_rn(1.f + __expf(score));
 }
 
+// resident blocks per SM the register allocator is asked to make room for: the kernel is
+// latency-bound on dependent gathers, so samples in flight per SM (= groups x S) is the lever
+template <int NPL, bool VEC, int S>
+constexpr int hogwild_min_blocks()
+{
+    constexpr int E = NPL * (VEC ? 4 : 1);
+    return (E * S <= 4) ? 5 : (E * S <= 8) ? 4 : (E * S <= 16) ? 2 : 1;
+}
+
 template <int G, int NPL, bool VEC, bool ATOMIC, bool EXACT, int S>
-__global__ void __launch_bounds__(256) bpr_hogwild_kernel(const BprParams p)
+__global__ void __launch_bounds__(256, hogwild_min_blocks<NPL, VEC, S>()) bpr_hogwild_kernel(const BprParams p)
 {
     using Frag = RowFrag<NPL, VEC>;
     constexpr int E = NPL * Frag::W;
@@ -59,9 +88,12 @@ __global__ void __launch_bounds__(256) bpr_hogwild_kernel(const BprParams p)
 
     for (int64_t s0 = gid * S; s0 < p.n_samples; s0 += n_groups * S) {
         int32_t u[S], it[S], jt[S];
-        int64_t lo[S], hi[S];
         bool live[S];
-        // ---- phase A: draw the triplets (every lane of the group computes the same values)
+        Frag fu[S], fi[S], fj[S];
+        float bi[S], bj[S];
+        // ---- phase A: draw the triplets (every lane of the group computes the same values);
+        //      the negative row does not depend on the interaction gather, so it goes out first
+        int2 pr[S];
 #pragma unroll
         for (int t = 0; t < S; ++t) {
             const uint64_t s = p.sample_base + (uint64_t)(s0 + t);
@@ -69,26 +101,40 @@ __global__ void __launch_bounds__(256) bpr_hogwild_kernel(const BprParams p)
             Philox4 r = philox4x32_10((uint32_t)s, (uint32_t)(s >> 32), p.epoch_lo, p.epoch_hi, p.seed_lo, p.seed_hi);
             const int64_t ii = (int64_t)range64(r.x, r.y, (uint64_t)p.nnz);
             jt[t] = (int32_t)range64(r.z, r.w, (uint64_t)p.n_neg);
-            u[t] = __ldg(p.coo_row + ii);
-            it[t] = __ldg(p.indices + ii);
-        }
-        // ---- phase B: row bounds + all factor-row gathers in flight before the skip test resolves
-        Frag fu[S], fi[S], fj[S];
-        float bi[S], bj[S];
-#pragma unroll
-        for (int t = 0; t < S; ++t) {
-            lo[t] = __ldg(p.indptr + u[t]);
-            hi[t] = __ldg(p.indptr + u[t] + 1);
-            row_load<G, NPL, VEC>(fu[t], p.U + (size_t)u[t] * k, lg, n_units);
-            row_load<G, NPL, VEC>(fi[t], p.V + (size_t)it[t] * k, lg, n_units);
+            pr[t] = __ldg(p.pairs + ii);
             row_load<G, NPL, VEC>(fj[t], p.V + (size_t)jt[t] * k, lg, n_units);
-            bi[t] = __ldcg(p.B + it[t]);
             bj[t] = __ldcg(p.B + jt[t]);
         }
-        // ---- phase C: has_non_zero(u, j)  (recom_bpr.pyx:241-243)
+        // ---- phase B: user row, positive row and the membership bucket, all in flight together.
+        //      The 32-byte bucket is read by the first four lanes of the group, 8 bytes each.
+        unsigned long long slot[S];
+        uint64_t bkt[S];
 #pragma unroll
         for (int t = 0; t < S; ++t) {
-            if (live[t] && row_contains(p.indices, lo[t], hi[t], jt[t])) {
+            u[t] = pr[t].x;
+            it[t] = pr[t].y;
+            const uint64_t key = ((uint64_t)(uint32_t)u[t] << 32) | (uint32_t)jt[t];
+            bkt[t] = mix64(key) & p.bucket_mask;
+            slot[t] = (lg < 4) ? __ldg(p.table + 4 * bkt[t] + lg) : 0ull;
+            row_load<G, NPL, VEC>(fu[t], p.U + (size_t)u[t] * k, lg, n_units);
+            row_load<G, NPL, VEC>(fi[t], p.V + (size_t)it[t] * k, lg, n_units);
+            bi[t] = __ldcg(p.B + it[t]);
+        }
+        // ---- phase C: has_non_zero(u, j)  (recom_bpr.pyx:241-243) = key (u, j) in the table
+        const unsigned gmask = group_mask<G>();
+#pragma unroll
+        for (int t = 0; t < S; ++t) {
+            const uint64_t key = ((uint64_t)(uint32_t)u[t] << 32) | (uint32_t)jt[t];
+            unsigned hit = __ballot_sync(gmask, lg < 4 && slot[t] == key) & gmask;
+            unsigned full = __ballot_sync(gmask, lg == 3 && slot[t] != TABLE_EMPTY) & gmask;
+            uint64_t bb = bkt[t];
+            while (!hit && full) {            // rare: the bucket overflowed into the next one
+                bb = (bb + 1) & p.bucket_mask;
+                const unsigned long long sl = (lg < 4) ? __ldg(p.table + 4 * bb + lg) : 0ull;
+                hit = __ballot_sync(gmask, lg < 4 && sl == key) & gmask;
+                full = __ballot_sync(gmask, lg == 3 && sl != TABLE_EMPTY) & gmask;
+            }
+            if (live[t] && hit) {
                 live[t] = false;
                 ++n_skipped;
             }
@@ -233,17 +279,63 @@ __global__ void __launch_bounds__(32) bpr_replay_kernel(const ReplayParams p)
     }
 }
 
-template <int G, int NPL, bool VEC, bool ATOMIC, bool EXACT>
-static int launch_hogwild(const BprParams& p, cudaStream_t st)
+// ---------------------------------------------------------------------------------------
+// b200_bpr_prepare: CSR -> (pairs, membership table).  One thread per interaction.
+__global__ void bpr_prepare_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                   int64_t n_users, int64_t nnz, int2* __restrict__ pairs,
+                                   unsigned long long* __restrict__ table, uint64_t bucket_mask)
 {
-    // samples in flight per group: keep the register footprint of the 3*S row fragments moderate
-    constexpr int E = NPL * (VEC ? 4 : 1);
-    constexpr int S = (E <= 4) ? 2 : 1;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) {
+        // user of interaction e: last row with indptr[row] <= e  (COO row, recom_bpr.pyx:154-161)
+        int64_t lo = 0, hi = n_users;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if ((int64_t)__ldg(indptr + mid + 1) <= e) lo = mid + 1; else hi = mid;
+        }
+        const int32_t u = (int32_t)lo, i = __ldg(indices + e);
+        pairs[e] = make_int2(u, i);
+        const unsigned long long key = ((unsigned long long)(uint32_t)u << 32) | (uint32_t)i;
+        uint64_t b = mix64(key) & bucket_mask;
+        for (;;) {
+            bool done = false;
+            for (int sl = 0; sl < 4 && !done; ++sl) {
+                const unsigned long long old = atomicCAS(table + 4 * b + sl, TABLE_EMPTY, key);
+                done = (old == TABLE_EMPTY) || (old == key);
+            }
+            if (done) break;
+            b = (b + 1) & bucket_mask;
+        }
+    }
+}
+
+static int64_t table_buckets_for(int64_t nnz)
+{
+    int64_t b = 1;
+    while (b * 2 < nnz) b <<= 1;     // 4 slots per bucket => load factor in (0.25, 0.5]
+    return b;
+}
+
+struct HogwildTune {
+    int S, threads, blocks_per_sm;
+};
+static HogwildTune read_tune()
+{
+    HogwildTune t{0, 256, 0};
+    if (const char* e = getenv("B200_BPR_TUNE")) sscanf(e, "%d,%d,%d", &t.S, &t.threads, &t.blocks_per_sm);
+    if (t.threads != 64 && t.threads != 128 && t.threads != 256) t.threads = 256;
+    return t;
+}
+
+template <int G, int NPL, bool VEC, bool ATOMIC, bool EXACT, int S>
+static int launch_hogwild_s(const BprParams& p, cudaStream_t st, const HogwildTune& tune)
+{
     auto kern = bpr_hogwild_kernel<G, NPL, VEC, ATOMIC, EXACT, S>;
-    const int threads = 256;
+    const int threads = tune.threads;
     int occ = 0;
     B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, 0));
     if (occ < 1) occ = 1;
+    if (tune.blocks_per_sm > 0 && tune.blocks_per_sm < occ) occ = tune.blocks_per_sm;
     const int64_t groups_per_block = threads / G;
     int64_t want = (p.n_samples + groups_per_block * S - 1) / (groups_per_block * S);
     int64_t grid = (int64_t)sm_count() * occ;
@@ -253,21 +345,64 @@ static int launch_hogwild(const BprParams& p, cudaStream_t st)
     return B200_OK;
 }
 
+template <int G, int NPL, bool VEC, bool ATOMIC, bool EXACT>
+static int launch_hogwild(const BprParams& p, cudaStream_t st)
+{
+    // samples in flight per group: bounded by the register footprint of the 3*S row fragments
+    constexpr int E = NPL * (VEC ? 4 : 1);
+    const HogwildTune tune = read_tune();
+    if constexpr (E <= 4) {
+        const int S = tune.S ? tune.S : 2;
+        if (S == 1) return launch_hogwild_s<G, NPL, VEC, ATOMIC, EXACT, 1>(p, st, tune);
+        if (S == 4) return launch_hogwild_s<G, NPL, VEC, ATOMIC, EXACT, 4>(p, st, tune);
+        return launch_hogwild_s<G, NPL, VEC, ATOMIC, EXACT, 2>(p, st, tune);
+    } else {
+        return launch_hogwild_s<G, NPL, VEC, ATOMIC, EXACT, 1>(p, st, tune);
+    }
+}
+
 }  // namespace b200
 
 using namespace b200;
 
-extern "C" int b200_bpr_epoch(const int32_t* indptr, const int32_t* indices, const int32_t* coo_row,
+extern "C" int64_t b200_bpr_table_slots(int64_t nnz)
+{
+    return nnz <= 0 ? 4 : table_buckets_for(nnz) * 4;
+}
+
+extern "C" int b200_bpr_prepare(const int32_t* indptr, const int32_t* indices, int64_t n_users, int64_t nnz,
+                                int32_t* pairs, uint64_t* table, int64_t table_slots, void* stream)
+{
+    B200_REQUIRE(indptr && indices && pairs && table, "b200_bpr_prepare: null pointer argument");
+    B200_REQUIRE(n_users >= 0 && nnz >= 0, "b200_bpr_prepare: bad sizes");
+    B200_REQUIRE(table_slots == b200_bpr_table_slots(nnz), "b200_bpr_prepare: table_slots=%lld, expected %lld",
+                 (long long)table_slots, (long long)b200_bpr_table_slots(nnz));
+    B200_REQUIRE((((uintptr_t)pairs) & 7) == 0 && (((uintptr_t)table) & 31) == 0, "b200_bpr_prepare: pairs/table misaligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    B200_CUDA(cudaMemsetAsync(table, 0xff, (size_t)table_slots * sizeof(uint64_t), st));
+    if (nnz == 0) return B200_OK;
+    const uint64_t mask = (uint64_t)(table_slots / 4) - 1;
+    int64_t grid = (nnz + 255) / 256;
+    if (grid > (int64_t)sm_count() * 16) grid = (int64_t)sm_count() * 16;
+    bpr_prepare_kernel<<<(unsigned)grid, 256, 0, st>>>(indptr, indices, n_users, nnz, reinterpret_cast<int2*>(pairs),
+                                                       reinterpret_cast<unsigned long long*>(table), mask);
+    B200_CUDA(cudaGetLastError());
+    return B200_OK;
+}
+
+extern "C" int b200_bpr_epoch(const int32_t* pairs, const uint64_t* table, int64_t table_slots,
                               int64_t nnz, int64_t n_neg, int64_t n_samples,
                               float* U, float* V, float* B, int k,
                               float lr, float reg, int use_bias,
                               uint64_t seed, uint64_t epoch, uint64_t sample_base,
                               unsigned flags, int64_t* stats, void* stream)
 {
-    B200_REQUIRE(indptr && indices && coo_row && U && V && B && stats, "b200_bpr_epoch: null pointer argument");
+    B200_REQUIRE(pairs && table && U && V && B && stats, "b200_bpr_epoch: null pointer argument");
     B200_REQUIRE(k >= 1 && k <= 1024, "b200_bpr_epoch: k=%d out of range [1, 1024]", k);
     B200_REQUIRE(nnz >= 0 && n_neg >= 1 && n_samples >= 0, "b200_bpr_epoch: bad sizes nnz=%lld n_neg=%lld n_samples=%lld",
                  (long long)nnz, (long long)n_neg, (long long)n_samples);
+    B200_REQUIRE(table_slots == b200_bpr_table_slots(nnz), "b200_bpr_epoch: table_slots=%lld does not match nnz=%lld",
+                 (long long)table_slots, (long long)nnz);
     if (n_samples == 0 || nnz == 0) return B200_OK;
     const RowLayout L = pick_layout(k);
     B200_REQUIRE(L.npl <= 8, "b200_bpr_epoch: k=%d not supported (scalar rows are limited to k <= 256)", k);
@@ -275,7 +410,9 @@ extern "C" int b200_bpr_epoch(const int32_t* indptr, const int32_t* indices, con
         B200_REQUIRE((((uintptr_t)U | (uintptr_t)V) & 15) == 0, "b200_bpr_epoch: U/V must be 16-byte aligned");
     }
     BprParams p;
-    p.indptr = indptr; p.indices = indices; p.coo_row = coo_row;
+    p.pairs = reinterpret_cast<const int2*>(pairs);
+    p.table = reinterpret_cast<const unsigned long long*>(table);
+    p.bucket_mask = (uint64_t)(table_slots / 4) - 1;
     p.nnz = nnz; p.n_neg = n_neg; p.n_samples = n_samples;
     p.U = U; p.V = V; p.B = B; p.k = k; p.lr = lr; p.reg = reg; p.use_bias = use_bias;
     p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32);

@@ -38,22 +38,40 @@ def to_device(a, dtype=None, pinned=True):
 
 
 class BprData:
-    """Device copy of train_set.matrix in the layout the BPR kernels read:
-    CSR (indptr int32 [n_users+1], sorted indices int32 [nnz]) + the COO row array
-    (BPR._prepare_data, recom_bpr.pyx:154-161)."""
+    """Device copy of train_set.matrix: the CSR arrays (indptr int32 [n_users+1], sorted indices
+    int32 [nnz]) + the COO row array (BPR._prepare_data, recom_bpr.pyx:154-161) used by the
+    parity kernel, and -- built on first use by b200_bpr_prepare -- the (pairs, membership
+    table) store the throughput kernel gathers from."""
 
     def __init__(self, indptr, indices, coo_row=None):
         self.indptr = _dev(indptr, torch.int32, "indptr")
         self.indices = _dev(indices, torch.int32, "indices")
         self.n_users = self.indptr.numel() - 1
         self.nnz = self.indices.numel()
-        if coo_row is None:
+        self._coo_row = None if coo_row is None else _dev(coo_row, torch.int32, "coo_row")
+        if self._coo_row is not None and self._coo_row.numel() != self.nnz:
+            raise B200Error("coo_row length %d != nnz %d" % (self._coo_row.numel(), self.nnz))
+        self.pairs = self.table = None
+
+    @property
+    def coo_row(self):
+        if self._coo_row is None:
             counts = (self.indptr[1:] - self.indptr[:-1]).to(torch.int64)
-            coo_row = torch.repeat_interleave(
+            self._coo_row = torch.repeat_interleave(
                 torch.arange(self.n_users, device=self.indptr.device, dtype=torch.int32), counts)
-        self.coo_row = _dev(coo_row, torch.int32, "coo_row")
-        if self.coo_row.numel() != self.nnz:
-            raise B200Error("coo_row length %d != nnz %d" % (self.coo_row.numel(), self.nnz))
+        return self._coo_row
+
+    def prepare(self):
+        """Build pairs + membership table (idempotent)."""
+        if self.pairs is None:
+            L = require_cuda()
+            slots = int(L.b200_bpr_table_slots(self.nnz))
+            pairs = torch.empty((max(self.nnz, 1), 2), dtype=torch.int32, device=self.indptr.device)
+            table = torch.empty(slots, dtype=torch.int64, device=self.indptr.device)
+            check(L.b200_bpr_prepare(ptr(self.indptr), ptr(self.indices), self.n_users, self.nnz, ptr(pairs),
+                                     ptr(table), slots, current_stream()), "b200_bpr_prepare")
+            self.pairs, self.table = pairs, table
+        return self
 
     @classmethod
     def from_host(cls, indptr, indices):
@@ -72,7 +90,8 @@ def bpr_epoch(data, n_neg, U, V, B, lr, reg, use_bias, seed, epoch, stats, n_sam
     _dev(stats, torch.int64, "stats")
     flags = (_lib.SGD_ATOMIC if atomic else 0) | (_lib.SGD_EXACT_EXP if exact_exp else 0)
     n = data.nnz if n_samples is None else int(n_samples)
-    check(L.b200_bpr_epoch(ptr(data.indptr), ptr(data.indices), ptr(data.coo_row), data.nnz, int(n_neg), n,
+    data.prepare()
+    check(L.b200_bpr_epoch(ptr(data.pairs), ptr(data.table), data.table.numel(), data.nnz, int(n_neg), n,
                            ptr(U), ptr(V), ptr(B), int(k), float(lr), float(reg), int(bool(use_bias)),
                            int(seed) & (2 ** 64 - 1), int(epoch), int(sample_base), flags, ptr(stats),
                            current_stream()), "b200_bpr_epoch")

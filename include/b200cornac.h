@@ -49,17 +49,30 @@ B200_API int b200_abi_version(void);
 B200_API int b200_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
 /* ------------------------------------------------------------------------------------
- * BPR, throughput mode.  Replaces one call of BPR._fit_sgd (recom_bpr.pyx:208-269) run
- * Hogwild over all cores: `n_samples` triplets, each drawing i_index uniformly from
- * [0, nnz) and j uniformly from [0, n_neg) ON DEVICE (Philox4x32-10 keyed by `seed`,
- * counter = (sample_base + s, epoch)), skipping (not redrawing) a sample when user u
- * already has item j (has_non_zero, recom_bpr.pyx:46-51,241-243), otherwise applying the
- * update of recom_bpr.pyx:249-267 to U[u], V[i], V[j], B[i], B[j].
- *   indptr  device int32[n_users+1], indices device int32[nnz]  (train_set.matrix, sorted rows)
- *   coo_row device int32[nnz]   = user_ids of BPR._prepare_data (recom_bpr.pyx:154-161)
+ * BPR, throughput mode.
+ *
+ * b200_bpr_prepare: analogue of BPR._prepare_data (recom_bpr.pyx:154-161).  Turns the CSR
+ * training matrix into the two device structures the epoch kernel gathers from:
+ *   pairs  device int32[nnz, 2]  (user, item) of every stored interaction, CSR order
+ *                                (= the reference's user_ids[] and X.indices[] interleaved);
+ *   table  device uint64[table_slots], table_slots = b200_bpr_table_slots(nnz): an
+ *                                open-addressing hash set of (user << 32 | item) with 4-slot
+ *                                buckets, answering has_non_zero(u, j) (recom_bpr.pyx:46-51)
+ *                                with one 32-byte gather instead of a binary search.
+ *   indptr device int32[n_users+1], indices device int32[nnz] (train_set.matrix).           */
+B200_API int64_t b200_bpr_table_slots(int64_t nnz);
+B200_API int b200_bpr_prepare(const int32_t* indptr, const int32_t* indices, int64_t n_users, int64_t nnz,
+                              int32_t* pairs, uint64_t* table, int64_t table_slots, void* stream);
+
+/* b200_bpr_epoch replaces one call of BPR._fit_sgd (recom_bpr.pyx:208-269) run Hogwild
+ * over all cores: `n_samples` triplets, each drawing i_index uniformly from [0, nnz) and j
+ * uniformly from [0, n_neg) ON DEVICE (Philox4x32-10 keyed by `seed`, counter =
+ * (sample_base + s, epoch)), skipping (not redrawing) a sample when user u already has
+ * item j (recom_bpr.pyx:241-243), otherwise applying the update of recom_bpr.pyx:249-267
+ * to U[u], V[i], V[j], B[i], B[j].
  *   U device f32[*, k], V device f32[*, k], B device f32[*]
  *   stats   device int64[2]: {correct, skipped} are ADDED to it (caller zeroes)           */
-B200_API int b200_bpr_epoch(const int32_t* indptr, const int32_t* indices, const int32_t* coo_row,
+B200_API int b200_bpr_epoch(const int32_t* pairs, const uint64_t* table, int64_t table_slots,
                             int64_t nnz, int64_t n_neg, int64_t n_samples,
                             float* U, float* V, float* B, int k,
                             float lr, float reg, int use_bias,

@@ -33,6 +33,14 @@ def test_seeded_fit_matches_reference_golden(name):
     g_neg = engine.MTSampler(O.rngvector_seed(s_neg))
     data = _data(g["indptr"], g["indices"])
     assert np.array_equal(data.coo_row.cpu().numpy(), O.coo_rows(g["indptr"]))
+    # b200_bpr_prepare: pairs == (coo_row, indices) interleaved; every stored key is in the table
+    data.prepare()
+    pairs = data.pairs.cpu().numpy()
+    assert np.array_equal(pairs[:, 0], O.coo_rows(g["indptr"])) and np.array_equal(pairs[:, 1], g["indices"])
+    tbl = data.table.cpu().numpy().view(np.uint64)
+    keys = (pairs[:, 0].astype(np.uint64) << np.uint64(32)) | pairs[:, 1].astype(np.uint64)
+    stored = tbl[tbl != np.uint64(2 ** 64 - 1)]
+    assert len(stored) == len(keys) and np.array_equal(np.sort(stored), np.sort(keys))
     U, V, B = _dev(U0), _dev(V0), _dev(B0)
     stats = torch.zeros(2, dtype=torch.int64, device="cuda")
     ref = O.bpr_fit(g["indptr"], g["indices"], num_items, int(g["total_users"]), int(g["total_items"]), k,
@@ -93,6 +101,21 @@ def _conflict_free_prefix(ii, jj, coo, indices):
     return len(ii)
 
 
+def conflict_free_window(seed, epoch, nnz, n_items, coo, indices, want=48, tries=200):
+    """(sample_base, n): a window of the Philox stream with >= `want` pairwise-disjoint samples"""
+    from cornac_b200 import engine
+    best = (0, 0)
+    for w in range(tries):
+        base = w * 1000
+        ii, jj = engine.bpr_draw_host(seed, epoch, 200, nnz, n_items, sample_base=base)
+        n = _conflict_free_prefix(ii, jj, coo, indices)
+        if n > best[1]:
+            best = (base, n)
+        if n >= want:
+            break
+    return best
+
+
 @pytest.mark.parametrize("atomic", [False, True])
 @pytest.mark.parametrize("k", [4, 10, 16, 32, 64, 100, 128, 256, 512])
 def test_hogwild_equals_sequential_when_conflict_free(k, atomic):
@@ -105,9 +128,9 @@ def test_hogwild_equals_sequential_when_conflict_free(k, atomic):
     nnz = len(indices)
     coo = O.coo_rows(indptr)
     seed, epoch = 1234 + k, 7
-    ii, jj = engine.bpr_draw_host(seed, epoch, 400, nnz, n_items)
-    n = _conflict_free_prefix(ii, jj, coo, indices)
-    assert n >= 40, n
+    base, n = conflict_free_window(seed, epoch, nnz, n_items, coo, indices)
+    assert n >= 48, n
+    ii, jj = engine.bpr_draw_host(seed, epoch, n, nnz, n_items, sample_base=base)
     rng = np.random.RandomState(k)
     U0 = rng.normal(0, 0.3, (n_users, k)).astype(np.float32)
     V0 = rng.normal(0, 0.3, (n_items, k)).astype(np.float32)
@@ -117,8 +140,8 @@ def test_hogwild_equals_sequential_when_conflict_free(k, atomic):
     data = _data(indptr, indices)
     U, V, B = _dev(U0), _dev(V0), _dev(B0)
     stats = torch.zeros(2, dtype=torch.int64, device="cuda")
-    engine.bpr_epoch(data, n_items, U, V, B, 0.05, 0.02, True, seed, epoch, stats, n_samples=n, atomic=atomic,
-                     exact_exp=True)
+    engine.bpr_epoch(data, n_items, U, V, B, 0.05, 0.02, True, seed, epoch, stats, n_samples=n, sample_base=base,
+                     atomic=atomic, exact_exp=True)
     c, s = stats.cpu().tolist()
     assert (c, s) == (c_ref, s_ref)
     for got, want in ((U, Ur), (V, Vr), (B, Br)):

@@ -1,0 +1,52 @@
+"""Sweep launch shapes of the BPR throughput kernel on the bench workload (dev tool, GPU box).
+
+    python tools/tune_bpr.py [--k 64] [--scale 1.0]
+Prints one line per configuration: ms per epoch, G updates/s."""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+from cornac_b200 import engine  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--k", type=int, default=64)
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--uniform", type=int, default=0)
+    args = ap.parse_args()
+    W = dict(bench.WORKLOAD)
+    W["k"] = args.k
+    W["n_users"] = int(W["n_users"] * args.scale)
+    W["nnz"] = int(W["nnz"] * args.scale)
+    dev = torch.device("cuda", 0)
+    indptr, indices = bench.synth_interactions(W["n_users"], W["n_items"], W["nnz"], 1234, dev)
+    if args.uniform:
+        indices = torch.randint(0, W["n_items"], indices.shape, device=dev, dtype=torch.int32)   # law check only
+    data = engine.BprData(indptr, indices).prepare()
+    U, V, B = bench.init_factors(W["n_users"], W["n_items"], args.k, 99, dev)
+    stats = torch.zeros(2, dtype=torch.int64, device=dev)
+    configs = [("S=%d thr=%d blk=%d atomic=%d" % (S, thr, blk, at), "%d,%d,%d" % (S, thr, blk), at)
+               for at in (0, 1) for S in (1, 2, 4) for thr in (128, 256) for blk in (0,)]
+    configs += [("S=2 thr=256 blk=%d atomic=0" % b, "2,256,%d" % b, 0) for b in (1, 2, 3)]
+    for name, tune, at in configs:
+        os.environ["B200_BPR_TUNE"] = tune
+        for e in range(2):
+            engine.bpr_epoch(data, W["n_items"], U, V, B, W["lr"], W["reg"], True, 1, e, stats, atomic=bool(at))
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for e in range(3):
+            engine.bpr_epoch(data, W["n_items"], U, V, B, W["lr"], W["reg"], True, 1, 10 + e, stats, atomic=bool(at))
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        print("k=%d %-32s %8.2f ms  %6.3f G samples/s" % (args.k, name, ms, data.nnz / ms / 1e6), flush=True)
+
+
+if __name__ == "__main__":
+    main()
