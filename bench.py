@@ -215,7 +215,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debug only; result then INVALID)")
-    ap.add_argument("--atomic", type=int, default=0)
+    ap.add_argument("--atomic", type=int, default=1, help="1: red.global.add scatter (default), 0: plain racy stores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-rank", action="store_true")
@@ -317,7 +317,7 @@ def main():
             traffic = json.load(open(prof)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"kernel": "bpr_hogwild_kernel<G=16,NPL=1,VEC,S=2>", "bound": "hbm", "achieved": round(achieved, 1),
+    roofline = {"kernel": "bpr_hogwild_kernel<G=16,NPL=1,VEC,%s,S=1>" % ("ATOMIC" if args.atomic else "PLAIN"), "bound": "hbm", "achieved": round(achieved, 1),
                 "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_update": 24 * k + 32 + 4 * math.ceil(math.log2(mean_deg + 1)),
                 "kernel_ms": round(kern_ms, 3)}

@@ -26,7 +26,7 @@ SIGNATURES = {
     "b200_device_info": (_int, [_vp, _vp, _vp]),
     "b200_bpr_table_slots": (_i64, [_i64]),
     "b200_bpr_prepare": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _i64, _vp]),
-    "b200_bpr_epoch": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _int, _f32, _f32, _int,
+    "b200_bpr_epoch": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _int, _f32, _f32, _int,
                               _u64, _u64, _u64, _c.c_uint, _vp, _vp]),
     "b200_bpr_draw_host": (_int, [_u64, _u64, _u64, _i64, _i64, _i64, _vp, _vp]),
     "b200_bpr_epoch_replay": (_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _int, _f32, _f32, _int,
@@ -35,7 +35,7 @@ SIGNATURES = {
     "b200_mt_sampler_destroy": (None, [_vp]),
     "b200_mt_sampler_fill_i64": (_int, [_vp, _i64, _i64, _vp]),
     "b200_mt_sampler_fill_i32": (_int, [_vp, _i64, _i64, _vp]),
-    "b200_mf_epoch": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp, _vp, _vp, _int, _f32, _f32, _f32, _int, _int,
+    "b200_mf_epoch": (_int, [_vp, _vp, _vp, _i64, _int, _i64, _i64, _vp, _vp, _vp, _vp, _int, _f32, _f32, _f32, _int, _int,
                              _c.c_uint, _vp, _vp]),
     "b200_score_batch": (_int, [_vp, _vp, _i64, _vp, _i64, _int, _vp, _vp, _vp, _vp]),
     "b200_topk_rows": (_int, [_vp, _i64, _i64, _vp, _vp, _int, _vp, _vp, _vp]),
@@ -48,6 +48,7 @@ SIGNATURES = {
 
 SGD_ATOMIC = 1
 SGD_EXACT_EXP = 2
+SGD_UNBOUNDED = 4
 
 _lib = None
 

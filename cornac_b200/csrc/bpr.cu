@@ -43,6 +43,7 @@ struct BprParams {
     int64_t nnz;
     int64_t n_neg;
     int64_t n_samples;
+    int64_t max_groups;          // cap on concurrently running samples (Hogwild staleness bound)
     float* U;
     float* V;
     float* B;
@@ -72,8 +73,8 @@ constexpr int hogwild_min_blocks()
     return (E * S <= 4) ? 5 : (E * S <= 8) ? 4 : (E * S <= 16) ? 2 : 1;
 }
 
-template <int G, int NPL, bool VEC, bool ATOMIC, bool EXACT, int S>
-__global__ void __launch_bounds__(256, hogwild_min_blocks<NPL, VEC, S>()) bpr_hogwild_kernel(const BprParams p)
+template <int G, int NPL, bool VEC, bool ATOMIC, bool EXACT, int S, int MINB>
+__global__ void __launch_bounds__(256, MINB) bpr_hogwild_kernel(const BprParams p)
 {
     using Frag = RowFrag<NPL, VEC>;
     constexpr int E = NPL * Frag::W;
@@ -327,10 +328,10 @@ static HogwildTune read_tune()
     return t;
 }
 
-template <int G, int NPL, bool VEC, bool ATOMIC, bool EXACT, int S>
+template <int G, int NPL, bool VEC, bool ATOMIC, bool EXACT, int S, int MINB>
 static int launch_hogwild_s(const BprParams& p, cudaStream_t st, const HogwildTune& tune)
 {
-    auto kern = bpr_hogwild_kernel<G, NPL, VEC, ATOMIC, EXACT, S>;
+    auto kern = bpr_hogwild_kernel<G, NPL, VEC, ATOMIC, EXACT, S, MINB>;
     const int threads = tune.threads;
     int occ = 0;
     B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, 0));
@@ -339,7 +340,13 @@ static int launch_hogwild_s(const BprParams& p, cudaStream_t st, const HogwildTu
     const int64_t groups_per_block = threads / G;
     int64_t want = (p.n_samples + groups_per_block * S - 1) / (groups_per_block * S);
     int64_t grid = (int64_t)sm_count() * occ;
-    if (want < grid) grid = want < 1 ? 1 : want;
+    if (want < grid) grid = want;
+    // Hogwild staleness bound: never run more samples concurrently than a quarter of the rows
+    // of the smaller factor matrix (with fewer rows than in-flight samples every update would
+    // be computed from a stale row and the epoch degenerates into one huge-batch step)
+    const int64_t cap = (p.max_groups + groups_per_block * S - 1) / (groups_per_block * S);
+    if (cap < grid) grid = cap;
+    if (grid < 1) grid = 1;
     kern<<<(unsigned)grid, threads, 0, st>>>(p);
     B200_CUDA(cudaGetLastError());
     return B200_OK;
@@ -352,12 +359,11 @@ static int launch_hogwild(const BprParams& p, cudaStream_t st)
     constexpr int E = NPL * (VEC ? 4 : 1);
     const HogwildTune tune = read_tune();
     if constexpr (E <= 4) {
-        const int S = tune.S ? tune.S : 2;
-        if (S == 1) return launch_hogwild_s<G, NPL, VEC, ATOMIC, EXACT, 1>(p, st, tune);
-        if (S == 4) return launch_hogwild_s<G, NPL, VEC, ATOMIC, EXACT, 4>(p, st, tune);
-        return launch_hogwild_s<G, NPL, VEC, ATOMIC, EXACT, 2>(p, st, tune);
+        if (tune.S == 4) return launch_hogwild_s<G, NPL, VEC, ATOMIC, EXACT, 4, 2>(p, st, tune);
+        if (tune.S == 8) return launch_hogwild_s<G, NPL, VEC, ATOMIC, EXACT, 1, 8>(p, st, tune);   // S=1, <=32 regs
+        return launch_hogwild_s<G, NPL, VEC, ATOMIC, EXACT, 1, 5>(p, st, tune);
     } else {
-        return launch_hogwild_s<G, NPL, VEC, ATOMIC, EXACT, 1>(p, st, tune);
+        return launch_hogwild_s<G, NPL, VEC, ATOMIC, EXACT, 1, hogwild_min_blocks<NPL, VEC, 1>()>(p, st, tune);
     }
 }
 
@@ -391,7 +397,7 @@ extern "C" int b200_bpr_prepare(const int32_t* indptr, const int32_t* indices, i
 }
 
 extern "C" int b200_bpr_epoch(const int32_t* pairs, const uint64_t* table, int64_t table_slots,
-                              int64_t nnz, int64_t n_neg, int64_t n_samples,
+                              int64_t nnz, int64_t n_users, int64_t n_neg, int64_t n_samples,
                               float* U, float* V, float* B, int k,
                               float lr, float reg, int use_bias,
                               uint64_t seed, uint64_t epoch, uint64_t sample_base,
@@ -399,8 +405,8 @@ extern "C" int b200_bpr_epoch(const int32_t* pairs, const uint64_t* table, int64
 {
     B200_REQUIRE(pairs && table && U && V && B && stats, "b200_bpr_epoch: null pointer argument");
     B200_REQUIRE(k >= 1 && k <= 1024, "b200_bpr_epoch: k=%d out of range [1, 1024]", k);
-    B200_REQUIRE(nnz >= 0 && n_neg >= 1 && n_samples >= 0, "b200_bpr_epoch: bad sizes nnz=%lld n_neg=%lld n_samples=%lld",
-                 (long long)nnz, (long long)n_neg, (long long)n_samples);
+    B200_REQUIRE(nnz >= 0 && n_users >= 1 && n_neg >= 1 && n_samples >= 0, "b200_bpr_epoch: bad sizes nnz=%lld n_users=%lld n_neg=%lld n_samples=%lld",
+                 (long long)nnz, (long long)n_users, (long long)n_neg, (long long)n_samples);
     B200_REQUIRE(table_slots == b200_bpr_table_slots(nnz), "b200_bpr_epoch: table_slots=%lld does not match nnz=%lld",
                  (long long)table_slots, (long long)nnz);
     if (n_samples == 0 || nnz == 0) return B200_OK;
@@ -414,6 +420,11 @@ extern "C" int b200_bpr_epoch(const int32_t* pairs, const uint64_t* table, int64
     p.table = reinterpret_cast<const unsigned long long*>(table);
     p.bucket_mask = (uint64_t)(table_slots / 4) - 1;
     p.nnz = nnz; p.n_neg = n_neg; p.n_samples = n_samples;
+    {
+        int64_t rows = n_users < n_neg ? n_users : n_neg;
+        p.max_groups = rows / 4 < 16 ? 16 : rows / 4;
+        if (flags & B200_SGD_UNBOUNDED) p.max_groups = INT64_MAX / 1024;
+    }
     p.U = U; p.V = V; p.B = B; p.k = k; p.lr = lr; p.reg = reg; p.use_bias = use_bias;
     p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32);
     p.epoch_lo = (uint32_t)epoch; p.epoch_hi = (uint32_t)(epoch >> 32);

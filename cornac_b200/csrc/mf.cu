@@ -24,6 +24,7 @@ struct MfParams {
     float lr, reg, mu;
     int use_bias;
     float* loss;
+    int64_t max_groups;      // cap on concurrently running ratings (Hogwild staleness bound)
 };
 
 template <typename IdT, int G, int NPL, bool VEC, bool ATOMIC, int S>
@@ -168,7 +169,10 @@ static int launch_mf(const MfParams<IdT>& p, cudaStream_t st)
     const int64_t groups_per_block = threads / G;
     int64_t want = (p.n + groups_per_block * S - 1) / (groups_per_block * S);
     int64_t grid = (int64_t)sm_count() * occ;
-    if (want < grid) grid = want < 1 ? 1 : want;
+    if (want < grid) grid = want;
+    const int64_t cap = (p.max_groups + groups_per_block * S - 1) / (groups_per_block * S);
+    if (cap < grid) grid = cap;
+    if (grid < 1) grid = 1;
     kern<<<(unsigned)grid, threads, 0, st>>>(p);
     B200_CUDA(cudaGetLastError());
     return B200_OK;
@@ -176,7 +180,7 @@ static int launch_mf(const MfParams<IdT>& p, cudaStream_t st)
 
 template <typename IdT>
 static int mf_epoch_impl(const IdT* rid, const IdT* cid, const float* val, int64_t n,
-                         float* U, float* V, float* Bu, float* Bi, int k,
+                         int64_t n_users, int64_t n_items, float* U, float* V, float* Bu, float* Bi, int k,
                          float lr, float reg, float mu, int use_bias, int ordered,
                          unsigned flags, float* loss, cudaStream_t st)
 {
@@ -184,6 +188,11 @@ static int mf_epoch_impl(const IdT* rid, const IdT* cid, const float* val, int64
     p.rid = rid; p.cid = cid; p.val = val; p.n = n;
     p.U = U; p.V = V; p.Bu = Bu; p.Bi = Bi; p.k = k;
     p.lr = lr; p.reg = reg; p.mu = mu; p.use_bias = use_bias; p.loss = loss;
+    {
+        const int64_t rows = n_users < n_items ? n_users : n_items;
+        p.max_groups = rows / 4 < 16 ? 16 : rows / 4;
+        if (flags & B200_SGD_UNBOUNDED) p.max_groups = INT64_MAX / 1024;
+    }
     B200_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
     if (n == 0) return B200_OK;
     if (ordered) {
@@ -213,17 +222,18 @@ static int mf_epoch_impl(const IdT* rid, const IdT* cid, const float* val, int64
 using namespace b200;
 
 extern "C" int b200_mf_epoch(const void* rid, const void* cid, const float* val, int64_t n, int ids_are_i32,
-                             float* U, float* V, float* Bu, float* Bi, int k,
+                             int64_t n_users, int64_t n_items, float* U, float* V, float* Bu, float* Bi, int k,
                              float lr, float reg, float mu, int use_bias, int ordered,
                              unsigned flags, float* loss, void* stream)
 {
     B200_REQUIRE(U && V && Bu && Bi && loss, "b200_mf_epoch: null pointer argument");
     B200_REQUIRE(n >= 0 && (n == 0 || (rid && cid && val)), "b200_mf_epoch: bad rating arrays");
     B200_REQUIRE(k >= 1 && k <= 1024, "b200_mf_epoch: k=%d out of range [1, 1024]", k);
+    B200_REQUIRE(n_users >= 1 && n_items >= 1, "b200_mf_epoch: bad n_users/n_items");
     cudaStream_t st = (cudaStream_t)stream;
     if (ids_are_i32)
-        return mf_epoch_impl<int32_t>((const int32_t*)rid, (const int32_t*)cid, val, n, U, V, Bu, Bi, k, lr, reg, mu,
+        return mf_epoch_impl<int32_t>((const int32_t*)rid, (const int32_t*)cid, val, n, n_users, n_items, U, V, Bu, Bi, k, lr, reg, mu,
                                       use_bias, ordered, flags, loss, st);
-    return mf_epoch_impl<int64_t>((const int64_t*)rid, (const int64_t*)cid, val, n, U, V, Bu, Bi, k, lr, reg, mu,
+    return mf_epoch_impl<int64_t>((const int64_t*)rid, (const int64_t*)cid, val, n, n_users, n_items, U, V, Bu, Bi, k, lr, reg, mu,
                                   use_bias, ordered, flags, loss, st);
 }

@@ -81,17 +81,18 @@ class BprData:
 
 
 def bpr_epoch(data, n_neg, U, V, B, lr, reg, use_bias, seed, epoch, stats, n_samples=None,
-              sample_base=0, atomic=False, exact_exp=False):
+              sample_base=0, atomic=True, exact_exp=False, unbounded=False):
     """One Hogwild BPR epoch on the current stream; `stats` (int64[2] CUDA) accumulates
     (correct, skipped)."""
     L = require_cuda()
     k = U.shape[1]
     _dev(U, torch.float32, "U"), _dev(V, torch.float32, "V"), _dev(B, torch.float32, "B")
     _dev(stats, torch.int64, "stats")
-    flags = (_lib.SGD_ATOMIC if atomic else 0) | (_lib.SGD_EXACT_EXP if exact_exp else 0)
+    flags = ((_lib.SGD_ATOMIC if atomic else 0) | (_lib.SGD_EXACT_EXP if exact_exp else 0)
+             | (_lib.SGD_UNBOUNDED if unbounded else 0))
     n = data.nnz if n_samples is None else int(n_samples)
     data.prepare()
-    check(L.b200_bpr_epoch(ptr(data.pairs), ptr(data.table), data.table.numel(), data.nnz, int(n_neg), n,
+    check(L.b200_bpr_epoch(ptr(data.pairs), ptr(data.table), data.table.numel(), data.nnz, data.n_users, int(n_neg), n,
                            ptr(U), ptr(V), ptr(B), int(k), float(lr), float(reg), int(bool(use_bias)),
                            int(seed) & (2 ** 64 - 1), int(epoch), int(sample_base), flags, ptr(stats),
                            current_stream()), "b200_bpr_epoch")
@@ -119,7 +120,7 @@ def bpr_epoch_replay(data, i_index, j_id, U, V, B, lr, reg, use_bias, stats):
 
 
 def bpr_train_host(indptr, indices, n_neg, U, V, B, lr, reg, use_bias, max_iter, key=0, replay_seeds=None,
-                   atomic=False, on_epoch=None, keep_device=False):
+                   atomic=True, on_epoch=None, keep_device=False):
     """Host-buffer entry of BPR training (what BPR.fit calls): uploads the CSR matrix and the
     factors, runs `max_iter` epochs, writes the trained factors back INTO the given numpy
     arrays U, V, B (pinned staging both ways).
@@ -191,7 +192,7 @@ class MTSampler:
             self._h = None
 
 
-def mf_epoch(rid, cid, val, U, V, Bu, Bi, lr, reg, mu, use_bias, loss, ordered=False, atomic=False):
+def mf_epoch(rid, cid, val, U, V, Bu, Bi, lr, reg, mu, use_bias, loss, ordered=False, atomic=True, unbounded=False):
     """One MF epoch; `loss` (float32[1] CUDA) receives sum(err^2)."""
     L = require_cuda()
     if rid.dtype not in (torch.int32, torch.int64) or cid.dtype != rid.dtype:
@@ -200,8 +201,9 @@ def mf_epoch(rid, cid, val, U, V, Bu, Bi, lr, reg, mu, use_bias, loss, ordered=F
     for n_, t_ in (("U", U), ("V", V), ("Bu", Bu), ("Bi", Bi), ("loss", loss)):
         _dev(t_, torch.float32, n_)
     check(L.b200_mf_epoch(ptr(rid), ptr(cid), ptr(val), val.numel(), int(rid.dtype == torch.int32),
-                          ptr(U), ptr(V), ptr(Bu), ptr(Bi), int(U.shape[1]), float(lr), float(reg), float(mu),
-                          int(bool(use_bias)), int(bool(ordered)), _lib.SGD_ATOMIC if atomic else 0, ptr(loss),
+                          int(U.shape[0]), int(V.shape[0]), ptr(U), ptr(V), ptr(Bu), ptr(Bi), int(U.shape[1]), float(lr), float(reg), float(mu),
+                          int(bool(use_bias)), int(bool(ordered)),
+                          (_lib.SGD_ATOMIC if atomic else 0) | (_lib.SGD_UNBOUNDED if unbounded else 0), ptr(loss),
                           current_stream()), "b200_mf_epoch")
 
 

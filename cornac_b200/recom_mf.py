@@ -28,7 +28,7 @@ DTYPE = np.float32
 class MF(DeviceScoringMixin, Recommender, ANNMixin):
     def __init__(self, name="MF", k=10, backend="cpu", optimizer="sgd", max_iter=20, learning_rate=0.01,
                  batch_size=256, lambda_reg=0.02, dropout=0.0, use_bias=True, early_stop=False, num_threads=0,
-                 trainable=True, verbose=False, init_params=None, seed=None, mode="auto", atomic_updates=False):
+                 trainable=True, verbose=False, init_params=None, seed=None, mode="auto", atomic_updates=True):
         super().__init__(name=name, trainable=trainable, verbose=verbose)
         self.k = k
         self.backend = backend

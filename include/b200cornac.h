@@ -42,6 +42,7 @@ extern "C" {
 /* flags for the SGD epochs */
 #define B200_SGD_ATOMIC 1u   /* scatter with red.global.add.f32 (no lost updates) instead of plain stores */
 #define B200_SGD_EXACT_EXP 2u /* z = 1/(1+exp(double)) like the reference instead of the fast f32 path */
+#define B200_SGD_UNBOUNDED 4u /* do not cap the number of concurrently running samples (see b200_bpr_epoch) */
 
 B200_API const char* b200_last_error(void);
 B200_API int b200_abi_version(void);
@@ -69,11 +70,14 @@ B200_API int b200_bpr_prepare(const int32_t* indptr, const int32_t* indices, int
  * uniformly from [0, n_neg) ON DEVICE (Philox4x32-10 keyed by `seed`, counter =
  * (sample_base + s, epoch)), skipping (not redrawing) a sample when user u already has
  * item j (recom_bpr.pyx:241-243), otherwise applying the update of recom_bpr.pyx:249-267
- * to U[u], V[i], V[j], B[i], B[j].
+ * to U[u], V[i], V[j], B[i], B[j].  Updates are scattered with red.global.add (B200_SGD_ATOMIC,
+ * no lost updates; recommended and ~3x faster on B200) or plain stores (the reference's racy
+ * Hogwild).  At most min(n_users, n_neg)/4 samples run concurrently so that small matrices
+ * are not trained from hopelessly stale rows (B200_SGD_UNBOUNDED lifts the cap).
  *   U device f32[*, k], V device f32[*, k], B device f32[*]
  *   stats   device int64[2]: {correct, skipped} are ADDED to it (caller zeroes)           */
 B200_API int b200_bpr_epoch(const int32_t* pairs, const uint64_t* table, int64_t table_slots,
-                            int64_t nnz, int64_t n_neg, int64_t n_samples,
+                            int64_t nnz, int64_t n_users, int64_t n_neg, int64_t n_samples,
                             float* U, float* V, float* B, int k,
                             float lr, float reg, int use_bias,
                             uint64_t seed, uint64_t epoch, uint64_t sample_base,
@@ -109,13 +113,13 @@ B200_API int b200_mt_sampler_fill_i32(b200_mt_sampler* s, int64_t hi, int64_t n,
 /* ------------------------------------------------------------------------------------
  * MF.  Replaces one epoch of backend_cpu.fit_sgd (mf/backend_cpu.pyx:58-83).
  *   rid, cid device int64[n] (the reference's INT64_t layout) or int32[n] when ids_are_i32
- *   val device f32[n]; U f32[num_users,k]; V f32[num_items,k]; Bu, Bi f32
+ *   val device f32[n]; U f32[n_users,k]; V f32[n_items,k]; Bu f32[n_users], Bi f32[n_items]
  *   ordered = 1: ratings are applied with the same result as the stored-order sequential
  *                loop (seeded reference); ordered = 0: Hogwild over the whole GPU.
  *   loss device f32[1]: receives sum(err^2) of the epoch (caller multiplies by 0.5,
  *                backend_cpu.pyx:85); it is overwritten, not accumulated.                   */
 B200_API int b200_mf_epoch(const void* rid, const void* cid, const float* val, int64_t n, int ids_are_i32,
-                           float* U, float* V, float* Bu, float* Bi, int k,
+                           int64_t n_users, int64_t n_items, float* U, float* V, float* Bu, float* Bi, int k,
                            float lr, float reg, float mu, int use_bias, int ordered,
                            unsigned flags, float* loss, void* stream);
 

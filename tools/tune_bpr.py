@@ -31,8 +31,8 @@ def main():
     U, V, B = bench.init_factors(W["n_users"], W["n_items"], args.k, 99, dev)
     stats = torch.zeros(2, dtype=torch.int64, device=dev)
     configs = [("S=%d thr=%d blk=%d atomic=%d" % (S, thr, blk, at), "%d,%d,%d" % (S, thr, blk), at)
-               for at in (0, 1) for S in (1, 2, 4) for thr in (128, 256) for blk in (0,)]
-    configs += [("S=2 thr=256 blk=%d atomic=0" % b, "2,256,%d" % b, 0) for b in (1, 2, 3)]
+               for at in (1, 0) for S in (1, 4, 8) for thr in (128, 256) for blk in (0,)]
+    configs += [("S=1 thr=256 blk=%d atomic=1" % b, "1,256,%d" % b, 1) for b in (1, 2, 3, 4)]
     for name, tune, at in configs:
         os.environ["B200_BPR_TUNE"] = tune
         for e in range(2):
