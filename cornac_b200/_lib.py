@@ -42,6 +42,7 @@ SIGNATURES = {
     "b200_rank_topk_workspace_bytes": (_i64, [_i64, _i64, _int, _int]),
     "b200_rank_topk": (_int, [_vp, _vp, _i64, _vp, _i64, _int, _vp, _vp, _vp, _vp, _int, _vp, _vp,
                               _vp, _i64, _vp]),
+    "b200_rank_tc_debug_scores": (_int, [_vp, _i64, _vp, _i64, _int, _vp, _vp, _i64, _vp, _i64, _vp]),
     "b200_delta_make": (_int, [_vp, _vp, _vp, _i64, _vp]),
     "b200_delta_apply": (_int, [_vp, _vp, _vp, _i64, _vp]),
 }

@@ -1,0 +1,125 @@
+"""Tensor-core (tcgen05) rank path: the approximate pass against a bf16 matmul, and the fused
+b200_rank_topk against the oracle -- ids and scores bit-exact.  GPU only."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(a, dtype=None):
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    return (t if dtype is None else t.to(dtype)).cuda()
+
+
+def _rank_topk(U, V, base, uidx, uoff, excl, topk):
+    import torch
+    from cornac_b200._lib import check, current_stream, load, ptr
+    L = load()
+    n_q = len(uidx) if uidx is not None else U.shape[0]
+    n_items, k = V.shape
+    ids = torch.empty((n_q, topk), dtype=torch.int32, device="cuda")
+    sc = torch.empty((n_q, topk), dtype=torch.float32, device="cuda")
+    nbytes = int(L.b200_rank_topk_workspace_bytes(n_q, n_items, k, topk))
+    ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device="cuda")
+    dp = dx = None
+    if excl is not None:
+        ex_ptr = np.concatenate([[0], np.cumsum([len(e) for e in excl])]).astype(np.int64)
+        ex_idx = np.concatenate([np.sort(e) for e in excl]).astype(np.int32) if ex_ptr[-1] else np.zeros(1, np.int32)
+        dp, dx = _dev(ex_ptr), _dev(ex_idx)
+    keep = [_dev(U), _dev(V), None if base is None else _dev(base), None if uidx is None else _dev(uidx),
+            None if uoff is None else _dev(uoff)]
+    check(L.b200_rank_topk(ptr(keep[0]), ptr(keep[3]), n_q, ptr(keep[1]), n_items, k, ptr(keep[2]), ptr(keep[4]),
+                           ptr(dp), ptr(dx), topk, ptr(ids), ptr(sc), ptr(ws), nbytes, current_stream()), "b200_rank_topk")
+    torch.cuda.synchronize()
+    return ids.cpu().numpy(), sc.cpu().numpy()
+
+
+@pytest.mark.parametrize("k,n_items,n_q", [(16, 1024, 128), (64, 1500, 100), (128, 3000, 260), (100, 2048, 37), (8, 1100, 5)])
+def test_tensor_pass_matches_bf16_matmul(k, n_items, n_q):
+    """UMMA descriptors / packing / TMEM read-back: dense approximate scores == bf16 x bf16 -> f32."""
+    import torch
+    from cornac_b200._lib import check, current_stream, load, ptr
+    L = load()
+    assert L.b200_rank_topk_workspace_bytes(n_q, n_items, k, 10) > 0
+    rng = np.random.RandomState(k + n_items)
+    U = rng.normal(0, 0.5, (n_q, k)).astype(np.float32)
+    V = rng.normal(0, 0.5, (n_items, k)).astype(np.float32)
+    base = rng.normal(0, 0.5, n_items).astype(np.float32)
+    dU, dV, db = _dev(U), _dev(V), _dev(base)
+    rows, cols = (n_q + 127) // 128 * 128, (n_items + 255) // 256 * 256
+    out = torch.full((rows, cols), float("nan"), dtype=torch.float32, device="cuda")
+    nbytes = int(L.b200_rank_topk_workspace_bytes(n_q, n_items, k, 10))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    check(L.b200_rank_tc_debug_scores(ptr(dU), n_q, ptr(dV), n_items, k, ptr(db), ptr(out), out.numel(), ptr(ws), nbytes,
+                                      current_stream()), "b200_rank_tc_debug_scores")
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()[:n_q]
+    Ub = dU.bfloat16().double().cpu().numpy()
+    Vb = dV.bfloat16().double().cpu().numpy()
+    want = Ub @ Vb.T + base[None, :].astype(np.float64)
+    scale = np.abs(Ub) @ np.abs(Vb).T + np.abs(base)[None, :]
+    err = np.abs(got[:, :n_items] - want)
+    assert np.all(err <= 2e-6 * scale + 1e-6), float((err / (scale + 1e-9)).max())
+    assert np.all(np.isneginf(got[:, n_items:]))            # padding items carry -inf
+
+
+@pytest.mark.parametrize("k,n_items,n_q,topk", [(64, 20000, 300, 100), (128, 5000, 64, 100), (128, 100003, 130, 100),
+                                                (10, 1682, 40, 10), (100, 1024, 129, 256), (32, 4096, 1, 1)])
+def test_fused_rank_is_bit_exact(k, n_items, n_q, topk):
+    rng = np.random.RandomState(k + n_q)
+    U = rng.normal(0, 0.3, (1000, k)).astype(np.float32)
+    V = rng.normal(0, 0.3, (n_items, k)).astype(np.float32)
+    base = rng.normal(0, 0.3, n_items).astype(np.float32)
+    uidx = rng.randint(1000, size=n_q).astype(np.int64)
+    uoff = rng.normal(0, 0.3, n_q).astype(np.float32)
+    excl = [np.unique(rng.randint(n_items, size=rng.randint(0, 300))) for _ in range(n_q)]
+    ids, sc = _rank_topk(U, V, base, uidx, uoff, excl, topk)
+    want = O.score_batch(U[uidx], V, base, uoff)
+    for q in range(n_q):
+        wi, ws, w = O.topk(want[q], topk, excl[q])
+        assert np.array_equal(ids[q], wi), (q, ids[q][:8], wi[:8])
+        assert np.array_equal(sc[q][:w], ws[:w])
+
+
+def test_fused_rank_plain_rows_no_exclusion_no_bias():
+    rng = np.random.RandomState(3)
+    U = rng.normal(0, 1, (200, 64)).astype(np.float32)
+    V = rng.normal(0, 1, (7000, 64)).astype(np.float32)
+    ids, sc = _rank_topk(U, V, None, None, None, None, 50)
+    want = O.score_batch(U, V)
+    for q in range(200):
+        wi, ws, _ = O.topk(want[q], 50)
+        assert np.array_equal(ids[q], wi) and np.array_equal(sc[q], ws)
+
+
+def test_fused_rank_degenerate_rows_fall_back_to_exact():
+    """zero / tied rows overflow the candidate lists: those users are redone by the exact path"""
+    rng = np.random.RandomState(5)
+    U = rng.normal(0, 0.3, (140, 64)).astype(np.float32)
+    U[3] = 0.0                                              # every score == base
+    U[77] = 0.0
+    V = rng.normal(0, 0.3, (3000, 64)).astype(np.float32)
+    base = np.zeros(3000, np.float32)                       # => rows 3, 77: 3000-way tie
+    V[100:1200] = V[100]                                    # 1100 identical items: ties inside every row
+    ids, sc = _rank_topk(U, V, base, None, None, None, 100)
+    want = O.score_batch(U, V, base)
+    for q in range(140):
+        wi, ws, _ = O.topk(want[q], 100)
+        assert np.array_equal(ids[q], wi), q
+        assert np.array_equal(sc[q], ws)
+
+
+def test_tensor_path_and_exact_path_agree(monkeypatch):
+    rng = np.random.RandomState(9)
+    U = rng.normal(0, 0.3, (300, 128)).astype(np.float32)
+    V = rng.normal(0, 0.3, (9000, 128)).astype(np.float32)
+    base = rng.normal(0, 0.3, 9000).astype(np.float32)
+    a = _rank_topk(U, V, base, None, None, None, 100)
+    monkeypatch.setenv("B200_RANK_TC", "0")
+    b = _rank_topk(U, V, base, None, None, None, 100)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
