@@ -208,6 +208,141 @@ __global__ void __launch_bounds__(256, MINB) bpr_hogwild_kernel(const BprParams 
 }
 
 // ---------------------------------------------------------------------------------------
+// Chunked variant (the default): the per-sample bookkeeping that every lane of a group used
+// to compute redundantly (Philox, range reduction, pair gather, key hash, bucket probe) is done
+// ONCE PER LANE FOR G DIFFERENT SAMPLES -- lane l of a group resolves sample (chunk*G + l) --
+// so a group has G independent metadata gathers in flight at once and pays 1/G of those
+// instructions per sample.  The G resolved triplets are then broadcast one by one with warp
+// shuffles and applied by the whole group (row gathers of sample t+1 are issued before the
+// arithmetic of sample t).
+template <int G, int NPL, bool VEC, bool ATOMIC, bool EXACT, int MINB>
+__global__ void __launch_bounds__(256, MINB) bpr_hogwild_chunk_kernel(const BprParams p)
+{
+    using Frag = RowFrag<NPL, VEC>;
+    constexpr int E = NPL * Frag::W;
+    const int lane = threadIdx.x & 31;
+    const int lg = lane & (G - 1);
+    const int gbase = lane & ~(G - 1);
+    const unsigned gmask = group_mask<G>();
+    const int n_units = VEC ? p.k / 4 : p.k;
+    const int64_t groups_per_block = blockDim.x / G;
+    const int64_t n_groups = (int64_t)gridDim.x * groups_per_block;
+    const int64_t gid = (int64_t)blockIdx.x * groups_per_block + threadIdx.x / G;
+    const int64_t n_chunks = (p.n_samples + G - 1) / G;
+    const size_t k = (size_t)p.k;
+    const float lr = p.lr, reg = p.reg;
+
+    unsigned int n_correct = 0, n_skipped = 0;
+
+    for (int64_t c = gid; c < n_chunks; c += n_groups) {
+        // ---- phase 1: this lane's own sample
+        const int64_t sl = c * G + lg;
+        int mlive = sl < p.n_samples;
+        const uint64_t s = p.sample_base + (uint64_t)sl;
+        const Philox4 r = philox4x32_10((uint32_t)s, (uint32_t)(s >> 32), p.epoch_lo, p.epoch_hi, p.seed_lo, p.seed_hi);
+        const int64_t ii = (int64_t)range64(r.x, r.y, (uint64_t)p.nnz);
+        const int32_t mj = (int32_t)range64(r.z, r.w, (uint64_t)p.n_neg);
+        const int2 pr = __ldg(p.pairs + ii);
+        const int32_t mu = pr.x, mi = pr.y;
+        {
+            const uint64_t key = ((uint64_t)(uint32_t)mu << 32) | (uint32_t)mj;
+            uint64_t bb = mix64(key) & p.bucket_mask;
+            bool found, full;
+            do {
+                const ulonglong2 b0 = __ldg(reinterpret_cast<const ulonglong2*>(p.table + 4 * bb));
+                const ulonglong2 b1 = __ldg(reinterpret_cast<const ulonglong2*>(p.table + 4 * bb) + 1);
+                found = (b0.x == key) | (b0.y == key) | (b1.x == key) | (b1.y == key);
+                full = (b1.y != TABLE_EMPTY);
+                bb = (bb + 1) & p.bucket_mask;
+            } while (!found && full);              // rare: the bucket overflowed into the next one
+            if (mlive && found) { mlive = 0; ++n_skipped; }          // recom_bpr.pyx:241-243
+        }
+        // ---- phase 2: apply the G samples one after the other, one row-gather ahead
+        Frag fu[2], fi[2], fj[2];
+        float bi[2], bj[2];
+        int32_t cu[2], ci[2], cj[2];
+        int cl[2];
+        auto fetch = [&](int t, int slot) {
+            cu[slot] = __shfl_sync(gmask, mu, gbase + t);
+            ci[slot] = __shfl_sync(gmask, mi, gbase + t);
+            cj[slot] = __shfl_sync(gmask, mj, gbase + t);
+            cl[slot] = __shfl_sync(gmask, mlive, gbase + t);
+            if (cl[slot]) {
+                row_load<G, NPL, VEC>(fu[slot], p.U + (size_t)cu[slot] * k, lg, n_units);
+                row_load<G, NPL, VEC>(fi[slot], p.V + (size_t)ci[slot] * k, lg, n_units);
+                row_load<G, NPL, VEC>(fj[slot], p.V + (size_t)cj[slot] * k, lg, n_units);
+                bi[slot] = __ldcg(p.B + ci[slot]);
+                bj[slot] = __ldcg(p.B + cj[slot]);
+            }
+        };
+        fetch(0, 0);
+#pragma unroll
+        for (int t = 0; t < G; ++t) {
+            const int cur = t & 1, nxt = cur ^ 1;
+            if (t + 1 < G) fetch(t + 1, nxt);
+            if (!cl[cur]) continue;                 // group-uniform
+            float part = 0.f;
+#pragma unroll
+            for (int e = 0; e < E; ++e) part = fmaf(fu[cur].v[e], fi[cur].v[e] - fj[cur].v[e], part);
+            const float score = (bi[cur] - bj[cur]) + group_sum<G>(part);      // recom_bpr.pyx:249-251
+            const float z = bpr_z<EXACT>(score);
+            n_correct += (z < .5f);
+            float* pu = p.U + (size_t)cu[cur] * k;
+            float* pi = p.V + (size_t)ci[cur] * k;
+            float* pj = p.V + (size_t)cj[cur] * k;
+            if (ATOMIC) {
+                Frag du, di, dj;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const float uf = fu[cur].v[e], vi = fi[cur].v[e], vj = fj[cur].v[e];
+                    du.v[e] = lr * (z * (vi - vj) - reg * uf);
+                    di.v[e] = lr * (z * uf - reg * vi);
+                    dj.v[e] = lr * (-z * uf - reg * vj);
+                }
+                row_red_add<G, NPL, VEC>(du, pu, lg, n_units);
+                row_red_add<G, NPL, VEC>(di, pi, lg, n_units);
+                row_red_add<G, NPL, VEC>(dj, pj, lg, n_units);
+                if (p.use_bias && lg == 0) {
+                    red_add_f32(p.B + ci[cur], lr * (z - reg * bi[cur]));
+                    red_add_f32(p.B + cj[cur], lr * (-z - reg * bj[cur]));
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const float uf = fu[cur].v[e], vi = fi[cur].v[e], vj = fj[cur].v[e];
+                    fu[cur].v[e] = uf + lr * (z * (vi - vj) - reg * uf);
+                    fi[cur].v[e] = vi + lr * (z * uf - reg * vi);
+                    fj[cur].v[e] = vj + lr * (-z * uf - reg * vj);
+                }
+                row_store<G, NPL, VEC>(fu[cur], pu, lg, n_units);
+                row_store<G, NPL, VEC>(fi[cur], pi, lg, n_units);
+                row_store<G, NPL, VEC>(fj[cur], pj, lg, n_units);
+                if (p.use_bias && lg == 0) {
+                    __stcg(p.B + ci[cur], bi[cur] + lr * (z - reg * bi[cur]));
+                    __stcg(p.B + cj[cur], bj[cur] + lr * (-z - reg * bj[cur]));
+                }
+            }
+        }
+    }
+
+    __shared__ unsigned int sh_stats[2];
+    if (threadIdx.x < 2) sh_stats[threadIdx.x] = 0;
+    __syncthreads();
+    unsigned int cc = (lg == 0) ? n_correct : 0u, sk = n_skipped;     // skips were counted per lane
+    cc = __reduce_add_sync(0xffffffffu, cc);
+    sk = __reduce_add_sync(0xffffffffu, sk);
+    if (lane == 0) {
+        atomicAdd(&sh_stats[0], cc);
+        atomicAdd(&sh_stats[1], sk);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atomicAdd(p.stats + 0, (unsigned long long)sh_stats[0]);
+        atomicAdd(p.stats + 1, (unsigned long long)sh_stats[1]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Parity mode: one warp, serial-equivalent.  Unfused f32 arithmetic in the operation order
 // of recom_bpr.pyx:249-267 (the dot is a lane-strided partial sum + shuffle tree).
 struct ReplayParams {
@@ -352,12 +487,38 @@ static int launch_hogwild_s(const BprParams& p, cudaStream_t st, const HogwildTu
     return B200_OK;
 }
 
+template <int G, int NPL, bool VEC, bool ATOMIC, bool EXACT, int MINB>
+static int launch_hogwild_chunk(const BprParams& p, cudaStream_t st, const HogwildTune& tune)
+{
+    auto kern = bpr_hogwild_chunk_kernel<G, NPL, VEC, ATOMIC, EXACT, MINB>;
+    const int threads = tune.threads;
+    int occ = 0;
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, 0));
+    if (occ < 1) occ = 1;
+    if (tune.blocks_per_sm > 0 && tune.blocks_per_sm < occ) occ = tune.blocks_per_sm;
+    const int64_t groups_per_block = threads / G;
+    const int64_t n_chunks = (p.n_samples + G - 1) / G;
+    int64_t want = (n_chunks + groups_per_block - 1) / groups_per_block;
+    int64_t grid = (int64_t)sm_count() * occ;
+    if (want < grid) grid = want;
+    const int64_t cap = (p.max_groups + groups_per_block - 1) / groups_per_block;     // staleness bound
+    if (cap < grid) grid = cap;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, threads, 0, st>>>(p);
+    B200_CUDA(cudaGetLastError());
+    return B200_OK;
+}
+
 template <int G, int NPL, bool VEC, bool ATOMIC, bool EXACT>
 static int launch_hogwild(const BprParams& p, cudaStream_t st)
 {
     // samples in flight per group: bounded by the register footprint of the 3*S row fragments
     constexpr int E = NPL * (VEC ? 4 : 1);
     const HogwildTune tune = read_tune();
+    if constexpr (E <= 8) {
+        if (tune.S == 0) return launch_hogwild_chunk<G, NPL, VEC, ATOMIC, EXACT, 4>(p, st, tune);
+        if (tune.S == 16) return launch_hogwild_chunk<G, NPL, VEC, ATOMIC, EXACT, 3>(p, st, tune);
+    }
     if constexpr (E <= 4) {
         if (tune.S == 4) return launch_hogwild_s<G, NPL, VEC, ATOMIC, EXACT, 4, 2>(p, st, tune);
         if (tune.S == 8) return launch_hogwild_s<G, NPL, VEC, ATOMIC, EXACT, 1, 8>(p, st, tune);   // S=1, <=32 regs

@@ -30,9 +30,9 @@ def main():
     data = engine.BprData(indptr, indices).prepare()
     U, V, B = bench.init_factors(W["n_users"], W["n_items"], args.k, 99, dev)
     stats = torch.zeros(2, dtype=torch.int64, device=dev)
-    configs = [("S=%d thr=%d blk=%d atomic=%d" % (S, thr, blk, at), "%d,%d,%d" % (S, thr, blk), at)
-               for at in (1, 0) for S in (1, 4, 8) for thr in (128, 256) for blk in (0,)]
-    configs += [("S=1 thr=256 blk=%d atomic=1" % b, "1,256,%d" % b, 1) for b in (1, 2, 3, 4)]
+    configs = [("chunk minb4 thr=%d blk=%d" % (thr, blk), "0,%d,%d" % (thr, blk), 1) for thr in (256, 128) for blk in (0, 3, 2)]
+    configs += [("chunk minb3 thr=256", "16,256,0", 1), ("old S=1 thr=256 blk=4", "1,256,4", 1), ("old S=1 thr=128", "1,128,0", 1),
+                ("chunk minb4 plain-stores", "0,256,0", 0)]
     for name, tune, at in configs:
         os.environ["B200_BPR_TUNE"] = tune
         for e in range(2):
