@@ -404,7 +404,7 @@ def run_e2e(args, W, engine, indptr, indices, dev, world, rank):
     def one(e):
         hist, _ = engine.bpr_train_host(h_indptr.numpy(), h_indices.numpy(), W["n_items"], hU.numpy(), hV.numpy(),
                                         hB.numpy(), W["lr"], W["reg"], W["use_bias"], 1, key=77 + e + rank,
-                                        atomic=bool(args.atomic), on_epoch=lambda *a: None)
+                                        atomic=bool(args.atomic), on_epoch=lambda *a: None, replica_sync=world > 1)
         return hist[0]
 
     one(0)                                             # warm-up (allocator, pinned staging)
@@ -425,7 +425,8 @@ def run_e2e(args, W, engine, indptr, indices, dev, world, rank):
         dt, upd = tm[0].item(), ts[1].item()
     return {"value": round(upd / dt, 1), "unit": "updates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "steps": steps, "ms_per_step": round(dt / steps * 1e3, 2),
-            "path": "engine.bpr_train_host (the call BPR.fit makes): pinned host CSR + U/V/B -> H2D -> 1 epoch -> D2H U/V/B + stats"}
+            "path": "engine.bpr_train_host (the call BPR.fit makes): pinned host CSR + U/V/B -> H2D -> prepare -> 1 epoch"
+                    + (" -> item-delta all-reduce" if world > 1 else "") + " -> D2H U/V/B + stats"}
 
 
 def run_rank(W, engine, data, U, V, B, dev):

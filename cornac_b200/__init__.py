@@ -8,7 +8,7 @@ Layers:  include/b200cornac.h (C ABI)  <-  cornac_b200/csrc (CUDA)  <-  cornac_b
 plug-ins).  The plug-in classes need the `cornac` package importable (they subclass its
 Recommender so that cornac.Experiment accepts them); the engine does not.
 """
-__all__ = ["BPR", "MF", "engine", "B200Error"]
+__all__ = ["BPR", "WBPR", "MF", "engine", "B200Error"]
 
 from ._lib import B200Error  # noqa: F401
 
@@ -17,6 +17,9 @@ def __getattr__(name):
     if name == "BPR":
         from .recom_bpr import BPR
         return BPR
+    if name == "WBPR":
+        from .recom_bpr import WBPR
+        return WBPR
     if name == "MF":
         from .recom_mf import MF
         return MF

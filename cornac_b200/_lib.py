@@ -50,6 +50,7 @@ SIGNATURES = {
 SGD_ATOMIC = 1
 SGD_EXACT_EXP = 2
 SGD_UNBOUNDED = 4
+BPR_NEG_WEIGHTED = 8
 
 _lib = None
 

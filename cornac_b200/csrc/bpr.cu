@@ -44,6 +44,7 @@ struct BprParams {
     int64_t n_neg;
     int64_t n_samples;
     int64_t max_groups;          // cap on concurrently running samples (Hogwild staleness bound)
+    int neg_weighted;            // WBPR: negatives drawn from the interaction list (popularity-weighted)
     float* U;
     float* V;
     float* B;
@@ -101,7 +102,8 @@ __global__ void __launch_bounds__(256, MINB) bpr_hogwild_kernel(const BprParams 
             live[t] = (s0 + t) < p.n_samples;
             Philox4 r = philox4x32_10((uint32_t)s, (uint32_t)(s >> 32), p.epoch_lo, p.epoch_hi, p.seed_lo, p.seed_hi);
             const int64_t ii = (int64_t)range64(r.x, r.y, (uint64_t)p.nnz);
-            jt[t] = (int32_t)range64(r.z, r.w, (uint64_t)p.n_neg);
+            jt[t] = p.neg_weighted ? __ldg(p.pairs + range64(r.z, r.w, (uint64_t)p.nnz)).y
+                                   : (int32_t)range64(r.z, r.w, (uint64_t)p.n_neg);
             pr[t] = __ldg(p.pairs + ii);
             row_load<G, NPL, VEC>(fj[t], p.V + (size_t)jt[t] * k, lg, n_units);
             bj[t] = __ldcg(p.B + jt[t]);
@@ -241,7 +243,8 @@ __global__ void __launch_bounds__(256, MINB) bpr_hogwild_chunk_kernel(const BprP
         const uint64_t s = p.sample_base + (uint64_t)sl;
         const Philox4 r = philox4x32_10((uint32_t)s, (uint32_t)(s >> 32), p.epoch_lo, p.epoch_hi, p.seed_lo, p.seed_hi);
         const int64_t ii = (int64_t)range64(r.x, r.y, (uint64_t)p.nnz);
-        const int32_t mj = (int32_t)range64(r.z, r.w, (uint64_t)p.n_neg);
+        const int32_t mj = p.neg_weighted ? __ldg(p.pairs + range64(r.z, r.w, (uint64_t)p.nnz)).y     // recom_wbpr.pyx:131
+                                          : (int32_t)range64(r.z, r.w, (uint64_t)p.n_neg);
         const int2 pr = __ldg(p.pairs + ii);
         const int32_t mu = pr.x, mi = pr.y;
         {
@@ -586,6 +589,7 @@ extern "C" int b200_bpr_epoch(const int32_t* pairs, const uint64_t* table, int64
         p.max_groups = rows / 4 < 16 ? 16 : rows / 4;
         if (flags & B200_SGD_UNBOUNDED) p.max_groups = INT64_MAX / 1024;
     }
+    p.neg_weighted = (flags & B200_BPR_NEG_WEIGHTED) ? 1 : 0;
     p.U = U; p.V = V; p.B = B; p.k = k; p.lr = lr; p.reg = reg; p.use_bias = use_bias;
     p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32);
     p.epoch_lo = (uint32_t)epoch; p.epoch_hi = (uint32_t)(epoch >> 32);

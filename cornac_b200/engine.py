@@ -81,7 +81,7 @@ class BprData:
 
 
 def bpr_epoch(data, n_neg, U, V, B, lr, reg, use_bias, seed, epoch, stats, n_samples=None,
-              sample_base=0, atomic=True, exact_exp=False, unbounded=False):
+              sample_base=0, atomic=True, exact_exp=False, unbounded=False, neg_weighted=False):
     """One Hogwild BPR epoch on the current stream; `stats` (int64[2] CUDA) accumulates
     (correct, skipped)."""
     L = require_cuda()
@@ -89,7 +89,7 @@ def bpr_epoch(data, n_neg, U, V, B, lr, reg, use_bias, seed, epoch, stats, n_sam
     _dev(U, torch.float32, "U"), _dev(V, torch.float32, "V"), _dev(B, torch.float32, "B")
     _dev(stats, torch.int64, "stats")
     flags = ((_lib.SGD_ATOMIC if atomic else 0) | (_lib.SGD_EXACT_EXP if exact_exp else 0)
-             | (_lib.SGD_UNBOUNDED if unbounded else 0))
+             | (_lib.SGD_UNBOUNDED if unbounded else 0) | (_lib.BPR_NEG_WEIGHTED if neg_weighted else 0))
     n = data.nnz if n_samples is None else int(n_samples)
     data.prepare()
     check(L.b200_bpr_epoch(ptr(data.pairs), ptr(data.table), data.table.numel(), data.nnz, data.n_users, int(n_neg), n,
@@ -120,7 +120,8 @@ def bpr_epoch_replay(data, i_index, j_id, U, V, B, lr, reg, use_bias, stats):
 
 
 def bpr_train_host(indptr, indices, n_neg, U, V, B, lr, reg, use_bias, max_iter, key=0, replay_seeds=None,
-                   atomic=True, on_epoch=None, keep_device=False):
+                   atomic=True, on_epoch=None, keep_device=False, replica_sync=False, weighted_seed=None,
+                   neg_weighted=False):
     """Host-buffer entry of BPR training (what BPR.fit calls): uploads the CSR matrix and the
     factors, runs `max_iter` epochs, writes the trained factors back INTO the given numpy
     arrays U, V, B (pinned staging both ways).
@@ -128,6 +129,9 @@ def bpr_train_host(indptr, indices, n_neg, U, V, B, lr, reg, use_bias, max_iter,
     replay_seeds = (seed_pos, seed_neg): deterministic mode -- per epoch the two mt19937 streams
     of the reference's RNGVector are drawn on the host and applied by the serial-equivalent
     replay kernel.  Otherwise Hogwild epochs with the on-device Philox sampler keyed by `key`.
+    replica_sync=True (multi-GPU, one process per GPU, torch.distributed initialised): `indptr/indices/U`
+    are this rank's USER SHARD, V/B are replicas; after every epoch the ranks exchange their item-side
+    changes (parallel.ItemReplicaSync: make-delta -> NCCL all-reduce -> apply).
     Returns (per-epoch (correct, skipped) list or [], device tensors (U, V, B) if keep_device)."""
     require_cuda()
     data = BprData.from_host(indptr, indices)
@@ -136,7 +140,29 @@ def bpr_train_host(indptr, indices, n_neg, U, V, B, lr, reg, use_bias, max_iter,
     stats = torch.zeros(2, dtype=torch.int64, device="cuda")
     lr, reg = float(np.float32(lr)), float(np.float32(reg))
     history = []
-    if replay_seeds is not None:
+    sync = None
+    if replica_sync:
+        from .parallel import ItemReplicaSync
+        sync = ItemReplicaSync([dV, dB])
+    if weighted_seed is not None:
+        # WBPR, deterministic: ONE mt19937 stream, each sample takes (pos draw, neg draw) from it and
+        # the negative is the item of the drawn interaction (recom_wbpr.pyx:125-136)
+        g = MTSampler(weighted_seed)
+        h_ij = np.empty(2 * nnz, dtype=np.int64)
+        h_i = torch.empty(nnz, dtype=torch.int64).pin_memory()
+        h_j = torch.empty(nnz, dtype=torch.int32).pin_memory()
+        host_indices = np.asarray(indices)
+        for epoch in range(max_iter):
+            g.fill(nnz - 1, 2 * nnz, out=h_ij)
+            h_i.numpy()[:] = h_ij[0::2]
+            h_j.numpy()[:] = host_indices[h_ij[1::2]]
+            d_i, d_j = h_i.cuda(non_blocking=True), h_j.cuda(non_blocking=True)
+            stats.zero_()
+            bpr_epoch_replay(data, d_i, d_j, dU, dV, dB, lr, reg, use_bias, stats)
+            history.append(tuple(stats.cpu().tolist()))
+            if on_epoch:
+                on_epoch(epoch, *history[-1])
+    elif replay_seeds is not None:
         g_pos, g_neg = MTSampler(replay_seeds[0]), MTSampler(replay_seeds[1])
         h_i = torch.empty(nnz, dtype=torch.int64).pin_memory()
         h_j = torch.empty(nnz, dtype=torch.int32).pin_memory()
@@ -152,7 +178,10 @@ def bpr_train_host(indptr, indices, n_neg, U, V, B, lr, reg, use_bias, max_iter,
     else:
         for epoch in range(max_iter):
             stats.zero_()
-            bpr_epoch(data, n_neg, dU, dV, dB, lr, reg, use_bias, key, epoch, stats, atomic=atomic)
+            bpr_epoch(data, n_neg, dU, dV, dB, lr, reg, use_bias, key, epoch, stats, atomic=atomic,
+                      neg_weighted=neg_weighted)
+            if sync is not None:
+                sync.exchange()
             if on_epoch:
                 history.append(tuple(stats.cpu().tolist()))
                 on_epoch(epoch, *history[-1])

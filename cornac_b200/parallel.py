@@ -73,3 +73,25 @@ class ItemReplicaSync:
                 dist.all_reduce(d, op=dist.ReduceOp.SUM, group=self.group)
         for t, s, d in zip(self.tensors, self.snapshots, self.deltas):
             self.ops.apply(t, s, d)
+
+
+def bpr_fit_sharded(indptr, indices, n_items, U, V, B, lr, reg, use_bias, max_iter, key=0, atomic=True):
+    """Multi-GPU BPR training of ONE model: call from every rank (one process per GPU, process
+    group initialised, torch.cuda.set_device done) with the FULL host CSR matrix and factor arrays.
+
+    Rank r trains users [bounds[r], bounds[r+1]) (equal interaction counts) against its replica of
+    V / B; item-side changes are all-reduced once per epoch.  On return every rank's V and B hold
+    the shared result and U[bounds[r]:bounds[r+1]] holds this rank's trained rows (other rows of U
+    are untouched on this rank; gather them with torch.distributed if one process needs all)."""
+    import torch.distributed as dist
+    from . import engine
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    bounds = shard_users_by_nnz(indptr, world)
+    ip, ix = shard_csr(indptr, indices, bounds, rank)
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    U_shard = U[lo:hi]                      # a view: trained in place
+    hist, _ = engine.bpr_train_host(ip, ix, n_items, U_shard, V, B, lr, reg, use_bias, max_iter,
+                                    key=(int(key) << 8) + rank, atomic=atomic, replica_sync=world > 1,
+                                    on_epoch=lambda *a: None)
+    return bounds, hist

@@ -147,3 +147,39 @@ def _copy_back(host, dev):
         np.copyto(host, out)
         return host
     return out
+
+
+class WBPR(BPR):
+    """Weighted BPR (negatives sampled in proportion to item popularity): drop-in for
+    cornac.models.WBPR (cornac/models/bpr/recom_wbpr.pyx:30-142).  Same kernels as BPR with the
+    sampler switched: j = item of a uniformly drawn interaction, one shared RNG stream."""
+
+    def __init__(self, name="WBPR", k=10, max_iter=100, learning_rate=0.001, lambda_reg=0.01, use_bias=True,
+                 num_threads=0, trainable=True, verbose=False, init_params=None, seed=None, mode="auto",
+                 atomic_updates=True):
+        super().__init__(name=name, k=k, max_iter=max_iter, learning_rate=learning_rate, lambda_reg=lambda_reg,
+                         use_bias=use_bias, num_threads=num_threads, trainable=trainable, verbose=verbose,
+                         init_params=init_params, seed=seed, mode=mode, atomic_updates=atomic_updates)
+
+    def fit(self, train_set, val_set=None):
+        Recommender.fit(self, train_set, val_set)
+        self._init()
+        self._b200_invalidate()
+        if not self.trainable:
+            return self
+        engine.require_cuda()
+        X = train_set.matrix
+        if X.nnz == 0 or self.max_iter <= 0:
+            return self
+        replay = (self.seed is not None) if self.mode == "auto" else (self.mode == "replay")
+        s_vec = self.rng.randint(2 ** 31)                                   # recom_wbpr.pyx:128
+        self.u_factors = _writable_f32(self.u_factors)
+        self.i_factors = _writable_f32(self.i_factors)
+        self.i_biases = _writable_f32(self.i_biases)
+        self.epoch_stats, dev = engine.bpr_train_host(
+            X.indptr, X.indices, train_set.num_items, self.u_factors, self.i_factors, self.i_biases,
+            self.learning_rate, self.lambda_reg, self.use_bias, self.max_iter, key=int(s_vec),
+            weighted_seed=get_rng(s_vec).randint(2 ** 31) if replay else None, neg_weighted=True,
+            atomic=self.atomic_updates, on_epoch=(lambda *a: None) if replay else None, keep_device=True)
+        self._b200_adopt_device(dev[0], dev[1], dev[2], None, self.total_items)
+        return self

@@ -42,6 +42,7 @@ extern "C" {
 /* flags for the SGD epochs */
 #define B200_SGD_ATOMIC 1u   /* scatter with red.global.add.f32 (no lost updates) instead of plain stores */
 #define B200_SGD_EXACT_EXP 2u /* z = 1/(1+exp(double)) like the reference instead of the fast f32 path */
+#define B200_BPR_NEG_WEIGHTED 8u /* WBPR (recom_wbpr.pyx:125-136): j = item of a uniformly drawn INTERACTION */
 #define B200_SGD_UNBOUNDED 4u /* do not cap the number of concurrently running samples (see b200_bpr_epoch) */
 
 B200_API const char* b200_last_error(void);

@@ -191,6 +191,31 @@ ORA_API void ora_bpr_fit_sgd(ora_mt19937 *rng_pos, ora_mt19937 *rng_neg,
     *skipped = sk;
 }
 
+/* WBPR epoch (cornac/models/bpr/recom_wbpr.pyx:125-136): the same _fit_sgd loop called with
+ * rng_neg = rng_pos (ONE shared mt19937, so each sample consumes "pos draw, then neg draw" from
+ * the same stream) and neg_item_ids = X.indices, i.e. negatives are drawn in proportion to
+ * item popularity: j_id = item_ids[j_index], j_index uniform over [0, nnz-1].              */
+ORA_API void ora_wbpr_fit_sgd(ora_mt19937 *rng, int64_t nnz,
+                              const int32_t *user_ids, const int32_t *item_ids, const int32_t *indptr,
+                              float *U, float *V, float *B, int k,
+                              float lr, float reg, int use_bias,
+                              int64_t *correct, int64_t *skipped,
+                              int64_t *trace_i, int32_t *trace_j)
+{
+    int64_t c = 0, sk = 0;
+    for (int64_t s = 0; s < nnz; ++s) {
+        int64_t i_index = (int64_t)ora_boost_uniform_u64(rng, (uint64_t)(nnz - 1));
+        int64_t j_index = (int64_t)ora_boost_uniform_u64(rng, (uint64_t)(nnz - 1));
+        int32_t j_id = item_ids[j_index];
+        if (trace_i) trace_i[s] = i_index;
+        if (trace_j) trace_j[s] = j_id;
+        sk += ora_bpr_one(indptr, item_ids, user_ids[i_index], item_ids[i_index], j_id, U, V, B, k,
+                          lr, reg, use_bias, &c);
+    }
+    *correct = c;
+    *skipped = sk;
+}
+
 /* Same loop body driven by an explicit (i_index, j_id) stream, sequentially.
  * Used to check the GPU replay kernel on arbitrary streams.                   */
 ORA_API void ora_bpr_replay(const int64_t *i_index, const int32_t *j_ids, int64_t n,

@@ -265,3 +265,25 @@ def test_bad_arguments_are_reported():
         engine.bpr_epoch(data, 10, U, U, U[:, 0].contiguous(), 0.1, 0.1, True, 1, 0, stats)
     with pytest.raises(B200Error, match="contiguous CUDA tensor"):
         engine.bpr_epoch(data, 10, U.cpu(), U, U[:, 0].contiguous(), 0.1, 0.1, True, 1, 0, stats)
+
+
+def test_hogwild_weighted_negatives_follow_item_popularity():
+    """B200_BPR_NEG_WEIGHTED: with lr=0 the skip count must equal the oracle's count on the stream whose
+    negatives are items of uniformly drawn interactions (b200_bpr_draw_host with n_neg = nnz)."""
+    import torch
+    from cornac_b200 import engine
+    indptr, indices = synth_csr(5000, 400, 60000, seed=12, zipf=1.0)
+    nnz, k = len(indices), 16
+    rng = np.random.RandomState(0)
+    U0 = rng.normal(0, 0.3, (5000, k)).astype(np.float32)
+    V0 = rng.normal(0, 0.3, (400, k)).astype(np.float32)
+    B0 = np.zeros(400, np.float32)
+    data = _data(indptr, indices)
+    U, V, B = _dev(U0), _dev(V0), _dev(B0)
+    stats = torch.zeros(2, dtype=torch.int64, device="cuda")
+    n = 300001
+    engine.bpr_epoch(data, 400, U, V, B, 0.0, 0.01, True, 21, 0, stats, n_samples=n, neg_weighted=True, exact_exp=True)
+    ii, jidx = engine.bpr_draw_host(21, 0, n, nnz, nnz)
+    c_ref, s_ref = O.bpr_replay(ii, indices[jidx], indptr, indices, U0.copy(), V0.copy(), B0.copy(), 0.0, 0.01, True)
+    c, s = stats.cpu().tolist()
+    assert s == s_ref and s > 0.02 * n and abs(c - c_ref) <= 5        # popular negatives are skipped far more often

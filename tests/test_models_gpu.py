@@ -178,3 +178,15 @@ def test_hogwild_plugin_quality_close_to_reference_multithread():
     a = ranking_eval(ours, [AUC()], train_set, test_set)[0][0]
     b = ranking_eval(ref, [AUC()], train_set, test_set)[0][0]
     assert a > 0.9 and b > 0.9 and abs(a - b) < 0.03, (a, b)
+
+
+def test_wbpr_plugin_reproduces_seeded_reference_and_trains_hogwild():
+    """row (f)1 of SURVEY 8: WBPR = the BPR kernels with popularity-weighted negatives from ONE RNG stream"""
+    from cornac_b200 import WBPR
+    g = golden("wbpr_mid_k16")
+    ds = _dataset_from_csr(g)
+    m = WBPR(k=16, max_iter=10, learning_rate=0.05, lambda_reg=0.01, seed=11).fit(ds)
+    assert rel_err(m.u_factors, g["U"]) < TOL and rel_err(m.i_factors, g["V"]) < TOL and rel_err(m.i_biases, g["B"]) < TOL
+    h = WBPR(k=16, max_iter=10, learning_rate=0.05, lambda_reg=0.01).fit(ds)          # Hogwild, device sampler
+    assert np.isfinite(h.u_factors).all() and np.abs(h.i_factors - m.i_factors).max() < 1.0
+    assert rel_err(h.i_biases, g["B"]) < 0.5          # same popularity-driven bias pattern

@@ -104,3 +104,10 @@ def test_rank_restatement_semantics():
     ranked, item_scores = O.rank(scores, item_indices=np.array([4, 3, 2, 0]), k=2)
     assert ranked[:2].tolist() == [2, 3] and sorted(ranked.tolist()) == [0, 2, 3, 4]
     assert np.array_equal(item_scores, scores[[4, 3, 2, 0]])
+
+
+def test_wbpr_fit_matches_compiled_reference():
+    g = golden("wbpr_mid_k16")
+    r = O.wbpr_fit(g["indptr"], g["indices"], int(g["total_users"]), int(g["total_items"]), int(g["k"]),
+                   int(g["max_iter"]), float(g["lr"]), float(g["reg"]), True, int(g["seed"]))
+    assert rel_err(r["U"], g["U"]) < TOL and rel_err(r["V"], g["V"]) < TOL and rel_err(r["B"], g["B"]) < TOL
