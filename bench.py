@@ -33,7 +33,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOAD = dict(n_users=1_000_000, n_items=100_000, nnz=100_000_000, k=64, lr=0.05, reg=0.01, use_bias=True)
-RANK_WORKLOAD = dict(n_q=4096, topk=100)          # secondary metric: ranked users/s on the same model
+RANK_WORKLOAD = dict(n_q=75776, topk=100)          # secondary metric: ranked users/s on the same model
 CPU_SAMPLE = dict(n_users=100_000, nnz_target=10_000_000)   # bounded sample for the CPU legs (same k, same items)
 
 
@@ -335,7 +335,7 @@ def main():
             traffic = json.load(open(prof)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"kernel": "bpr_hogwild_kernel<G=16,NPL=1,VEC,%s,S=1>" % ("ATOMIC" if args.atomic else "PLAIN"), "bound": "hbm", "achieved": round(achieved, 1),
+    roofline = {"kernel": "bpr_hogwild_chunk_kernel<G=16,NPL=1,VEC,%s>" % ("ATOMIC" if args.atomic else "PLAIN"), "bound": "hbm", "achieved": round(achieved, 1),
                 "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_update": 24 * k + 32 + 4 * math.ceil(math.log2(mean_deg + 1)),
                 "kernel_ms": round(kern_ms, 3)}

@@ -519,8 +519,13 @@ static int launch_hogwild(const BprParams& p, cudaStream_t st)
     constexpr int E = NPL * (VEC ? 4 : 1);
     const HogwildTune tune = read_tune();
     if constexpr (E <= 8) {
-        if (tune.S == 0) return launch_hogwild_chunk<G, NPL, VEC, ATOMIC, EXACT, 4>(p, st, tune);
-        if (tune.S == 16) return launch_hogwild_chunk<G, NPL, VEC, ATOMIC, EXACT, 3>(p, st, tune);
+        // measured on B200 (profiles/): 64-register variant wins for 16-lane groups, 80 registers
+        // (no spills) for 32-lane groups
+        if (tune.S == 0) {
+            if (G >= 32) return launch_hogwild_chunk<G, NPL, VEC, ATOMIC, EXACT, 3>(p, st, tune);
+            return launch_hogwild_chunk<G, NPL, VEC, ATOMIC, EXACT, 4>(p, st, tune);
+        }
+        if (tune.S == 16) return launch_hogwild_chunk<G, NPL, VEC, ATOMIC, EXACT, (G >= 32 ? 4 : 3)>(p, st, tune);
     }
     if constexpr (E <= 4) {
         if (tune.S == 4) return launch_hogwild_s<G, NPL, VEC, ATOMIC, EXACT, 4, 2>(p, st, tune);
