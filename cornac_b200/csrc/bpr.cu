@@ -44,6 +44,7 @@ struct BprParams {
     int64_t n_neg;
     int64_t n_samples;
     int64_t max_groups;          // cap on concurrently running samples (Hogwild staleness bound)
+    int exact_exp;               // B200_SGD_EXACT_EXP
     int neg_weighted;            // WBPR: negatives drawn from the interaction list (popularity-weighted)
     float* U;
     float* V;
@@ -57,11 +58,10 @@ struct BprParams {
     unsigned long long* stats;   // {correct, skipped}
 };
 
-// z = 1 / (1 + exp(score))   (recom_bpr.pyx:252)
-template <bool EXACT>
-__device__ __forceinline__ float bpr_z(float score)
+// z = 1 / (1 + exp(score))   (recom_bpr.pyx:252); `exact` is warp-uniform
+__device__ __forceinline__ float bpr_z(float score, int exact)
 {
-    if (EXACT) return (float)(1.0 / (1.0 + exp((double)score)));
+    if (exact) return (float)(1.0 / (1.0 + exp((double)score)));
     return __frcp_rn(1.f + __expf(score));
 }
 
@@ -74,7 +74,7 @@ constexpr int hogwild_min_blocks()
     return (E * S <= 4) ? 5 : (E * S <= 8) ? 4 : (E * S <= 16) ? 2 : 1;
 }
 
-template <int G, int NPL, bool VEC, bool ATOMIC, bool EXACT, int S, int MINB>
+template <int G, int NPL, bool VEC, bool ATOMIC, int S, int MINB>
 __global__ void __launch_bounds__(256, MINB) bpr_hogwild_kernel(const BprParams p)
 {
     using Frag = RowFrag<NPL, VEC>;
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(256, MINB) bpr_hogwild_kernel(const BprParams 
             for (int e = 0; e < E; ++e) part = fmaf(fu[t].v[e], fi[t].v[e] - fj[t].v[e], part);
             const float score = (bi[t] - bj[t]) + group_sum<G>(part);
             if (!live[t]) continue;     // group-uniform
-            const float z = bpr_z<EXACT>(score);
+            const float z = bpr_z(score, p.exact_exp);
             n_correct += (z < .5f);
             const float lr = p.lr, reg = p.reg;
             float* pu = p.U + (size_t)u[t] * k;
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(256, MINB) bpr_hogwild_kernel(const BprParams 
 // instructions per sample.  The G resolved triplets are then broadcast one by one with warp
 // shuffles and applied by the whole group (row gathers of sample t+1 are issued before the
 // arithmetic of sample t).
-template <int G, int NPL, bool VEC, bool ATOMIC, bool EXACT, int MINB>
+template <int G, int NPL, bool VEC, bool ATOMIC, int MINB>
 __global__ void __launch_bounds__(256, MINB) bpr_hogwild_chunk_kernel(const BprParams p)
 {
     using Frag = RowFrag<NPL, VEC>;
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(256, MINB) bpr_hogwild_chunk_kernel(const BprP
 #pragma unroll
             for (int e = 0; e < E; ++e) part = fmaf(fu[cur].v[e], fi[cur].v[e] - fj[cur].v[e], part);
             const float score = (bi[cur] - bj[cur]) + group_sum<G>(part);      // recom_bpr.pyx:249-251
-            const float z = bpr_z<EXACT>(score);
+            const float z = bpr_z(score, p.exact_exp);
             n_correct += (z < .5f);
             float* pu = p.U + (size_t)cu[cur] * k;
             float* pi = p.V + (size_t)ci[cur] * k;
@@ -466,10 +466,10 @@ static HogwildTune read_tune()
     return t;
 }
 
-template <int G, int NPL, bool VEC, bool ATOMIC, bool EXACT, int S, int MINB>
+template <int G, int NPL, bool VEC, bool ATOMIC, int S, int MINB>
 static int launch_hogwild_s(const BprParams& p, cudaStream_t st, const HogwildTune& tune)
 {
-    auto kern = bpr_hogwild_kernel<G, NPL, VEC, ATOMIC, EXACT, S, MINB>;
+    auto kern = bpr_hogwild_kernel<G, NPL, VEC, ATOMIC, S, MINB>;
     const int threads = tune.threads;
     int occ = 0;
     B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, 0));
@@ -490,10 +490,10 @@ static int launch_hogwild_s(const BprParams& p, cudaStream_t st, const HogwildTu
     return B200_OK;
 }
 
-template <int G, int NPL, bool VEC, bool ATOMIC, bool EXACT, int MINB>
+template <int G, int NPL, bool VEC, bool ATOMIC, int MINB>
 static int launch_hogwild_chunk(const BprParams& p, cudaStream_t st, const HogwildTune& tune)
 {
-    auto kern = bpr_hogwild_chunk_kernel<G, NPL, VEC, ATOMIC, EXACT, MINB>;
+    auto kern = bpr_hogwild_chunk_kernel<G, NPL, VEC, ATOMIC, MINB>;
     const int threads = tune.threads;
     int occ = 0;
     B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, 0));
@@ -512,7 +512,7 @@ static int launch_hogwild_chunk(const BprParams& p, cudaStream_t st, const Hogwi
     return B200_OK;
 }
 
-template <int G, int NPL, bool VEC, bool ATOMIC, bool EXACT>
+template <int G, int NPL, bool VEC, bool ATOMIC>
 static int launch_hogwild(const BprParams& p, cudaStream_t st)
 {
     // samples in flight per group: bounded by the register footprint of the 3*S row fragments
@@ -522,17 +522,14 @@ static int launch_hogwild(const BprParams& p, cudaStream_t st)
         // measured on B200 (profiles/): 64-register variant wins for 16-lane groups, 80 registers
         // (no spills) for 32-lane groups
         if (tune.S == 0) {
-            if (G >= 32) return launch_hogwild_chunk<G, NPL, VEC, ATOMIC, EXACT, 3>(p, st, tune);
-            return launch_hogwild_chunk<G, NPL, VEC, ATOMIC, EXACT, 4>(p, st, tune);
+            if (G >= 32) return launch_hogwild_chunk<G, NPL, VEC, ATOMIC, 3>(p, st, tune);
+            return launch_hogwild_chunk<G, NPL, VEC, ATOMIC, 4>(p, st, tune);
         }
-        if (tune.S == 16) return launch_hogwild_chunk<G, NPL, VEC, ATOMIC, EXACT, (G >= 32 ? 4 : 3)>(p, st, tune);
     }
     if constexpr (E <= 4) {
-        if (tune.S == 4) return launch_hogwild_s<G, NPL, VEC, ATOMIC, EXACT, 4, 2>(p, st, tune);
-        if (tune.S == 8) return launch_hogwild_s<G, NPL, VEC, ATOMIC, EXACT, 1, 8>(p, st, tune);   // S=1, <=32 regs
-        return launch_hogwild_s<G, NPL, VEC, ATOMIC, EXACT, 1, 5>(p, st, tune);
+        return launch_hogwild_s<G, NPL, VEC, ATOMIC, 1, 5>(p, st, tune);      // register-only variant (B200_BPR_TUNE=1,...)
     } else {
-        return launch_hogwild_s<G, NPL, VEC, ATOMIC, EXACT, 1, hogwild_min_blocks<NPL, VEC, 1>()>(p, st, tune);
+        return launch_hogwild_s<G, NPL, VEC, ATOMIC, 1, hogwild_min_blocks<NPL, VEC, 1>()>(p, st, tune);
     }
 }
 
@@ -601,14 +598,12 @@ extern "C" int b200_bpr_epoch(const int32_t* pairs, const uint64_t* table, int64
     p.sample_base = sample_base;
     p.stats = reinterpret_cast<unsigned long long*>(stats);
     cudaStream_t st = (cudaStream_t)stream;
-    const bool atomic = flags & B200_SGD_ATOMIC, exact = flags & B200_SGD_EXACT_EXP;
+    const bool atomic = flags & B200_SGD_ATOMIC;
+    p.exact_exp = (flags & B200_SGD_EXACT_EXP) ? 1 : 0;
 #define CALL(G_, NPL_, VEC_)                                                                      \
     do {                                                                                          \
-        int rc;                                                                                   \
-        if (atomic) rc = exact ? launch_hogwild<G_, NPL_, VEC_, true, true>(p, st)                \
-                               : launch_hogwild<G_, NPL_, VEC_, true, false>(p, st);              \
-        else        rc = exact ? launch_hogwild<G_, NPL_, VEC_, false, true>(p, st)               \
-                               : launch_hogwild<G_, NPL_, VEC_, false, false>(p, st);             \
+        const int rc = atomic ? launch_hogwild<G_, NPL_, VEC_, true>(p, st)                       \
+                              : launch_hogwild<G_, NPL_, VEC_, false>(p, st);                     \
         if (rc) return rc;                                                                        \
     } while (0)
     B200_DISPATCH_LAYOUT(L, CALL);

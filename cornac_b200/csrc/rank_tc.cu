@@ -103,7 +103,7 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar)
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // 32 lanes x 32 columns of f32: thread t of the warp receives row (lane base + t), columns c..c+31
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32])
 {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -115,7 +115,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// wait for the outstanding tcgen05.ld; the registers are passed through the asm so that no use of
+// them can be scheduled above the wait
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :: "memory");
 }
 
 // UMMA shared-memory descriptor, K-major, SWIZZLE_NONE ("interleaved" core matrices):
@@ -272,20 +282,56 @@ __device__ __forceinline__ void raise_threshold(unsigned long long* __restrict__
     cnt = w;
 }
 
-// append (score bits, id) to the row's list unless the item is excluded for this user
-__device__ __noinline__ void nominate(unsigned long long* __restrict__ list, int& cnt, uint32_t score_bits, int32_t id,
-                                      const int32_t* __restrict__ ex, int n_ex)
+// Per-row epilogue state.  Items reach a row in increasing id order during one sweep over the
+// catalogue, so the exclusion test is a cursor over the row's sorted exclusion list: `ex_next` caches
+// the next excluded id and the common case (id < ex_next) costs one register compare.
+struct RowState {
+    unsigned long long* list;
+    const int32_t* ex;
+    int n_ex, ex_cur;
+    int32_t ex_next;
+    int cnt;
+    float tau, tau_f;
+};
+
+__device__ __forceinline__ void nominate(RowState& st, uint32_t score_bits, int32_t id)
 {
-    if (n_ex) {
-        int lo = 0, hi = n_ex;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (__ldg(ex + mid) < id) lo = mid + 1; else hi = mid;
+    if (id >= st.ex_next) {
+        while (st.ex_next < id) {
+            ++st.ex_cur;
+            st.ex_next = st.ex_cur < st.n_ex ? __ldg(st.ex + st.ex_cur) : 0x7fffffff;
         }
-        if (lo < n_ex && __ldg(ex + lo) == id) return;
+        if (st.ex_next == id) return;           // excluded for this user
     }
-    list[(size_t)cnt * 32] = ((unsigned long long)score_bits << 32) | (uint32_t)id;
-    ++cnt;
+    st.list[(size_t)st.cnt * 32] = ((unsigned long long)score_bits << 32) | (uint32_t)id;
+    ++st.cnt;
+}
+
+// one 32-column chunk of the accumulator: add the item base, then nominate everything above tau_f
+template <bool DUMP>
+__device__ __forceinline__ void epilogue_chunk(uint32_t (&r)[32], const float* __restrict__ bias, RowState& st,
+                                               int32_t id0, float* __restrict__ dump_row, bool valid)
+{
+    float m = -INFINITY;
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 b = *reinterpret_cast<const float4*>(bias + j4 * 4);
+        const float s0 = __uint_as_float(r[j4 * 4 + 0]) + b.x, s1 = __uint_as_float(r[j4 * 4 + 1]) + b.y;
+        const float s2 = __uint_as_float(r[j4 * 4 + 2]) + b.z, s3 = __uint_as_float(r[j4 * 4 + 3]) + b.w;
+        r[j4 * 4 + 0] = __float_as_uint(s0); r[j4 * 4 + 1] = __float_as_uint(s1);
+        r[j4 * 4 + 2] = __float_as_uint(s2); r[j4 * 4 + 3] = __float_as_uint(s3);
+        m = fmaxf(fmaxf(m, fmaxf(s0, s1)), fmaxf(s2, s3));
+    }
+    if (DUMP) {
+        if (valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dump_row[id0 + j] = __uint_as_float(r[j]);
+        }
+    } else if (m > st.tau_f) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (__uint_as_float(r[j]) > st.tau_f) nominate(st, r[j], id0 + j);
+    }
 }
 
 template <bool DUMP>
@@ -380,16 +426,20 @@ __global__ void __launch_bounds__(THREADS, 1) rank_tc_kernel(const RankTcParams 
             // |approx - exact| <= eps: bf16 rounding of both operands (2^-8 each) + f32 accumulation
             const float eps = 0.0083f * un * vmax + 2e-6f * (un * vmax + bmax);
             const float eps2 = 2.f * eps;
-            unsigned long long* list = p.lists + ((size_t)(ut * 4 + q) * CAP) * 32 + lane;
-            const int32_t* ex = nullptr;
-            int n_ex = 0;
+            RowState st;
+            st.list = p.lists + ((size_t)(ut * 4 + q) * CAP) * 32 + lane;
+            st.ex = nullptr; st.n_ex = 0; st.ex_cur = 0; st.ex_next = 0x7fffffff;
             if (valid && p.excl_indptr) {
                 const int64_t a = p.excl_indptr[row], b = p.excl_indptr[row + 1];
-                ex = p.excl_indices + a;
-                n_ex = (int)(b - a);
+                st.ex = p.excl_indices + a;
+                st.n_ex = (int)(b - a);
+                if (st.n_ex > 0) st.ex_next = __ldg(st.ex);
             }
-            int cnt = 0, flag = 0;
-            float tau = -INFINITY, tau_f = valid ? -INFINITY : INFINITY;
+            st.cnt = 0;
+            st.tau = -INFINITY;
+            st.tau_f = valid ? -INFINITY : INFINITY;
+            int flag = 0;
+            float* dump_row = DUMP ? p.dump + (size_t)(valid ? row : 0) * ((size_t)p.n_it * TN) : nullptr;
             for (int it = 0; it < p.n_it; ++it, ++it_global) {
                 const int s = it_global % NS;
                 const int acc = it_global & 1;
@@ -398,29 +448,18 @@ __global__ void __launch_bounds__(THREADS, 1) rank_tc_kernel(const RankTcParams 
                 tc_fence_after();
                 const float* bias = sB + (size_t)s * TN;
                 const int32_t item0 = it * TN;
+                const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN);
+                uint32_t r0[32], r1[32];
+                tmem_ld32_issue(t0, r0);
+                tmem_ld_wait(r0);
 #pragma unroll 1
-                for (int c0 = 0; c0 < TN; c0 += 32) {
-                    uint32_t r[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN + c0), r);
-                    float m = -INFINITY;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float sc = __uint_as_float(r[j]) + bias[c0 + j];
-                        r[j] = __float_as_uint(sc);
-                        m = fmaxf(m, sc);
-                    }
-                    if (DUMP) {
-                        if (valid) {
-                            float* o = p.dump + (size_t)row * ((size_t)p.n_it * TN) + item0 + c0;
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(r[j]);
-                        }
-                    } else if (m > tau_f) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            if (__uint_as_float(r[j]) > tau_f) nominate(list, cnt, r[j], item0 + c0 + j, ex, n_ex);
-                        }
-                    }
+                for (int c0 = 0; c0 < TN; c0 += 64) {
+                    tmem_ld32_issue(t0 + c0 + 32, r1);                        // in flight while r0 is processed
+                    epilogue_chunk<DUMP>(r0, bias + c0, st, item0 + c0, dump_row, valid);
+                    tmem_ld_wait(r1);
+                    if (c0 + 64 < TN) tmem_ld32_issue(t0 + c0 + 64, r0);
+                    epilogue_chunk<DUMP>(r1, bias + c0 + 32, st, item0 + c0 + 32, dump_row, valid);
+                    if (c0 + 64 < TN) tmem_ld_wait(r0);
                 }
                 // accumulator and stage are free again
                 tc_fence_before();
@@ -428,12 +467,13 @@ __global__ void __launch_bounds__(THREADS, 1) rank_tc_kernel(const RankTcParams 
                 if (lane == 0) { mbar_arrive(acc_empty + acc); mbar_arrive(empty + s); }
                 if (!DUMP) {
                     // lists may grow by at most TN entries per stage: keep cnt <= CAP - TN
-                    if (__any_sync(0xffffffffu, cnt >= TRIGGER)) {
-                        raise_threshold(list, cnt, p.topk, eps2, tau, tau_f);
-                        if (cnt > CAP - TN) { flag = 1; cnt = 0; tau_f = INFINITY; }
+                    if (__any_sync(0xffffffffu, st.cnt >= TRIGGER)) {
+                        raise_threshold(st.list, st.cnt, p.topk, eps2, st.tau, st.tau_f);
+                        if (st.cnt > CAP - TN) { flag = 1; st.cnt = 0; st.tau_f = INFINITY; }
                     }
                 }
             }
+            const int cnt = st.cnt;
             if (valid && !DUMP) { p.row_cnt[row] = cnt; p.row_flag[row] = flag; }
         }
     }
