@@ -35,7 +35,9 @@ namespace tc {
 
 constexpr int TM = 128;            // users per tile  (UMMA M)
 constexpr int TN = 256;            // items per stage (UMMA N)
-constexpr int THREADS = 256;       // 8 warps: TMA, MMA, TMEM-alloc, idle, 4 x epilogue
+constexpr int THREADS = 384;       // 12 warps: TMA, MMA, TMEM-alloc, idle, 8 x epilogue
+constexpr int EPI_WARPS = 8;       // warps 4-7 take accumulator columns [0,128), warps 8-11 columns [128,256)
+constexpr int HALF_N = TN / 2;
 constexpr int CAP = 1024;          // candidate-list capacity per row
 constexpr int TRIGGER = 512;       // raise the threshold when a list reaches this length
 constexpr int MAX_TOPK = 256;
@@ -228,29 +230,67 @@ struct RankTcParams {
     const int32_t* __restrict__ excl_indices;
     int64_t n_rows;                        // valid rows in this chunk
     int n_ut, n_it, kp, topk;
-    unsigned long long* __restrict__ lists;    // [n_ut * 4 warps][CAP][32] interleaved entries
-    int* __restrict__ row_cnt;             // [n_ut * TM]
-    int* __restrict__ row_flag;            // [n_ut * TM] 1 = list overflow -> exact path
+    unsigned long long* __restrict__ lists;    // [n_ut * 8 warps][CAP][32] interleaved entries
+    int* __restrict__ row_cnt;             // [n_ut * TM][2 halves]
+    int* __restrict__ row_flag;            // [n_ut * TM][2] 1 = list overflow -> exact path
     float* __restrict__ dump;              // debug: dense approximate scores [n_ut*TM][n_it*TN] or null
 };
 
 __device__ __forceinline__ float ent_score(unsigned long long e) { return __uint_as_float((unsigned)(e >> 32)); }
 
-// Raise the row threshold: tau = (approximately) the K-th largest listed score, never above it.
-// All 32 lanes run this together, each on its own list (entries of the lanes are interleaved, so
-// the scans are coalesced).  Returns the new count after dropping entries below tau - 2 eps.
-__device__ __forceinline__ void raise_threshold(unsigned long long* __restrict__ list, int& cnt, int K, float eps2,
-                                                float& tau, float& tau_f)
+// Per-thread epilogue state: one thread owns one (user row, column half) and its candidate list.
+// Items reach a list in increasing id order and compaction keeps that order, so lists stay sorted by
+// id; the user's exclusion list (sorted too) is merged against the NEW tail of the list whenever the
+// threshold is raised, and once more in the finish kernel -- the hot loop never branches on it.
+struct RowState {
+    unsigned long long* list;      // interleaved: entry e of this thread at list[e * 32]
+    const int32_t* ex;
+    int n_ex;
+    int cnt;                       // entries in the list
+    int checked;                   // entries [0, checked) are already exclusion-filtered
+    float tau, tau_f;              // tau_f = tau - 2 eps is the filter applied to every score
+};
+
+// Raise the threshold of one list: tau = (approximately) the K-th largest listed score, never above
+// it.  All 32 lanes run this together, each on its own list (the lanes' entries are interleaved in
+// memory, so the lock-step scans are coalesced).  Steps: (1) merge the new tail of the list against
+// the user's exclusion list and drop excluded items; (2) three rounds of 8-way bisection on the score
+// range for the largest t with #(score >= t) >= K; (3) drop entries below tau - 2 eps.
+__device__ __forceinline__ void raise_threshold(RowState& st, int K, float eps2)
 {
-    const int L = cnt;
+    unsigned long long* __restrict__ list = st.list;
+    // ---- (1) exclusion merge over entries [checked, cnt)
+    if (st.n_ex > 0 && st.checked < st.cnt) {
+        int w = st.checked, c = 0;
+        {   // lower_bound(ex, first new id)
+            const int32_t first = (int32_t)(list[(size_t)st.checked * 32] & 0xffffffffull);
+            int lo = 0, hi = st.n_ex;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (__ldg(st.ex + mid) < first) lo = mid + 1; else hi = mid;
+            }
+            c = lo;
+        }
+        int32_t ex_next = c < st.n_ex ? __ldg(st.ex + c) : 0x7fffffff;
+        for (int e = st.checked; e < st.cnt; ++e) {
+            const unsigned long long ent = list[(size_t)e * 32];
+            const int32_t id = (int32_t)(ent & 0xffffffffull);
+            while (ex_next < id) { ++c; ex_next = c < st.n_ex ? __ldg(st.ex + c) : 0x7fffffff; }
+            if (ex_next != id) { list[(size_t)w * 32] = ent; ++w; }
+        }
+        st.cnt = w;
+    }
+    st.checked = st.cnt;
+    const int L = st.cnt;
     if (L < K) return;
+    // ---- (2) score range, then bisection
     float lo = INFINITY, hi = -INFINITY;
     for (int e = 0; e < L; ++e) {
-        const float s = ent_score(list[(size_t)e * 32]);
-        lo = fminf(lo, s);
-        hi = fmaxf(hi, s);
+        const float sc = ent_score(list[(size_t)e * 32]);
+        lo = fminf(lo, sc);
+        hi = fmaxf(hi, sc);
     }
-    float a = lo, b = hi;                       // invariant: #(s >= a) >= K
+    float a = lo, b = hi;                       // invariant: #(score >= a) >= K
     for (int round = 0; round < 3; ++round) {
         const float step = (b - a) * 0.125f;
         if (!(step > 0.f) || !isfinite(step)) break;
@@ -258,9 +298,9 @@ __device__ __forceinline__ void raise_threshold(unsigned long long* __restrict__
         const float t1 = a + step, t2 = a + 2 * step, t3 = a + 3 * step, t4 = a + 4 * step, t5 = a + 5 * step,
                     t6 = a + 6 * step, t7 = a + 7 * step;
         for (int e = 0; e < L; ++e) {
-            const float s = ent_score(list[(size_t)e * 32]);
-            c1 += (s >= t1); c2 += (s >= t2); c3 += (s >= t3); c4 += (s >= t4);
-            c5 += (s >= t5); c6 += (s >= t6); c7 += (s >= t7);
+            const float sc = ent_score(list[(size_t)e * 32]);
+            c1 += (sc >= t1); c2 += (sc >= t2); c3 += (sc >= t3); c4 += (sc >= t4);
+            c5 += (sc >= t5); c6 += (sc >= t6); c7 += (sc >= t7);
         }
         float na = a, nb = t1;
         if (c1 >= K) { na = t1; nb = t2; }
@@ -272,65 +312,40 @@ __device__ __forceinline__ void raise_threshold(unsigned long long* __restrict__
         if (c7 >= K) { na = t7; nb = b; }
         a = na; b = nb;
     }
-    if (a > tau) tau = a;
-    tau_f = tau - eps2;
+    if (a > st.tau) st.tau = a;
+    st.tau_f = st.tau - eps2;
+    // ---- (3) compaction (order-preserving)
     int w = 0;
     for (int e = 0; e < L; ++e) {
         const unsigned long long ent = list[(size_t)e * 32];
-        if (ent_score(ent) >= tau_f) { list[(size_t)w * 32] = ent; ++w; }
+        if (ent_score(ent) >= st.tau_f) { list[(size_t)w * 32] = ent; ++w; }
     }
-    cnt = w;
+    st.cnt = w;
+    st.checked = w;
 }
 
-// Per-row epilogue state.  Items reach a row in increasing id order during one sweep over the
-// catalogue, so the exclusion test is a cursor over the row's sorted exclusion list: `ex_next` caches
-// the next excluded id and the common case (id < ex_next) costs one register compare.
-struct RowState {
-    unsigned long long* list;
-    const int32_t* ex;
-    int n_ex, ex_cur;
-    int32_t ex_next;
-    int cnt;
-    float tau, tau_f;
-};
-
-__device__ __forceinline__ void nominate(RowState& st, uint32_t score_bits, int32_t id)
-{
-    if (id >= st.ex_next) {
-        while (st.ex_next < id) {
-            ++st.ex_cur;
-            st.ex_next = st.ex_cur < st.n_ex ? __ldg(st.ex + st.ex_cur) : 0x7fffffff;
-        }
-        if (st.ex_next == id) return;           // excluded for this user
-    }
-    st.list[(size_t)st.cnt * 32] = ((unsigned long long)score_bits << 32) | (uint32_t)id;
-    ++st.cnt;
-}
-
-// one 32-column chunk of the accumulator: add the item base, then nominate everything above tau_f
+// one 32-column chunk of the accumulator: add the item base and append every score above tau_f.
+// Straight-line predicated code (FSETP / @P STG / IADD): no divergence, whatever the hit rate.
 template <bool DUMP>
 __device__ __forceinline__ void epilogue_chunk(uint32_t (&r)[32], const float* __restrict__ bias, RowState& st,
                                                int32_t id0, float* __restrict__ dump_row, bool valid)
 {
-    float m = -INFINITY;
 #pragma unroll
     for (int j4 = 0; j4 < 8; ++j4) {
         const float4 b = *reinterpret_cast<const float4*>(bias + j4 * 4);
-        const float s0 = __uint_as_float(r[j4 * 4 + 0]) + b.x, s1 = __uint_as_float(r[j4 * 4 + 1]) + b.y;
-        const float s2 = __uint_as_float(r[j4 * 4 + 2]) + b.z, s3 = __uint_as_float(r[j4 * 4 + 3]) + b.w;
-        r[j4 * 4 + 0] = __float_as_uint(s0); r[j4 * 4 + 1] = __float_as_uint(s1);
-        r[j4 * 4 + 2] = __float_as_uint(s2); r[j4 * 4 + 3] = __float_as_uint(s3);
-        m = fmaxf(fmaxf(m, fmaxf(s0, s1)), fmaxf(s2, s3));
-    }
-    if (DUMP) {
-        if (valid) {
+        const float sc[4] = {__uint_as_float(r[j4 * 4 + 0]) + b.x, __uint_as_float(r[j4 * 4 + 1]) + b.y,
+                             __uint_as_float(r[j4 * 4 + 2]) + b.z, __uint_as_float(r[j4 * 4 + 3]) + b.w};
 #pragma unroll
-            for (int j = 0; j < 32; ++j) dump_row[id0 + j] = __uint_as_float(r[j]);
+        for (int x = 0; x < 4; ++x) {
+            if (DUMP) {
+                if (valid) dump_row[id0 + j4 * 4 + x] = sc[x];
+            } else {
+                const bool hit = sc[x] > st.tau_f;
+                unsigned long long* dst = st.list + (size_t)st.cnt * 32;
+                if (hit) *dst = ((unsigned long long)__float_as_uint(sc[x]) << 32) | (uint32_t)(id0 + j4 * 4 + x);
+                st.cnt += hit ? 1 : 0;
+            }
         }
-    } else if (m > st.tau_f) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-            if (__uint_as_float(r[j]) > st.tau_f) nominate(st, r[j], id0 + j);
     }
 }
 
@@ -346,20 +361,20 @@ __global__ void __launch_bounds__(THREADS, 1) rank_tc_kernel(const RankTcParams 
     float* sB = reinterpret_cast<float*>(sV + (size_t)NS * v_bytes);
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sB) + (size_t)NS * b_bytes);
     uint64_t* full = bars;            // [NS]  TMA -> MMA / epilogue
-    uint64_t* empty = bars + 4;       // [NS]  MMA commit + 4 epilogue warps -> TMA
+    uint64_t* empty = bars + 4;       // [NS]  MMA commit + 8 epilogue warps -> TMA
     uint64_t* u_full = bars + 8;      // U tile landed
     uint64_t* u_empty = bars + 9;     // all MMAs of the user tile retired
     uint64_t* acc_full = bars + 10;   // [2] accumulator ready
-    uint64_t* acc_empty = bars + 12;  // [2] accumulator drained (4 epilogue warps)
+    uint64_t* acc_empty = bars + 12;  // [2] accumulator drained (8 epilogue warps)
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NS; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 5); }
+        for (int s = 0; s < NS; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1 + EPI_WARPS); }
         mbar_init(u_full, 1);
         mbar_init(u_empty, 1);
-        for (int a = 0; a < 2; ++a) { mbar_init(acc_full + a, 1); mbar_init(acc_empty + a, 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(acc_full + a, 1); mbar_init(acc_empty + a, EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) tmem_alloc(tmem_ptr, TMEM_COLS);
@@ -415,8 +430,9 @@ __global__ void __launch_bounds__(THREADS, 1) rank_tc_kernel(const RankTcParams 
             }
         }
     } else if (warp >= 4) {
-        // ===================== epilogue: one user row per thread =====================
-        const int q = warp - 4;                         // TMEM lane quarter == warp % 4
+        // ===================== epilogue: one (user row, column half) per thread =====================
+        const int q = warp & 3;                          // TMEM lane quarter == warp % 4
+        const int half = (warp - 4) >> 2;                // 0: columns [0,128), 1: columns [128,256)
         const float vmax = __uint_as_float(p.scal[0]), bmax = __uint_as_float(p.scal[1]);
         uint32_t it_global = 0;
         for (int ut = blockIdx.x; ut < p.n_ut; ut += gridDim.x) {
@@ -427,15 +443,14 @@ __global__ void __launch_bounds__(THREADS, 1) rank_tc_kernel(const RankTcParams 
             const float eps = 0.0083f * un * vmax + 2e-6f * (un * vmax + bmax);
             const float eps2 = 2.f * eps;
             RowState st;
-            st.list = p.lists + ((size_t)(ut * 4 + q) * CAP) * 32 + lane;
-            st.ex = nullptr; st.n_ex = 0; st.ex_cur = 0; st.ex_next = 0x7fffffff;
+            st.list = p.lists + ((size_t)(ut * EPI_WARPS + half * 4 + q) * CAP) * 32 + lane;
+            st.ex = nullptr; st.n_ex = 0;
             if (valid && p.excl_indptr) {
                 const int64_t a = p.excl_indptr[row], b = p.excl_indptr[row + 1];
                 st.ex = p.excl_indices + a;
                 st.n_ex = (int)(b - a);
-                if (st.n_ex > 0) st.ex_next = __ldg(st.ex);
             }
-            st.cnt = 0;
+            st.cnt = 0; st.checked = 0;
             st.tau = -INFINITY;
             st.tau_f = valid ? -INFINITY : INFINITY;
             int flag = 0;
@@ -446,35 +461,34 @@ __global__ void __launch_bounds__(THREADS, 1) rank_tc_kernel(const RankTcParams 
                 mbar_wait(full + s, (it_global / NS) & 1);          // item-base values visible
                 mbar_wait(acc_full + acc, (it_global >> 1) & 1);
                 tc_fence_after();
-                const float* bias = sB + (size_t)s * TN;
-                const int32_t item0 = it * TN;
-                const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN);
+                const float* bias = sB + (size_t)s * TN + half * HALF_N;
+                const int32_t item0 = it * TN + half * HALF_N;
+                const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN + half * HALF_N);
                 uint32_t r0[32], r1[32];
                 tmem_ld32_issue(t0, r0);
                 tmem_ld_wait(r0);
-#pragma unroll 1
-                for (int c0 = 0; c0 < TN; c0 += 64) {
+#pragma unroll
+                for (int c0 = 0; c0 < HALF_N; c0 += 64) {
                     tmem_ld32_issue(t0 + c0 + 32, r1);                        // in flight while r0 is processed
                     epilogue_chunk<DUMP>(r0, bias + c0, st, item0 + c0, dump_row, valid);
                     tmem_ld_wait(r1);
-                    if (c0 + 64 < TN) tmem_ld32_issue(t0 + c0 + 64, r0);
+                    if (c0 + 64 < HALF_N) tmem_ld32_issue(t0 + c0 + 64, r0);
                     epilogue_chunk<DUMP>(r1, bias + c0 + 32, st, item0 + c0 + 32, dump_row, valid);
-                    if (c0 + 64 < TN) tmem_ld_wait(r0);
+                    if (c0 + 64 < HALF_N) tmem_ld_wait(r0);
                 }
                 // accumulator and stage are free again
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(acc_empty + acc); mbar_arrive(empty + s); }
                 if (!DUMP) {
-                    // lists may grow by at most TN entries per stage: keep cnt <= CAP - TN
+                    // a list grows by at most HALF_N entries per stage: keep cnt <= CAP - HALF_N
                     if (__any_sync(0xffffffffu, st.cnt >= TRIGGER)) {
-                        raise_threshold(st.list, st.cnt, p.topk, eps2, st.tau, st.tau_f);
-                        if (st.cnt > CAP - TN) { flag = 1; st.cnt = 0; st.tau_f = INFINITY; }
+                        raise_threshold(st, p.topk, eps2);
+                        if (st.cnt > CAP - HALF_N) { flag = 1; st.cnt = 0; st.checked = 0; st.tau_f = INFINITY; }
                     }
                 }
             }
-            const int cnt = st.cnt;
-            if (valid && !DUMP) { p.row_cnt[row] = cnt; p.row_flag[row] = flag; }
+            if (valid && !DUMP) { p.row_cnt[row * 2 + half] = st.cnt; p.row_flag[row * 2 + half] = flag; }
         }
     }
 
@@ -496,6 +510,8 @@ struct FinishParams {
     const unsigned long long* __restrict__ lists;
     const int* __restrict__ row_cnt;
     const int* __restrict__ row_flag;
+    const int64_t* __restrict__ excl_indptr;   // offset to the chunk (may be null)
+    const int32_t* __restrict__ excl_indices;
     int32_t* __restrict__ out_ids;             // offset to the chunk
     float* __restrict__ out_scores;
     int* __restrict__ overflow_rows;           // [0] = count, [1..] = global query indices
@@ -503,43 +519,64 @@ struct FinishParams {
 
 __global__ void __launch_bounds__(128) rank_tc_finish_kernel(const FinishParams p)
 {
-    __shared__ unsigned long long sort_buf[CAP];
+    __shared__ unsigned long long sort_buf[2 * CAP];
     const int tid = threadIdx.x;
     for (int64_t row = blockIdx.x; row < p.n_rows; row += gridDim.x) {
         __syncthreads();
-        if (p.row_flag[row]) {
+        if (p.row_flag[row * 2] | p.row_flag[row * 2 + 1]) {
             if (tid == 0) {
                 const int slot = atomicAdd(p.overflow_rows, 1);
                 p.overflow_rows[1 + slot] = (int)(p.q0 + row);
             }
             continue;
         }
-        const int L = p.row_cnt[row];
+        const int L0 = p.row_cnt[row * 2], L1 = p.row_cnt[row * 2 + 1], L = L0 + L1;
         const int64_t ut = row / TM;
         const int r = (int)(row % TM);
-        const unsigned long long* list = p.lists + ((size_t)(ut * 4 + (r >> 5)) * CAP) * 32 + (r & 31);
+        const unsigned long long* list0 = p.lists + ((size_t)(ut * EPI_WARPS + (r >> 5)) * CAP) * 32 + (r & 31);
+        const unsigned long long* list1 = p.lists + ((size_t)(ut * EPI_WARPS + 4 + (r >> 5)) * CAP) * 32 + (r & 31);
         const int64_t gq = p.q0 + row;
         const int64_t urow = p.user_idx ? p.user_idx[row] : gq;
         const float* u = p.U + (size_t)urow * p.k;
         const float uo = p.user_off ? __ldg(p.user_off + gq) : 0.f;
-        for (int e = tid; e < CAP; e += 128) {
+        const int32_t* ex = nullptr;
+        int n_ex = 0;
+        if (p.excl_indptr) {
+            const int64_t a = p.excl_indptr[row], b = p.excl_indptr[row + 1];
+            ex = p.excl_indices + a;
+            n_ex = (int)(b - a);
+        }
+        int sort_n = 32;                            // power of two >= L (padding keys are 0 = below every entry)
+        while (sort_n < L) sort_n <<= 1;
+        for (int e = tid; e < sort_n; e += 128) {
             unsigned long long key = 0ull;
-            float sc = -INFINITY;
             if (e < L) {
-                const int32_t id = (int32_t)(list[(size_t)e * 32] & 0xffffffffull);
-                const float* v = p.V + (size_t)id * p.k;
-                double acc = 0.0;
-                for (int f = 0; f < p.k; ++f) acc = fma((double)__ldg(u + f), (double)__ldg(v + f), acc);
-                const float base = p.item_base ? __ldg(p.item_base + id) : 0.f;
-                sc = __fadd_rn(__fadd_rn(base, uo), __double2float_rn(acc));      // == score_batch_kernel
-                key = ((unsigned long long)float_key(sc) << 32) | (unsigned)(0xffffffffu - (unsigned)id);
+                const unsigned long long ent = e < L0 ? list0[(size_t)e * 32] : list1[(size_t)(e - L0) * 32];
+                const int32_t id = (int32_t)(ent & 0xffffffffull);
+                bool excluded = false;
+                if (n_ex) {                         // entries appended after the last merge are still unfiltered
+                    int lo = 0, hi = n_ex;
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if (__ldg(ex + mid) < id) lo = mid + 1; else hi = mid;
+                    }
+                    excluded = lo < n_ex && __ldg(ex + lo) == id;
+                }
+                if (!excluded) {
+                    const float* v = p.V + (size_t)id * p.k;
+                    double acc = 0.0;
+                    for (int f = 0; f < p.k; ++f) acc = fma((double)__ldg(u + f), (double)__ldg(v + f), acc);
+                    const float base = p.item_base ? __ldg(p.item_base + id) : 0.f;
+                    const float sc = __fadd_rn(__fadd_rn(base, uo), __double2float_rn(acc));      // == score_batch_kernel
+                    key = ((unsigned long long)float_key(sc) << 32) | (unsigned)(0xffffffffu - (unsigned)id);
+                }
             }
             sort_buf[e] = key;
         }
         __syncthreads();
-        for (int size = 2; size <= CAP; size <<= 1) {
+        for (int size = 2; size <= sort_n; size <<= 1) {
             for (int stride = size >> 1; stride > 0; stride >>= 1) {
-                for (int x = tid; x < CAP / 2; x += 128) {
+                for (int x = tid; x < sort_n / 2; x += 128) {
                     const int lo = 2 * x - (x & (stride - 1));
                     const int hi = lo + stride;
                     const bool desc = ((lo & size) == 0);
@@ -552,8 +589,8 @@ __global__ void __launch_bounds__(128) rank_tc_finish_kernel(const FinishParams 
         for (int x = tid; x < p.topk; x += 128) {
             int32_t id = -1;
             float sc = -INFINITY;
-            if (x < L) {
-                const unsigned long long ent = sort_buf[x];
+            const unsigned long long ent = x < sort_n ? sort_buf[x] : 0ull;
+            if (ent != 0ull) {                              // excluded / padding keys are 0 and sort last
                 id = (int32_t)(0xffffffffu - (unsigned)(ent & 0xffffffffull));
                 const unsigned kb = (unsigned)(ent >> 32);           // invert float_key
                 const unsigned bits = (kb & 0x80000000u) ? (kb & 0x7fffffffu) : ~kb;
@@ -587,9 +624,9 @@ static Layout make_layout(int64_t n_q, int64_t n_items, int k)
     L.off_scal = take(64);
     L.off_upack = take((size_t)L.chunk_ut * TM * L.kp * 2);
     L.off_unorm = take((size_t)L.chunk_rows * 4);
-    L.off_lists = take((size_t)L.chunk_ut * 4 * CAP * 32 * 8);
-    L.off_cnt = take((size_t)L.chunk_rows * 4);
-    L.off_flag = take((size_t)L.chunk_rows * 4);
+    L.off_lists = take((size_t)L.chunk_ut * EPI_WARPS * CAP * 32 * 8);
+    L.off_cnt = take((size_t)L.chunk_rows * 2 * 4);
+    L.off_flag = take((size_t)L.chunk_rows * 2 * 4);
     L.off_over = take((size_t)(L.chunk_rows + 1) * 4);
     L.off_slab = take((size_t)n_items * 4);          // one exact score row for overflowed users
     L.total = o;
@@ -678,6 +715,7 @@ int rank_tc(const float* U, const int64_t* user_idx, int64_t n_q, const float* V
         f.U = U; f.user_idx = uidx; f.q0 = q0; f.V = V; f.item_base = item_base; f.user_off = user_off;
         f.n_rows = rows; f.k = k; f.topk = topk;
         f.lists = p.lists; f.row_cnt = p.row_cnt; f.row_flag = p.row_flag;
+        f.excl_indptr = p.excl_indptr; f.excl_indices = p.excl_indices;
         f.out_ids = out_ids + (size_t)q0 * topk; f.out_scores = out_scores + (size_t)q0 * topk;
         f.overflow_rows = reinterpret_cast<int*>(ws + L.off_over);
         const int fgrid = (int)(rows < (int64_t)sm_count() * 8 ? rows : (int64_t)sm_count() * 8);
