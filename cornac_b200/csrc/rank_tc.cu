@@ -38,6 +38,7 @@ constexpr int TN = 256;            // items per stage (UMMA N)
 constexpr int THREADS = 384;       // 12 warps: TMA, MMA, TMEM-alloc, idle, 8 x epilogue
 constexpr int EPI_WARPS = 8;       // warps 4-7 take accumulator columns [0,128), warps 8-11 columns [128,256)
 constexpr int HALF_N = TN / 2;
+constexpr int NB = 4;              // item-base ring slots
 constexpr int CAP = 1024;          // candidate-list capacity per row
 constexpr int TRIGGER = 512;       // raise the threshold when a list reaches this length
 constexpr int MAX_TOPK = 256;
@@ -149,6 +150,14 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N)
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// V-tile ring depth that fits next to the U tile in 220 KB of shared memory (2..4)
+__host__ __device__ __forceinline__ int num_stages(int kp)
+{
+    const int budget = 220 * 1024 - TM * kp * 2 - NB * TN * 4;
+    int ns = budget / (TN * kp * 2);
+    return ns > 4 ? 4 : (ns < 2 ? 2 : ns);
+}
+
 // byte offset of element (row r, column c) inside a packed tile of `kp` bf16 columns
 __host__ __device__ __forceinline__ size_t packed_offset(int r, int c, int kp)
 {
@@ -251,6 +260,21 @@ struct RowState {
     float tau, tau_f;              // tau_f = tau - 2 eps is the filter applied to every score
 };
 
+// sequential scan of a list with 8 independent loads in flight (the lists live in global memory / L2)
+template <typename F>
+__device__ __forceinline__ void scan_list(const unsigned long long* list, int L, F f)
+{
+    int e = 0;
+    for (; e + 8 <= L; e += 8) {
+        unsigned long long v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = list[(size_t)(e + i) * 32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f(v[i]);
+    }
+    for (; e < L; ++e) f(list[(size_t)e * 32]);
+}
+
 // Raise the threshold of one list: tau = (approximately) the K-th largest listed score, never above
 // it.  All 32 lanes run this together, each on its own list (the lanes' entries are interleaved in
 // memory, so the lock-step scans are coalesced).  Steps: (1) merge the new tail of the list against
@@ -285,11 +309,11 @@ __device__ __forceinline__ void raise_threshold(RowState& st, int K, float eps2)
     if (L < K) return;
     // ---- (2) score range, then bisection
     float lo = INFINITY, hi = -INFINITY;
-    for (int e = 0; e < L; ++e) {
-        const float sc = ent_score(list[(size_t)e * 32]);
+    scan_list(list, L, [&](unsigned long long ent) {
+        const float sc = ent_score(ent);
         lo = fminf(lo, sc);
         hi = fmaxf(hi, sc);
-    }
+    });
     float a = lo, b = hi;                       // invariant: #(score >= a) >= K
     for (int round = 0; round < 3; ++round) {
         const float step = (b - a) * 0.125f;
@@ -297,11 +321,11 @@ __device__ __forceinline__ void raise_threshold(RowState& st, int K, float eps2)
         int c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0, c7 = 0;
         const float t1 = a + step, t2 = a + 2 * step, t3 = a + 3 * step, t4 = a + 4 * step, t5 = a + 5 * step,
                     t6 = a + 6 * step, t7 = a + 7 * step;
-        for (int e = 0; e < L; ++e) {
-            const float sc = ent_score(list[(size_t)e * 32]);
+        scan_list(list, L, [&](unsigned long long ent) {
+            const float sc = ent_score(ent);
             c1 += (sc >= t1); c2 += (sc >= t2); c3 += (sc >= t3); c4 += (sc >= t4);
             c5 += (sc >= t5); c6 += (sc >= t6); c7 += (sc >= t7);
-        }
+        });
         float na = a, nb = t1;
         if (c1 >= K) { na = t1; nb = t2; }
         if (c2 >= K) { na = t2; nb = t3; }
@@ -315,11 +339,10 @@ __device__ __forceinline__ void raise_threshold(RowState& st, int K, float eps2)
     if (a > st.tau) st.tau = a;
     st.tau_f = st.tau - eps2;
     // ---- (3) compaction (order-preserving)
-    int w = 0;
-    for (int e = 0; e < L; ++e) {
-        const unsigned long long ent = list[(size_t)e * 32];
+    int w = 0;          // writes trail the reads (w <= e), and each batch of 8 is read before it is written
+    scan_list(list, L, [&](unsigned long long ent) {
         if (ent_score(ent) >= st.tau_f) { list[(size_t)w * 32] = ent; ++w; }
-    }
+    });
     st.cnt = w;
     st.checked = w;
 }
@@ -355,23 +378,28 @@ __global__ void __launch_bounds__(THREADS, 1) rank_tc_kernel(const RankTcParams 
     extern __shared__ __align__(1024) uint8_t smem[];
     const int kp = p.kp;
     const uint32_t u_bytes = TM * kp * 2, v_bytes = TN * kp * 2, b_bytes = TN * 4;
-    const int NS = (kp <= 64) ? 4 : 2;
+    const int NS = num_stages(kp);
     uint8_t* sU = smem;
     uint8_t* sV = sU + u_bytes;
-    float* sB = reinterpret_cast<float*>(sV + (size_t)NS * v_bytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sB) + (size_t)NS * b_bytes);
-    uint64_t* full = bars;            // [NS]  TMA -> MMA / epilogue
-    uint64_t* empty = bars + 4;       // [NS]  MMA commit + 8 epilogue warps -> TMA
+    float* sB = reinterpret_cast<float*>(sV + (size_t)NS * v_bytes);      // [NB][TN] item-base ring
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sB) + (size_t)NB * b_bytes);
+    uint64_t* full = bars;            // [NS]  V tile landed                 TMA -> MMA
+    uint64_t* empty = bars + 4;       // [NS]  MMAs reading the tile retired MMA commit -> TMA
     uint64_t* u_full = bars + 8;      // U tile landed
     uint64_t* u_empty = bars + 9;     // all MMAs of the user tile retired
-    uint64_t* acc_full = bars + 10;   // [2] accumulator ready
-    uint64_t* acc_empty = bars + 12;  // [2] accumulator drained (8 epilogue warps)
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
+    uint64_t* acc_full = bars + 10;   // [2] accumulator ready               MMA commit -> epilogue
+    uint64_t* acc_empty = bars + 12;  // [2] accumulator drained             8 epilogue warps -> MMA
+    uint64_t* bfull = bars + 14;      // [NB] item-base slice landed         TMA -> epilogue
+    uint64_t* bempty = bars + 18;     // [NB] slice consumed                 8 epilogue warps -> TMA
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 22);
+    // The V ring is released by the tensor pipe alone, so the TMA producer runs NS tiles ahead of
+    // the MMAs whatever the epilogue does; the (tiny) item-base ring is what the epilogue releases.
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NS; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1 + EPI_WARPS); }
+        for (int s = 0; s < NS; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int s = 0; s < NB; ++s) { mbar_init(bfull + s, 1); mbar_init(bempty + s, EPI_WARPS); }
         mbar_init(u_full, 1);
         mbar_init(u_empty, 1);
         for (int a = 0; a < 2; ++a) { mbar_init(acc_full + a, 1); mbar_init(acc_empty + a, EPI_WARPS); }
@@ -395,9 +423,13 @@ __global__ void __launch_bounds__(THREADS, 1) rank_tc_kernel(const RankTcParams 
                     const int s = it_global % NS;
                     const uint32_t round = it_global / NS;
                     if (round > 0) mbar_wait(empty + s, (round - 1) & 1);
-                    mbar_expect_tx(full + s, v_bytes + b_bytes);
+                    mbar_expect_tx(full + s, v_bytes);
                     bulk_g2s(sV + (size_t)s * v_bytes, p.Vpack + (size_t)it * v_bytes, v_bytes, full + s);
-                    bulk_g2s(sB + (size_t)s * TN, p.base_pad + (size_t)it * TN, b_bytes, full + s);
+                    const int bs = it_global % NB;
+                    const uint32_t bround = it_global / NB;
+                    if (bround > 0) mbar_wait(bempty + bs, (bround - 1) & 1);
+                    mbar_expect_tx(bfull + bs, b_bytes);
+                    bulk_g2s(sB + (size_t)bs * TN, p.base_pad + (size_t)it * TN, b_bytes, bfull + bs);
                 }
             }
         }
@@ -456,12 +488,12 @@ __global__ void __launch_bounds__(THREADS, 1) rank_tc_kernel(const RankTcParams 
             int flag = 0;
             float* dump_row = DUMP ? p.dump + (size_t)(valid ? row : 0) * ((size_t)p.n_it * TN) : nullptr;
             for (int it = 0; it < p.n_it; ++it, ++it_global) {
-                const int s = it_global % NS;
+                const int bs = it_global % NB;
                 const int acc = it_global & 1;
-                mbar_wait(full + s, (it_global / NS) & 1);          // item-base values visible
+                mbar_wait(bfull + bs, (it_global / NB) & 1);        // item-base values visible
                 mbar_wait(acc_full + acc, (it_global >> 1) & 1);
                 tc_fence_after();
-                const float* bias = sB + (size_t)s * TN + half * HALF_N;
+                const float* bias = sB + (size_t)bs * TN + half * HALF_N;
                 const int32_t item0 = it * TN + half * HALF_N;
                 const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN + half * HALF_N);
                 uint32_t r0[32], r1[32];
@@ -479,7 +511,7 @@ __global__ void __launch_bounds__(THREADS, 1) rank_tc_kernel(const RankTcParams 
                 // accumulator and stage are free again
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) { mbar_arrive(acc_empty + acc); mbar_arrive(empty + s); }
+                if (lane == 0) { mbar_arrive(acc_empty + acc); mbar_arrive(bempty + bs); }
                 if (!DUMP) {
                     // a list grows by at most HALF_N entries per stage: keep cnt <= CAP - HALF_N
                     if (__any_sync(0xffffffffu, st.cnt >= TRIGGER)) {
@@ -635,8 +667,8 @@ static Layout make_layout(int64_t n_q, int64_t n_items, int k)
 
 static size_t smem_bytes_for(int kp)
 {
-    const int NS = (kp <= 64) ? 4 : 2;
-    return (size_t)TM * kp * 2 + (size_t)NS * (TN * kp * 2 + TN * 4) + 16 * 8 + 1024;
+    const int NS = num_stages(kp);
+    return (size_t)TM * kp * 2 + (size_t)NS * (TN * kp * 2) + (size_t)NB * TN * 4 + 32 * 8 + 1024;
 }
 
 }  // namespace tc
