@@ -430,22 +430,21 @@ def run_e2e(args, W, engine, indptr, indices, dev, world, rank):
 
 
 def run_rank(W, engine, data, U, V, B, dev):
-    """ranked users/s: score + exclusion of train positives + top-100 for a batch of users."""
+    """ranked users/s: score + exclusion of train positives + top-100 for a batch of users (tensor-core fused
+    kernel), device-resident request (`value`) and through the host-buffer entry (`e2e`)."""
     import torch
-    from cornac_b200._lib import check, current_stream, load, ptr
+    from cornac_b200._lib import load
     L = load()
     n_q, topk, k = RANK_WORKLOAD["n_q"], RANK_WORKLOAD["topk"], W["k"]
     n_q = min(n_q, W["n_users"])
     uidx = torch.arange(n_q, device=dev, dtype=torch.int64)
     ex_ptr = data.indptr[: n_q + 1].to(torch.int64).contiguous()
-    ids = torch.empty((n_q, topk), dtype=torch.int32, device=dev)
-    sc = torch.empty((n_q, topk), dtype=torch.float32, device=dev)
+    ex_idx = data.indices[: int(ex_ptr[-1].item())].contiguous()
     nb = int(L.b200_rank_topk_workspace_bytes(n_q, W["n_items"], k, topk))
     ws = torch.empty(max(nb, 16), dtype=torch.uint8, device=dev)
 
     def go():
-        check(L.b200_rank_topk(ptr(U), ptr(uidx), n_q, ptr(V), W["n_items"], k, ptr(B), None, ptr(ex_ptr), ptr(data.indices),
-                               topk, ptr(ids), ptr(sc), ptr(ws), nb, current_stream()), "b200_rank_topk")
+        return engine.rank_topk(U, V, topk, user_idx=uidx, item_base=B, excl_indptr=ex_ptr, excl_indices=ex_idx, workspace=ws)
     go()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -455,9 +454,29 @@ def run_rank(W, engine, data, U, V, B, dev):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 3
+    # end to end: pinned host request (user ids + exclusion CSR) -> H2D -> kernels -> D2H ids + scores
+    h_u = uidx.cpu().pin_memory()
+    h_p, h_i = ex_ptr.cpu().pin_memory(), ex_idx.cpu().pin_memory()
+    o_i = torch.empty((n_q, topk), dtype=torch.int32).pin_memory()
+    o_s = torch.empty((n_q, topk), dtype=torch.float32).pin_memory()
+
+    def go_host():
+        engine.rank_topk_host(U, V, topk, h_u.numpy(), item_base=B, excl_indptr=h_p.numpy(), excl_indices=h_i.numpy(),
+                              out_ids=o_i.numpy(), out_scores=o_s.numpy(), workspace=ws)
+    go_host()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        go_host()
+    torch.cuda.synchronize()
+    ms_h = (time.perf_counter() - t0) / 3 * 1e3
+    h2d = h_u.numel() * 8 + h_p.numel() * 8 + h_i.numel() * 4
     return {"metric": "ranked users/sec", "value": round(n_q / (ms * 1e-3), 1), "unit": "users/s",
-            "config": "%d users x %d items k=%d top-%d, train positives excluded" % (n_q, W["n_items"], k, topk),
-            "ms": round(ms, 3), "tflops": round(2.0 * k * W["n_items"] * n_q / (ms * 1e-3) / 1e12, 2)}
+            "config": "%d users x %d items k=%d top-%d, train positives excluded (BASELINE configs[1] model)" % (n_q, W["n_items"], k, topk),
+            "ms": round(ms, 3), "tflops": round(2.0 * k * W["n_items"] * n_q / (ms * 1e-3) / 1e12, 2),
+            "e2e": {"value": round(n_q / (ms_h * 1e-3), 1), "unit": "users/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(n_q * topk * 8), "ms": round(ms_h, 3),
+                    "path": "engine.rank_topk_host: pinned user ids + exclusion CSR -> H2D -> b200_rank_topk -> D2H ids + scores"}}
 
 
 def run_reference_arm(args, W):

@@ -65,31 +65,26 @@ class DeviceScoringMixin:
         Returns (ids int32 [n_q, k] (-1 padded), scores float32 [n_q, k]) as numpy arrays,
         ordered by (score desc, item id asc).
         """
-        from ._lib import check, ptr, current_stream, load
         d = self._b200_device()
-        L = load()
         user_indices = np.asarray(user_indices, dtype=np.int64)
         n_q = len(user_indices)
-        uidx = torch.from_numpy(user_indices).cuda()
-        uoff = None if d["user_off"] is None else d["user_off"][uidx].contiguous()
         ex_ptr = ex_idx = None
         if exclude is not None:
             sub = exclude[user_indices] if n_q != exclude.shape[0] or not np.array_equal(
                 user_indices, np.arange(exclude.shape[0])) else exclude
             sub = sub.tocsr()
             sub.sort_indices()
-            ex_ptr = engine.to_device(sub.indptr.astype(np.int64), torch.int64)
-            ex_idx = engine.to_device(sub.indices.astype(np.int32), torch.int32)
-            if ex_idx.numel() == 0:
-                ex_idx = torch.zeros(1, dtype=torch.int32, device="cuda")
-        n_items, kdim = d["n_items"], d["V"].shape[1]
-        ids = torch.empty((n_q, k), dtype=torch.int32, device="cuda")
-        sc = torch.empty((n_q, k), dtype=torch.float32, device="cuda")
-        ws_bytes = int(L.b200_rank_topk_workspace_bytes(n_q, n_items, kdim, int(k)))
-        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device="cuda")
-        check(L.b200_rank_topk(ptr(d["U"]), ptr(uidx), n_q, ptr(d["V"]), n_items, kdim, ptr(d["item_base"]), ptr(uoff),
-                               ptr(ex_ptr), ptr(ex_idx), int(k), ptr(ids), ptr(sc), ptr(ws), ws_bytes,
-                               current_stream()), "b200_rank_topk")
+            ex_ptr, ex_idx = sub.indptr.astype(np.int64), sub.indices.astype(np.int32)
+        uidx = torch.from_numpy(user_indices).cuda()
+        uoff = None if d["user_off"] is None else d["user_off"][uidx].contiguous()
+        if uoff is None:
+            return engine.rank_topk_host(d["U"], d["V"][: d["n_items"]], int(k), user_indices, item_base=d["item_base"],
+                                         excl_indptr=ex_ptr, excl_indices=ex_idx)
+        ep = None if ex_ptr is None else engine.to_device(ex_ptr, torch.int64)
+        ei = None if ex_ptr is None else (engine.to_device(ex_idx, torch.int32) if len(ex_idx) else
+                                          torch.zeros(1, dtype=torch.int32, device="cuda"))
+        ids, sc = engine.rank_topk(d["U"], d["V"], int(k), user_idx=uidx, item_base=d["item_base"], user_off=uoff,
+                                   excl_indptr=ep, excl_indices=ei, n_items=d["n_items"])
         return ids.cpu().numpy(), sc.cpu().numpy()
 
     # ---- Recommender.rank ------------------------------------------------------------

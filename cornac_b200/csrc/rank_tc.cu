@@ -258,19 +258,20 @@ struct RowState {
     int cnt;                       // entries in the list
     int checked;                   // entries [0, checked) are already exclusion-filtered
     float tau, tau_f;              // tau_f = tau - 2 eps is the filter applied to every score
+    float hi;                      // largest score seen at the last raise (bisection range)
 };
 
-// sequential scan of a list with 8 independent loads in flight (the lists live in global memory / L2)
+// sequential scan of a list with 16 independent loads in flight (the lists live in global memory / L2)
 template <typename F>
 __device__ __forceinline__ void scan_list(const unsigned long long* list, int L, F f)
 {
     int e = 0;
-    for (; e + 8 <= L; e += 8) {
-        unsigned long long v[8];
+    for (; e + 16 <= L; e += 16) {
+        unsigned long long v[16];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = list[(size_t)(e + i) * 32];
+        for (int i = 0; i < 16; ++i) v[i] = list[(size_t)(e + i) * 32];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) f(v[i]);
+        for (int i = 0; i < 16; ++i) f(v[i]);
     }
     for (; e < L; ++e) f(list[(size_t)e * 32]);
 }
@@ -278,7 +279,7 @@ __device__ __forceinline__ void scan_list(const unsigned long long* list, int L,
 // Raise the threshold of one list: tau = (approximately) the K-th largest listed score, never above
 // it.  All 32 lanes run this together, each on its own list (the lanes' entries are interleaved in
 // memory, so the lock-step scans are coalesced).  Steps: (1) merge the new tail of the list against
-// the user's exclusion list and drop excluded items; (2) three rounds of 8-way bisection on the score
+// the user's exclusion list and drop excluded items; (2) two rounds of 16-way bisection on the score
 // range for the largest t with #(score >= t) >= K; (3) drop entries below tau - 2 eps.
 __device__ __forceinline__ void raise_threshold(RowState& st, int K, float eps2)
 {
@@ -307,39 +308,41 @@ __device__ __forceinline__ void raise_threshold(RowState& st, int K, float eps2)
     st.checked = st.cnt;
     const int L = st.cnt;
     if (L < K) return;
-    // ---- (2) score range, then bisection
-    float lo = INFINITY, hi = -INFINITY;
-    scan_list(list, L, [&](unsigned long long ent) {
-        const float sc = ent_score(ent);
-        lo = fminf(lo, sc);
-        hi = fmaxf(hi, sc);
-    });
-    float a = lo, b = hi;                       // invariant: #(score >= a) >= K
-    for (int round = 0; round < 3; ++round) {
-        const float step = (b - a) * 0.125f;
-        if (!(step > 0.f) || !isfinite(step)) break;
-        int c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0, c7 = 0;
-        const float t1 = a + step, t2 = a + 2 * step, t3 = a + 3 * step, t4 = a + 4 * step, t5 = a + 5 * step,
-                    t6 = a + 6 * step, t7 = a + 7 * step;
+    // ---- (2) score range, then two rounds of 16-way bisection (resolution (hi - lo) / 256)
+    float lo = st.tau_f, hi = st.hi;
+    if (!(lo > -INFINITY)) {                     // first raise of this list: the range is unknown
+        lo = INFINITY; hi = -INFINITY;
         scan_list(list, L, [&](unsigned long long ent) {
             const float sc = ent_score(ent);
-            c1 += (sc >= t1); c2 += (sc >= t2); c3 += (sc >= t3); c4 += (sc >= t4);
-            c5 += (sc >= t5); c6 += (sc >= t6); c7 += (sc >= t7);
+            lo = fminf(lo, sc);
+            hi = fmaxf(hi, sc);
         });
-        float na = a, nb = t1;
-        if (c1 >= K) { na = t1; nb = t2; }
-        if (c2 >= K) { na = t2; nb = t3; }
-        if (c3 >= K) { na = t3; nb = t4; }
-        if (c4 >= K) { na = t4; nb = t5; }
-        if (c5 >= K) { na = t5; nb = t6; }
-        if (c6 >= K) { na = t6; nb = t7; }
-        if (c7 >= K) { na = t7; nb = b; }
+    }
+    float a = lo, b = hi;                       // invariant: #(score >= a) >= K  (every entry is >= lo)
+    float new_hi = -INFINITY;
+    for (int round = 0; round < 2; ++round) {
+        const float step = (b - a) * 0.0625f;
+        if (!(step > 0.f) || !isfinite(step)) break;
+        int c[15];
+#pragma unroll
+        for (int j = 0; j < 15; ++j) c[j] = 0;
+        scan_list(list, L, [&](unsigned long long ent) {
+            const float sc = ent_score(ent);
+            new_hi = fmaxf(new_hi, sc);
+#pragma unroll
+            for (int j = 0; j < 15; ++j) c[j] += (sc >= a + (float)(j + 1) * step);
+        });
+        float na = a, nb = a + step;
+#pragma unroll
+        for (int j = 0; j < 15; ++j)
+            if (c[j] >= K) { na = a + (float)(j + 1) * step; nb = (j < 14) ? a + (float)(j + 2) * step : b; }
         a = na; b = nb;
     }
+    st.hi = fmaxf(hi, new_hi);                  // scores above the old range only make the top bin fuller
     if (a > st.tau) st.tau = a;
     st.tau_f = st.tau - eps2;
     // ---- (3) compaction (order-preserving)
-    int w = 0;          // writes trail the reads (w <= e), and each batch of 8 is read before it is written
+    int w = 0;          // writes trail the reads (w <= e), and each batch of 16 is read before it is written
     scan_list(list, L, [&](unsigned long long ent) {
         if (ent_score(ent) >= st.tau_f) { list[(size_t)w * 32] = ent; ++w; }
     });
@@ -483,7 +486,7 @@ __global__ void __launch_bounds__(THREADS, 1) rank_tc_kernel(const RankTcParams 
                 st.n_ex = (int)(b - a);
             }
             st.cnt = 0; st.checked = 0;
-            st.tau = -INFINITY;
+            st.tau = -INFINITY; st.hi = -INFINITY;
             st.tau_f = valid ? -INFINITY : INFINITY;
             int flag = 0;
             float* dump_row = DUMP ? p.dump + (size_t)(valid ? row : 0) * ((size_t)p.n_it * TN) : nullptr;
@@ -513,8 +516,14 @@ __global__ void __launch_bounds__(THREADS, 1) rank_tc_kernel(const RankTcParams 
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(acc_empty + acc); mbar_arrive(bempty + bs); }
                 if (!DUMP) {
-                    // a list grows by at most HALF_N entries per stage: keep cnt <= CAP - HALF_N
-                    if (__any_sync(0xffffffffu, st.cnt >= TRIGGER)) {
+                    // Raise schedule: after stages 2, 4, 8, 16, ... for EVERY warp at once (a raise stalls the
+                    // accumulator hand-off; doing it in all warps at the same stage costs one stall instead of
+                    // eight), plus whenever a list reaches TRIGGER.  Between two scheduled raises a list gains
+                    // ~K ln 2 entries, so the lists stay short.  A list grows by at most HALF_N entries per
+                    // stage: keep cnt <= CAP - HALF_N.
+                    const int done = it + 1;
+                    const bool scheduled = done >= 2 && (done & (done - 1)) == 0;
+                    if (scheduled || __any_sync(0xffffffffu, st.cnt >= TRIGGER)) {
                         raise_threshold(st, p.topk, eps2);
                         if (st.cnt > CAP - HALF_N) { flag = 1; st.cnt = 0; st.checked = 0; st.tau_f = INFINITY; }
                     }
@@ -552,7 +561,9 @@ struct FinishParams {
 __global__ void __launch_bounds__(128) rank_tc_finish_kernel(const FinishParams p)
 {
     __shared__ unsigned long long sort_buf[2 * CAP];
+    __shared__ double su[MAX_KP];                   // the user's factors, widened once per row
     const int tid = threadIdx.x;
+    const bool vec4 = (p.k % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.V) & 15) == 0);
     for (int64_t row = blockIdx.x; row < p.n_rows; row += gridDim.x) {
         __syncthreads();
         if (p.row_flag[row * 2] | p.row_flag[row * 2 + 1]) {
@@ -580,6 +591,8 @@ __global__ void __launch_bounds__(128) rank_tc_finish_kernel(const FinishParams 
         }
         int sort_n = 32;                            // power of two >= L (padding keys are 0 = below every entry)
         while (sort_n < L) sort_n <<= 1;
+        for (int f = tid; f < p.k; f += 128) su[f] = (double)__ldg(u + f);
+        __syncthreads();
         for (int e = tid; e < sort_n; e += 128) {
             unsigned long long key = 0ull;
             if (e < L) {
@@ -596,8 +609,18 @@ __global__ void __launch_bounds__(128) rank_tc_finish_kernel(const FinishParams 
                 }
                 if (!excluded) {
                     const float* v = p.V + (size_t)id * p.k;
-                    double acc = 0.0;
-                    for (int f = 0; f < p.k; ++f) acc = fma((double)__ldg(u + f), (double)__ldg(v + f), acc);
+                    double acc = 0.0;                      // f ascending, one f64 fma per factor: == score_batch_kernel
+                    if (vec4) {
+                        for (int f = 0; f < p.k; f += 4) {
+                            const float4 x = __ldg(reinterpret_cast<const float4*>(v + f));
+                            acc = fma(su[f], (double)x.x, acc);
+                            acc = fma(su[f + 1], (double)x.y, acc);
+                            acc = fma(su[f + 2], (double)x.z, acc);
+                            acc = fma(su[f + 3], (double)x.w, acc);
+                        }
+                    } else {
+                        for (int f = 0; f < p.k; ++f) acc = fma(su[f], (double)__ldg(v + f), acc);
+                    }
                     const float base = p.item_base ? __ldg(p.item_base + id) : 0.f;
                     const float sc = __fadd_rn(__fadd_rn(base, uo), __double2float_rn(acc));      // == score_batch_kernel
                     key = ((unsigned long long)float_key(sc) << 32) | (unsigned)(0xffffffffu - (unsigned)id);

@@ -266,6 +266,47 @@ def topk_rows(scores, topk, excl_indptr=None, excl_indices=None):
     return ids, sc
 
 
+def rank_topk(U, V, topk, user_idx=None, item_base=None, user_off=None, excl_indptr=None, excl_indices=None,
+              n_items=None, workspace=None):
+    """Fused score + exclusion + top-k on device tensors (b200_rank_topk).  Returns (ids int32 [n_q, topk],
+    scores f32 [n_q, topk]) CUDA tensors ordered by (score desc, item id asc); ids are -1 padded."""
+    L = require_cuda()
+    _dev(U, torch.float32, "U"), _dev(V, torch.float32, "V")
+    n_items = V.shape[0] if n_items is None else int(n_items)
+    n_q = U.shape[0] if user_idx is None else user_idx.numel()
+    k = int(V.shape[1])
+    ids = torch.empty((n_q, topk), dtype=torch.int32, device=U.device)
+    sc = torch.empty((n_q, topk), dtype=torch.float32, device=U.device)
+    nbytes = int(L.b200_rank_topk_workspace_bytes(n_q, n_items, k, int(topk)))
+    if workspace is None or workspace.numel() < nbytes:
+        workspace = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=U.device)
+    check(L.b200_rank_topk(ptr(U), ptr(user_idx), n_q, ptr(V), n_items, k, ptr(item_base), ptr(user_off),
+                           ptr(excl_indptr), ptr(excl_indices), int(topk), ptr(ids), ptr(sc), ptr(workspace),
+                           workspace.numel(), current_stream()), "b200_rank_topk")
+    return ids, sc
+
+
+def rank_topk_host(U, V, topk, user_idx, item_base=None, excl_indptr=None, excl_indices=None, out_ids=None,
+                   out_scores=None, workspace=None):
+    """Host-buffer entry of the rank path (what the plug-ins' rank_batch calls): the factor matrices are
+    device resident (model state), the REQUEST -- user indices and the per-user sorted exclusion lists in CSR
+    form, numpy / pinned -- is copied in, ids + scores are copied back into numpy arrays."""
+    uidx = to_device(np.asarray(user_idx, dtype=np.int64), torch.int64)
+    ep = ei = None
+    if excl_indptr is not None:
+        ep = to_device(np.asarray(excl_indptr, dtype=np.int64), torch.int64)
+        ei = to_device(np.asarray(excl_indices, dtype=np.int32), torch.int32) if len(excl_indices) else \
+            torch.zeros(1, dtype=torch.int32, device="cuda")
+    ids, sc = rank_topk(U, V, topk, user_idx=uidx, item_base=item_base, excl_indptr=ep, excl_indices=ei,
+                        workspace=workspace)
+    n_q = len(user_idx)
+    out_ids = np.empty((n_q, topk), dtype=np.int32) if out_ids is None else out_ids
+    out_scores = np.empty((n_q, topk), dtype=np.float32) if out_scores is None else out_scores
+    torch.from_numpy(out_ids).copy_(ids)
+    torch.from_numpy(out_scores).copy_(sc)
+    return out_ids, out_scores
+
+
 def delta_make(x, snapshot, delta):
     L = require_cuda()
     check(L.b200_delta_make(ptr(x), ptr(snapshot), ptr(delta), x.numel(), current_stream()), "b200_delta_make")
