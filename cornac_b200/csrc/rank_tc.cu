@@ -75,6 +75,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
             : "memory");
     } while (!ok);
 }
+// same, for the two single-thread roles (TMA producer, MMA issuer): back off between polls so the
+// spinning lane does not steal issue slots from the epilogue warps that share its scheduler
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity)
+{
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok;
+    for (;;) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (ok) break;
+        __nanosleep(40);
+    }
+}
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -419,18 +437,18 @@ __global__ void __launch_bounds__(THREADS, 1) rank_tc_kernel(const RankTcParams 
         if (lane == 0) {
             uint32_t it_global = 0, tile_no = 0;
             for (int ut = blockIdx.x; ut < p.n_ut; ut += gridDim.x, ++tile_no) {
-                if (tile_no > 0) mbar_wait(u_empty, (tile_no - 1) & 1);
+                if (tile_no > 0) mbar_wait_backoff(u_empty, (tile_no - 1) & 1);
                 mbar_expect_tx(u_full, u_bytes);
                 bulk_g2s(sU, p.Upack + (size_t)ut * u_bytes, u_bytes, u_full);
                 for (int it = 0; it < p.n_it; ++it, ++it_global) {
                     const int s = it_global % NS;
                     const uint32_t round = it_global / NS;
-                    if (round > 0) mbar_wait(empty + s, (round - 1) & 1);
+                    if (round > 0) mbar_wait_backoff(empty + s, (round - 1) & 1);
                     mbar_expect_tx(full + s, v_bytes);
                     bulk_g2s(sV + (size_t)s * v_bytes, p.Vpack + (size_t)it * v_bytes, v_bytes, full + s);
                     const int bs = it_global % NB;
                     const uint32_t bround = it_global / NB;
-                    if (bround > 0) mbar_wait(bempty + bs, (bround - 1) & 1);
+                    if (bround > 0) mbar_wait_backoff(bempty + bs, (bround - 1) & 1);
                     mbar_expect_tx(bfull + bs, b_bytes);
                     bulk_g2s(sB + (size_t)bs * TN, p.base_pad + (size_t)it * TN, b_bytes, bfull + bs);
                 }
@@ -443,13 +461,13 @@ __global__ void __launch_bounds__(THREADS, 1) rank_tc_kernel(const RankTcParams 
             const uint32_t lbo = 128, sbo = (uint32_t)(kp >> 3) * 128;
             uint32_t it_global = 0, tile_no = 0;
             for (int ut = blockIdx.x; ut < p.n_ut; ut += gridDim.x, ++tile_no) {
-                mbar_wait(u_full, tile_no & 1);
+                mbar_wait_backoff(u_full, tile_no & 1);
                 for (int it = 0; it < p.n_it; ++it, ++it_global) {
                     const int s = it_global % NS;
                     const int acc = it_global & 1;
                     const uint32_t acc_round = it_global >> 1;
-                    mbar_wait(full + s, (it_global / NS) & 1);
-                    if (acc_round > 0) mbar_wait(acc_empty + acc, (acc_round - 1) & 1);
+                    mbar_wait_backoff(full + s, (it_global / NS) & 1);
+                    if (acc_round > 0) mbar_wait_backoff(acc_empty + acc, (acc_round - 1) & 1);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(sU), b_addr = smem_u32(sV + (size_t)s * v_bytes);
                     const uint32_t d_tmem = tmem_base + (uint32_t)acc * TN;

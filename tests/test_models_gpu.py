@@ -190,3 +190,27 @@ def test_wbpr_plugin_reproduces_seeded_reference_and_trains_hogwild():
     h = WBPR(k=16, max_iter=10, learning_rate=0.05, lambda_reg=0.01).fit(ds)          # Hogwild, device sampler
     assert np.isfinite(h.u_factors).all() and np.abs(h.i_factors - m.i_factors).max() < 1.0
     assert np.abs(h.i_biases).max() > 1e-3             # trained (biases start at zero)
+
+
+def test_batched_ranking_eval_equals_reference_loop():
+    """cornac_b200.evaluation.ranking_eval (one fused rank over all users + vectorised metrics)
+    returns the numbers of the reference's per-user Python loop for every top-k metric, user by user."""
+    from cornac.eval_methods.base_method import ranking_eval as ref_eval
+    from cornac.metrics import AUC, FMeasure, HitRatio, NDCG, Precision, Recall
+    from cornac_b200 import BPR, MF
+    from cornac_b200.evaluation import ranking_eval as b200_eval
+    _, train_set, test_set, _, _ = _split_sets()
+    metrics = [NDCG(k=10), Precision(k=10), Recall(k=10), FMeasure(k=10), HitRatio(k=5), Recall(k=20)]
+    for mdl in (BPR(k=10, max_iter=30, learning_rate=0.05, seed=123), MF(k=10, max_iter=20, seed=123)):
+        mdl.fit(train_set)
+        for thr in (1.0, 4.0):
+            a_avg, a_usr = ref_eval(mdl, metrics, train_set, test_set, rating_threshold=thr, exclude_unknowns=True)
+            b_avg, b_usr = b200_eval(mdl, metrics, train_set, test_set, rating_threshold=thr, exclude_unknowns=True)
+            assert np.allclose(a_avg, b_avg, rtol=1e-12, atol=1e-15), (mdl.name, thr, a_avg, b_avg)
+            for ua, ub in zip(a_usr, b_usr):
+                assert list(ua.keys()) == list(ub.keys())
+                assert np.allclose(list(ua.values()), list(ub.values()), rtol=1e-12, atol=1e-15)
+    # metrics that need full score vectors are delegated to the reference implementation
+    a = ref_eval(mdl, [AUC()], train_set, test_set, rating_threshold=4.0)[0]
+    b = b200_eval(mdl, [AUC()], train_set, test_set, rating_threshold=4.0)[0]
+    assert a == b
