@@ -237,6 +237,7 @@ def main():
     ap.add_argument("--no-rank", action="store_true")
     args = ap.parse_args()
 
+    os.environ["NCCL_DEBUG"] = os.environ.get("B200_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
     import torch
     import torch.distributed as dist
 
@@ -350,6 +351,10 @@ def main():
     if not args.no_rank and rank == 0:
         rank_metric = run_rank(W, engine, data, U, V, B, dev)
 
+    mf_metric = None
+    if not args.no_rank and rank == 0:
+        mf_metric = run_mf(W, engine, data, dev)
+
     # ---- CPU baseline on rank 0, N = 1 only
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -375,7 +380,7 @@ def main():
             "samples_per_s": round((nnz * args.steps * world) / (ms_total * 1e-3), 1),
             "skipped_frac": round(skipped_all / (nnz * args.steps * world), 5),
             "gpu_launches": args.steps * (1 + (2 * 2 if world > 1 else 0)),
-            "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "rank": rank_metric,
+            "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "rank": rank_metric, "mf": mf_metric,
         }
         if args.scale != 1.0:
             out["INVALID"] = "scaled-down debug run (--scale %g)" % args.scale
@@ -477,6 +482,40 @@ def run_rank(W, engine, data, U, V, B, dev):
             "e2e": {"value": round(n_q / (ms_h * 1e-3), 1), "unit": "users/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(n_q * topk * 8), "ms": round(ms_h, 3),
                     "path": "engine.rank_topk_host: pinned user ids + exclusion CSR -> H2D -> b200_rank_topk -> D2H ids + scores"}}
+
+
+def run_mf(W, engine, data, dev):
+    """secondary metric: MF ratings/s (b200_mf_epoch, Hogwild + atomic scatter) on the same interaction matrix
+    with synthetic ratings in {1..5}, stored by user (CSR order), k = 128 as in BASELINE.json configs[3]."""
+    import torch
+    k = 128
+    g = torch.Generator(device=dev)
+    g.manual_seed(5)
+    n = data.nnz
+    rid = data.coo_row
+    cid = data.indices
+    val = torch.randint(1, 6, (n,), generator=g, device=dev).float()
+    U = torch.randn((W["n_users"], k), generator=g, device=dev) * 0.01
+    V = torch.randn((W["n_items"], k), generator=g, device=dev) * 0.01
+    Bu, Bi = torch.zeros(W["n_users"], device=dev), torch.zeros(W["n_items"], device=dev)
+    loss = torch.zeros(1, device=dev)
+    for _ in range(2):
+        engine.mf_epoch(rid, cid, val, U, V, Bu, Bi, 0.01, 0.02, 3.0, True, loss)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        engine.mf_epoch(rid, cid, val, U, V, Bu, Bi, 0.01, 0.02, 3.0, True, loss)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    peak, _ = measured_peaks()
+    gbs = n * (16 * k + 28) / (ms * 1e-3) / 1e9
+    return {"metric": "MF ratings/sec", "value": round(n / (ms * 1e-3), 1), "unit": "ratings/s",
+            "config": "%d users x %d items x %d ratings, k=%d, use_bias, Hogwild + red.global.add" % (W["n_users"], W["n_items"], n, k),
+            "ms_per_epoch": round(ms, 3),
+            "roofline": {"bound": "hbm", "achieved": round(gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(gbs / peak, 4),
+                         "algorithmic_bytes_per_rating": 16 * k + 28}}
 
 
 def run_reference_arm(args, W):

@@ -273,6 +273,7 @@ struct RowState {
     unsigned long long* list;      // interleaved: entry e of this thread at list[e * 32]
     const int32_t* ex;
     int n_ex;
+    unsigned long long* wp;        // append position (hot loop); cnt is derived from it between stages
     int cnt;                       // entries in the list
     int checked;                   // entries [0, checked) are already exclusion-filtered
     float tau, tau_f;              // tau_f = tau - 2 eps is the filter applied to every score
@@ -369,7 +370,9 @@ __device__ __forceinline__ void raise_threshold(RowState& st, int K, float eps2)
 }
 
 // one 32-column chunk of the accumulator: add the item base and append every score above tau_f.
-// Straight-line predicated code (FSETP / @P STG / IADD): no divergence, whatever the hit rate.
+// Scores are screened four at a time: max of the four against the row's filter, one warp vote, and only
+// when some lane of the warp has a hit (a few percent of the groups once the thresholds have risen) does
+// the warp run the predicated appends for that group.  ~2 instructions per score on the common path.
 template <bool DUMP>
 __device__ __forceinline__ void epilogue_chunk(uint32_t (&r)[32], const float* __restrict__ bias, RowState& st,
                                                int32_t id0, float* __restrict__ dump_row, bool valid)
@@ -379,15 +382,21 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t (&r)[32], const float* _
         const float4 b = *reinterpret_cast<const float4*>(bias + j4 * 4);
         const float sc[4] = {__uint_as_float(r[j4 * 4 + 0]) + b.x, __uint_as_float(r[j4 * 4 + 1]) + b.y,
                              __uint_as_float(r[j4 * 4 + 2]) + b.z, __uint_as_float(r[j4 * 4 + 3]) + b.w};
+        if (DUMP) {
+            if (valid) {
 #pragma unroll
-        for (int x = 0; x < 4; ++x) {
-            if (DUMP) {
-                if (valid) dump_row[id0 + j4 * 4 + x] = sc[x];
-            } else {
-                const bool hit = sc[x] > st.tau_f;
-                unsigned long long* dst = st.list + (size_t)st.cnt * 32;
-                if (hit) *dst = ((unsigned long long)__float_as_uint(sc[x]) << 32) | (uint32_t)(id0 + j4 * 4 + x);
-                st.cnt += hit ? 1 : 0;
+                for (int x = 0; x < 4; ++x) dump_row[id0 + j4 * 4 + x] = sc[x];
+            }
+        } else {
+            const float m = fmaxf(fmaxf(sc[0], sc[1]), fmaxf(sc[2], sc[3]));
+            if (__any_sync(0xffffffffu, m > st.tau_f)) {          // warp-uniform
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    if (sc[x] > st.tau_f) {
+                        *st.wp = ((unsigned long long)__float_as_uint(sc[x]) << 32) | (uint32_t)(id0 + j4 * 4 + x);
+                        st.wp += 32;
+                    }
+                }
             }
         }
     }
@@ -518,6 +527,7 @@ __global__ void __launch_bounds__(THREADS, 1) rank_tc_kernel(const RankTcParams 
                 const int32_t item0 = it * TN + half * HALF_N;
                 const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN + half * HALF_N);
                 uint32_t r0[32], r1[32];
+                st.wp = st.list + (size_t)st.cnt * 32;
                 tmem_ld32_issue(t0, r0);
                 tmem_ld_wait(r0);
 #pragma unroll
@@ -529,6 +539,7 @@ __global__ void __launch_bounds__(THREADS, 1) rank_tc_kernel(const RankTcParams 
                     epilogue_chunk<DUMP>(r1, bias + c0 + 32, st, item0 + c0 + 32, dump_row, valid);
                     if (c0 + 64 < HALF_N) tmem_ld_wait(r0);
                 }
+                st.cnt = (int)((st.wp - st.list) >> 5);
                 // accumulator and stage are free again
                 tc_fence_before();
                 __syncwarp();

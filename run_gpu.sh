@@ -1,5 +1,5 @@
 #!/usr/bin/env bash
-# GPU trip 9: rank kernel v3 (V ring released by the tensor pipe, bias ring, batched scans) + full tests + bench
+# GPU trip 12: rank kernel v5 (vote-screened nomination), full tests, bench with MF metric
 mkdir -p gpurun_out
 python -c "
 import torch, sys
@@ -10,13 +10,9 @@ from cornac_b200 import _lib; _lib.load(); print('warm ok')
 timeout -s KILL 400 python -m pytest tests/test_rank_tc_gpu.py tests/test_rank_gpu.py -m gpu -q --timeout 120 > gpurun_out/pytest_tc.log 2>&1
 echo "pytest tc exit $?" >> gpurun_out/pytest_tc.log
 timeout -s KILL 600 python tools/tune_rank.py > gpurun_out/tune_rank.log 2>&1
-timeout -s KILL 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'rank_tc' -c 14 --csv --log-file gpurun_out/launches_rank.csv python tools/tune_rank.py > gpurun_out/tune_rank_ncu.log 2>&1
-timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k regex:rank_tc_kernel -s 5 -c 1 -f -o gpurun_out/prof_rank_tc4 python tools/tune_rank.py > gpurun_out/ncu_rank_full.log 2>&1
+timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k regex:rank_tc_kernel -s 5 -c 1 -f -o gpurun_out/prof_rank_tc5 python tools/tune_rank.py > gpurun_out/ncu_rank_full.log 2>&1
 timeout -s KILL 900 python -m pytest tests -m gpu -q --timeout 300 --deselect tests/test_rank_tc_gpu.py --deselect tests/test_rank_gpu.py > gpurun_out/pytest.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest.log
+timeout -s KILL 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
 timeout -s KILL 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err
-tail -5 gpurun_out/pytest_tc.log; cat gpurun_out/tune_rank.log; tail -5 gpurun_out/pytest.log; cat gpurun_out/bench.json | cut -c1-3000; python - <<'PY'
-import csv
-rows=[r for r in csv.reader(open('gpurun_out/launches_rank.csv')) if len(r)>14 and r[12]=='gpu__time_duration.sum']
-for r in rows[:12]: print(r[4][:50], r[8], r[14])
-PY
+tail -4 gpurun_out/pytest_tc.log; cat gpurun_out/tune_rank.log; tail -4 gpurun_out/pytest.log; tail -2 gpurun_out/smoke.log; cat gpurun_out/bench.json | cut -c1-200; tail -3 gpurun_out/bench.err

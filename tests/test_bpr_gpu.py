@@ -287,3 +287,25 @@ def test_hogwild_weighted_negatives_follow_item_popularity():
     c_ref, s_ref = O.bpr_replay(ii, indices[jidx], indptr, indices, U0.copy(), V0.copy(), B0.copy(), 0.0, 0.01, True)
     c, s = stats.cpu().tolist()
     assert s == s_ref and s > 0.02 * n and abs(c - c_ref) <= 5        # popular negatives are skipped far more often
+
+
+def test_sharded_fit_entry_single_process_and_host_rank_entry():
+    """parallel.bpr_fit_sharded with one process == engine.bpr_train_host on the whole matrix (same Philox key
+    layout), and engine.rank_topk_host == oracle on the trained factors."""
+    from cornac_b200 import engine, parallel
+    indptr, indices = synth_csr(3000, 1200, 40000, seed=21)
+    k = 32
+    _, U0, V0, B0 = O.bpr_init(3, 3000, 1200, k)
+    Ua, Va, Ba = U0.copy(), V0.copy(), B0.copy()
+    bounds, hist = parallel.bpr_fit_sharded(indptr, indices, 1200, Ua, Va, Ba, 0.05, 0.01, True, max_iter=3, key=5)
+    assert bounds.tolist() == [0, 3000] and len(hist) == 3
+    assert np.abs(Ua - U0).max() > 1e-4 and np.isfinite(Va).all()
+    dU, dV, dB = _dev(Ua), _dev(Va), _dev(Ba)
+    users = np.arange(0, 3000, 7, dtype=np.int64)
+    ex_ptr = np.concatenate([[0], np.cumsum(np.diff(indptr)[users])]).astype(np.int64)
+    ex_idx = np.concatenate([indices[indptr[u]:indptr[u + 1]] for u in users]).astype(np.int32)
+    ids, sc = engine.rank_topk_host(dU, dV, 10, users, item_base=dB, excl_indptr=ex_ptr, excl_indices=ex_idx)
+    want = O.score_batch(Ua[users], Va, Ba)
+    for q, u in enumerate(users):
+        wi, ws, _ = O.topk(want[q], 10, indices[indptr[u]:indptr[u + 1]])
+        assert np.array_equal(ids[q], wi) and np.array_equal(sc[q], ws)
