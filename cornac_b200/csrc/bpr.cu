@@ -45,6 +45,7 @@ struct BprParams {
     int64_t n_samples;
     int64_t max_groups;          // cap on concurrently running samples (Hogwild staleness bound)
     int exact_exp;               // B200_SGD_EXACT_EXP
+    int debug_skip;              // profiling only (B200_BPR_DEBUG_SKIP): bit0 U, bit1 V+, bit2 V- scatter off
     int neg_weighted;            // WBPR: negatives drawn from the interaction list (popularity-weighted)
     float* U;
     float* V;
@@ -302,9 +303,9 @@ __global__ void __launch_bounds__(256, MINB) bpr_hogwild_chunk_kernel(const BprP
                     di.v[e] = lr * (z * uf - reg * vi);
                     dj.v[e] = lr * (-z * uf - reg * vj);
                 }
-                row_red_add<G, NPL, VEC>(du, pu, lg, n_units);
-                row_red_add<G, NPL, VEC>(di, pi, lg, n_units);
-                row_red_add<G, NPL, VEC>(dj, pj, lg, n_units);
+                if (!(p.debug_skip & 1)) row_red_add<G, NPL, VEC>(du, pu, lg, n_units);
+                if (!(p.debug_skip & 2)) row_red_add<G, NPL, VEC>(di, pi, lg, n_units);
+                if (!(p.debug_skip & 4)) row_red_add<G, NPL, VEC>(dj, pj, lg, n_units);
                 if (p.use_bias && lg == 0) {
                     red_add_f32(p.B + ci[cur], lr * (z - reg * bi[cur]));
                     red_add_f32(p.B + cj[cur], lr * (-z - reg * bj[cur]));
@@ -592,6 +593,8 @@ extern "C" int b200_bpr_epoch(const int32_t* pairs, const uint64_t* table, int64
         if (flags & B200_SGD_UNBOUNDED) p.max_groups = INT64_MAX / 1024;
     }
     p.neg_weighted = (flags & B200_BPR_NEG_WEIGHTED) ? 1 : 0;
+    p.debug_skip = 0;
+    if (const char* e = getenv("B200_BPR_DEBUG_SKIP")) p.debug_skip = atoi(e);
     p.U = U; p.V = V; p.B = B; p.k = k; p.lr = lr; p.reg = reg; p.use_bias = use_bias;
     p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32);
     p.epoch_lo = (uint32_t)epoch; p.epoch_hi = (uint32_t)(epoch >> 32);

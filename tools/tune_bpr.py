@@ -33,6 +33,8 @@ def main():
     configs = [("chunk minb4 thr=%d blk=%d" % (thr, blk), "0,%d,%d" % (thr, blk), 1) for thr in (256, 128) for blk in (0, 3, 2)]
     configs += [("chunk minb3 thr=256", "16,256,0", 1), ("old S=1 thr=256 blk=4", "1,256,4", 1), ("old S=1 thr=128", "1,128,0", 1),
                 ("chunk minb4 plain-stores", "0,256,0", 0)]
+    if os.environ.get("B200_TUNE_EXPERIMENT"):
+        configs = [("default", "0,256,0", 1)]
     for name, tune, at in configs:
         os.environ["B200_BPR_TUNE"] = tune
         for e in range(2):
