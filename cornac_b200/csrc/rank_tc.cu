@@ -273,6 +273,8 @@ struct RowState {
     unsigned long long* list;      // interleaved: entry e of this thread at list[e * 32]
     const int32_t* ex;
     int n_ex;
+    int ex_c;                      // exclusion cursor: entries [0, ex_c) have been loaded into the window
+    int32_t ex_w0, ex_w1, ex_w2, ex_w3;   // next excluded ids (sorted), 0x7fffffff = none
     unsigned long long* wp;        // append position (hot loop); cnt is derived from it between stages
     int cnt;                       // entries in the list
     int checked;                   // entries [0, checked) are already exclusion-filtered
@@ -300,27 +302,38 @@ __device__ __forceinline__ void scan_list(const unsigned long long* list, int L,
 // memory, so the lock-step scans are coalesced).  Steps: (1) merge the new tail of the list against
 // the user's exclusion list and drop excluded items; (2) two rounds of 16-way bisection on the score
 // range for the largest t with #(score >= t) >= K; (3) drop entries below tau - 2 eps.
-__device__ __forceinline__ void raise_threshold(RowState& st, int K, float eps2)
+__device__ __forceinline__ void raise_threshold(RowState& st, int K, float eps2, uint32_t tile,
+                                                unsigned long long* my_tau, const unsigned long long* sibling_tau)
 {
     unsigned long long* __restrict__ list = st.list;
-    // ---- (1) exclusion merge over entries [checked, cnt)
+    // The other column half of this row publishes its own lower bound of the row's k-th best score; any
+    // such bound (even an old one) is valid for the whole row, so take the larger of the two.  The tag
+    // rejects a value the sibling warp left behind from the previous user tile.
+    {
+        const unsigned long long v = *reinterpret_cast<const volatile unsigned long long*>(sibling_tau);
+        const float other = __uint_as_float((unsigned)(v & 0xffffffffull));
+        if ((uint32_t)(v >> 32) == tile && other > st.tau) { st.tau = other; st.tau_f = other - eps2; }
+    }
+    // ---- (1) exclusion merge over entries [checked, cnt).  The list tail is sorted by id and every
+    //      id in it is larger than anything merged before, so one cursor walks the exclusion list once
+    //      per sweep; it is read four entries per round trip (independent loads) into a register window.
     if (st.n_ex > 0 && st.checked < st.cnt) {
-        int w = st.checked, c = 0;
-        {   // lower_bound(ex, first new id)
-            const int32_t first = (int32_t)(list[(size_t)st.checked * 32] & 0xffffffffull);
-            int lo = 0, hi = st.n_ex;
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (__ldg(st.ex + mid) < first) lo = mid + 1; else hi = mid;
-            }
-            c = lo;
-        }
-        int32_t ex_next = c < st.n_ex ? __ldg(st.ex + c) : 0x7fffffff;
+        int w = st.checked;
         for (int e = st.checked; e < st.cnt; ++e) {
             const unsigned long long ent = list[(size_t)e * 32];
             const int32_t id = (int32_t)(ent & 0xffffffffull);
-            while (ex_next < id) { ++c; ex_next = c < st.n_ex ? __ldg(st.ex + c) : 0x7fffffff; }
-            if (ex_next != id) { list[(size_t)w * 32] = ent; ++w; }
+            while (st.ex_w0 < id) {                       // advance the window past ids below `id`
+                st.ex_w0 = st.ex_w1; st.ex_w1 = st.ex_w2; st.ex_w2 = st.ex_w3; st.ex_w3 = 0x7fffffff;
+                if (st.ex_w0 == 0x7fffffff && st.ex_c < st.n_ex) {      // window empty: refill
+                    const int c = st.ex_c;
+                    st.ex_w0 = __ldg(st.ex + c);
+                    st.ex_w1 = c + 1 < st.n_ex ? __ldg(st.ex + c + 1) : 0x7fffffff;
+                    st.ex_w2 = c + 2 < st.n_ex ? __ldg(st.ex + c + 2) : 0x7fffffff;
+                    st.ex_w3 = c + 3 < st.n_ex ? __ldg(st.ex + c + 3) : 0x7fffffff;
+                    st.ex_c = c + 4;
+                }
+            }
+            if (st.ex_w0 != id) { list[(size_t)w * 32] = ent; ++w; }
         }
         st.cnt = w;
     }
@@ -360,6 +373,7 @@ __device__ __forceinline__ void raise_threshold(RowState& st, int K, float eps2)
     st.hi = fmaxf(hi, new_hi);                  // scores above the old range only make the top bin fuller
     if (a > st.tau) st.tau = a;
     st.tau_f = st.tau - eps2;
+    *reinterpret_cast<volatile unsigned long long*>(my_tau) = ((unsigned long long)tile << 32) | __float_as_uint(st.tau);
     // ---- (3) compaction (order-preserving)
     int w = 0;          // writes trail the reads (w <= e), and each batch of 16 is read before it is written
     scan_list(list, L, [&](unsigned long long ent) {
@@ -422,6 +436,8 @@ __global__ void __launch_bounds__(THREADS, 1) rank_tc_kernel(const RankTcParams 
     uint64_t* bfull = bars + 14;      // [NB] item-base slice landed         TMA -> epilogue
     uint64_t* bempty = bars + 18;     // [NB] slice consumed                 8 epilogue warps -> TMA
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 22);
+    // [2 halves][TM rows] last published row threshold, tagged with the tile it belongs to: (tile << 32) | f32 bits
+    unsigned long long* tau_share = reinterpret_cast<unsigned long long*>(bars + 24);
     // The V ring is released by the tensor pipe alone, so the TMA producer runs NS tiles ahead of
     // the MMAs whatever the epilogue does; the (tiny) item-base ring is what the epilogue releases.
 
@@ -506,14 +522,23 @@ __global__ void __launch_bounds__(THREADS, 1) rank_tc_kernel(const RankTcParams 
             const float eps2 = 2.f * eps;
             RowState st;
             st.list = p.lists + ((size_t)(ut * EPI_WARPS + half * 4 + q) * CAP) * 32 + lane;
-            st.ex = nullptr; st.n_ex = 0;
+            st.ex = nullptr; st.n_ex = 0; st.ex_c = 0;
+            st.ex_w0 = st.ex_w1 = st.ex_w2 = st.ex_w3 = 0x7fffffff;
             if (valid && p.excl_indptr) {
                 const int64_t a = p.excl_indptr[row], b = p.excl_indptr[row + 1];
                 st.ex = p.excl_indices + a;
                 st.n_ex = (int)(b - a);
+                if (st.n_ex > 0) {                         // first window (ids are < 0x7fffffff by construction)
+                    st.ex_w0 = __ldg(st.ex);
+                    st.ex_w1 = 1 < st.n_ex ? __ldg(st.ex + 1) : 0x7fffffff;
+                    st.ex_w2 = 2 < st.n_ex ? __ldg(st.ex + 2) : 0x7fffffff;
+                    st.ex_w3 = 3 < st.n_ex ? __ldg(st.ex + 3) : 0x7fffffff;
+                    st.ex_c = 4;
+                }
             }
             st.cnt = 0; st.checked = 0;
             st.tau = -INFINITY; st.hi = -INFINITY;
+            tau_share[half * TM + q * 32 + lane] = ((unsigned long long)(uint32_t)ut << 32) | 0xff800000u;   // -inf
             st.tau_f = valid ? -INFINITY : INFINITY;
             int flag = 0;
             float* dump_row = DUMP ? p.dump + (size_t)(valid ? row : 0) * ((size_t)p.n_it * TN) : nullptr;
@@ -553,7 +578,8 @@ __global__ void __launch_bounds__(THREADS, 1) rank_tc_kernel(const RankTcParams 
                     const int done = it + 1;
                     const bool scheduled = done >= 2 && (done & (done - 1)) == 0;
                     if (scheduled || __any_sync(0xffffffffu, st.cnt >= TRIGGER)) {
-                        raise_threshold(st, p.topk, eps2);
+                        raise_threshold(st, p.topk, eps2, (uint32_t)ut, tau_share + half * TM + q * 32 + lane,
+                                        tau_share + (1 - half) * TM + q * 32 + lane);
                         if (st.cnt > CAP - HALF_N) { flag = 1; st.cnt = 0; st.checked = 0; st.tau_f = INFINITY; }
                     }
                 }
@@ -720,7 +746,7 @@ static Layout make_layout(int64_t n_q, int64_t n_items, int k)
 static size_t smem_bytes_for(int kp)
 {
     const int NS = num_stages(kp);
-    return (size_t)TM * kp * 2 + (size_t)NS * (TN * kp * 2) + (size_t)NB * TN * 4 + 32 * 8 + 1024;
+    return (size_t)TM * kp * 2 + (size_t)NS * (TN * kp * 2) + (size_t)NB * TN * 4 + 32 * 8 + 2 * TM * 8 + 1024;
 }
 
 }  // namespace tc

@@ -1,5 +1,5 @@
 #!/usr/bin/env bash
-# GPU trip 13: BPR scatter experiments + C5-shape ncu capture of the rank kernel
+# GPU trip 14: rank kernel v6 (windowed exclusion cursor, shared row thresholds) tests + C5 launch breakdown
 mkdir -p gpurun_out
 python -c "
 import torch, sys
@@ -7,6 +7,12 @@ sys.path.insert(0, '.')
 torch.zeros(1).cuda(); torch.cuda.synchronize()
 from cornac_b200 import _lib; _lib.load(); print('warm ok')
 " > gpurun_out/warm.log 2>&1
-timeout -s KILL 900 bash tools/bpr_experiments.sh > gpurun_out/bpr_experiments.log 2>&1
-timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k regex:rank_tc_kernel -s 21 -c 1 -f -o gpurun_out/prof_rank_tc_c5 python tools/tune_rank.py > gpurun_out/ncu_rank_c5.log 2>&1
-cat gpurun_out/bpr_experiments.log; tail -3 gpurun_out/ncu_rank_c5.log
+timeout -s KILL 400 python -m pytest tests/test_rank_tc_gpu.py tests/test_rank_gpu.py tests/test_models_gpu.py -m gpu -q --timeout 120 > gpurun_out/pytest_tc.log 2>&1
+echo "pytest tc exit $?" >> gpurun_out/pytest_tc.log
+timeout -s KILL 600 python tools/tune_rank.py > gpurun_out/tune_rank.log 2>&1
+timeout -s KILL 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'rank_tc|pack_|norm_|base_pad' -s 140 -c 14 --csv --log-file gpurun_out/launches_rank_c5.csv python tools/tune_rank.py > gpurun_out/tune_rank_ncu.log 2>&1
+tail -4 gpurun_out/pytest_tc.log; cat gpurun_out/tune_rank.log; python - <<'PY'
+import csv
+rows=[r for r in csv.reader(open('gpurun_out/launches_rank_c5.csv')) if len(r)>14 and r[12]=='gpu__time_duration.sum']
+for r in rows[:14]: print(r[4][:50], r[8], r[14])
+PY
