@@ -666,12 +666,22 @@ __global__ void __launch_bounds__(128) rank_tc_finish_kernel(const FinishParams 
                     const float* v = p.V + (size_t)id * p.k;
                     double acc = 0.0;                      // f ascending, one f64 fma per factor: == score_batch_kernel
                     if (vec4) {
-                        for (int f = 0; f < p.k; f += 4) {
-                            const float4 x = __ldg(reinterpret_cast<const float4*>(v + f));
-                            acc = fma(su[f], (double)x.x, acc);
-                            acc = fma(su[f + 1], (double)x.y, acc);
-                            acc = fma(su[f + 2], (double)x.z, acc);
-                            acc = fma(su[f + 3], (double)x.w, acc);
+                        // the row gather is latency bound: keep 8 independent 16-byte loads in flight
+                        for (int f = 0; f < p.k; f += 32) {
+                            float4 x[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                x[i] = (f + 4 * i < p.k) ? __ldg(reinterpret_cast<const float4*>(v + f + 4 * i))
+                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                if (f + 4 * i < p.k) {
+                                    acc = fma(su[f + 4 * i], (double)x[i].x, acc);
+                                    acc = fma(su[f + 4 * i + 1], (double)x[i].y, acc);
+                                    acc = fma(su[f + 4 * i + 2], (double)x[i].z, acc);
+                                    acc = fma(su[f + 4 * i + 3], (double)x[i].w, acc);
+                                }
+                            }
                         }
                     } else {
                         for (int f = 0; f < p.k; ++f) acc = fma(su[f], (double)__ldg(v + f), acc);
@@ -778,7 +788,10 @@ static int pack_items(const float* V, int64_t n_items, int k, const float* item_
     B200_CUDA(cudaMemsetAsync(ws + L.off_scal, 0, 64, st));
     const int grid = sm_count() * 8;
     pack_kernel<TN><<<grid, 256, 0, st>>>(V, nullptr, n_items, n_pad, k, L.kp, ws + L.off_vpack);
-    norm_kernel<<<grid, 256, 0, st>>>(V, nullptr, n_items, k, nullptr, reinterpret_cast<unsigned int*>(ws + L.off_scal));
+    // one warp per row and a row is only 4k bytes: launch enough warps to cover the latency
+    const int64_t ngrid = (n_items + 7) / 8 < (1 << 20) ? (n_items + 7) / 8 : (1 << 20);
+    norm_kernel<<<(unsigned)(ngrid < grid ? grid : ngrid), 256, 0, st>>>(V, nullptr, n_items, k, nullptr,
+                                                                        reinterpret_cast<unsigned int*>(ws + L.off_scal));
     base_pad_kernel<<<grid, 256, 0, st>>>(item_base, n_items, n_pad, reinterpret_cast<float*>(ws + L.off_base),
                                           reinterpret_cast<unsigned int*>(ws + L.off_scal) + 1);
     B200_CUDA(cudaGetLastError());
