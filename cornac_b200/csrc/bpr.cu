@@ -420,33 +420,33 @@ __global__ void __launch_bounds__(32) bpr_replay_kernel(const ReplayParams p)
 }
 
 // ---------------------------------------------------------------------------------------
-// b200_bpr_prepare: CSR -> (pairs, membership table).  One thread per interaction.
+// b200_bpr_prepare: CSR -> (pairs, membership table).  One warp per user row (lanes stride over the row's
+// interactions): the user id is the row index, no search; the cost is the random 8-byte CAS per interaction.
 __global__ void bpr_prepare_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                                    int64_t n_users, int64_t nnz, int2* __restrict__ pairs,
                                    unsigned long long* __restrict__ table, uint64_t bucket_mask)
 {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) {
-        // user of interaction e: last row with indptr[row] <= e  (COO row, recom_bpr.pyx:154-161)
-        int64_t lo = 0, hi = n_users;
-        while (lo < hi) {
-            const int64_t mid = (lo + hi) >> 1;
-            if ((int64_t)__ldg(indptr + mid + 1) <= e) lo = mid + 1; else hi = mid;
-        }
-        const int32_t u = (int32_t)lo, i = __ldg(indices + e);
-        pairs[e] = make_int2(u, i);
-        const unsigned long long key = ((unsigned long long)(uint32_t)u << 32) | (uint32_t)i;
-        uint64_t b = mix64(key) & bucket_mask;
-        for (;;) {
-            bool done = false;
-            for (int sl = 0; sl < 4 && !done; ++sl) {
-                const unsigned long long old = atomicCAS(table + 4 * b + sl, TABLE_EMPTY, key);
-                done = (old == TABLE_EMPTY) || (old == key);
+    const int lane = threadIdx.x & 31;
+    const int64_t wstride = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t u = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); u < n_users; u += wstride) {
+        const int64_t lo = __ldg(indptr + u), hi = __ldg(indptr + u + 1);
+        for (int64_t e = lo + lane; e < hi; e += 32) {
+            const int32_t i = __ldg(indices + e);
+            pairs[e] = make_int2((int32_t)u, i);                    // COO row = user_ids of recom_bpr.pyx:154-161
+            const unsigned long long key = ((unsigned long long)(uint32_t)u << 32) | (uint32_t)i;
+            uint64_t b = mix64(key) & bucket_mask;
+            for (;;) {
+                bool done = false;
+                for (int sl = 0; sl < 4 && !done; ++sl) {
+                    const unsigned long long old = atomicCAS(table + 4 * b + sl, TABLE_EMPTY, key);
+                    done = (old == TABLE_EMPTY) || (old == key);
+                }
+                if (done) break;
+                b = (b + 1) & bucket_mask;
             }
-            if (done) break;
-            b = (b + 1) & bucket_mask;
         }
     }
+    (void)nnz;
 }
 
 static int64_t table_buckets_for(int64_t nnz)
@@ -555,8 +555,9 @@ extern "C" int b200_bpr_prepare(const int32_t* indptr, const int32_t* indices, i
     B200_CUDA(cudaMemsetAsync(table, 0xff, (size_t)table_slots * sizeof(uint64_t), st));
     if (nnz == 0) return B200_OK;
     const uint64_t mask = (uint64_t)(table_slots / 4) - 1;
-    int64_t grid = (nnz + 255) / 256;
-    if (grid > (int64_t)sm_count() * 16) grid = (int64_t)sm_count() * 16;
+    int64_t grid = (n_users + 7) / 8;                               // 8 warps (rows) per block
+    if (grid > (int64_t)sm_count() * 32) grid = (int64_t)sm_count() * 32;
+    if (grid < 1) grid = 1;
     bpr_prepare_kernel<<<(unsigned)grid, 256, 0, st>>>(indptr, indices, n_users, nnz, reinterpret_cast<int2*>(pairs),
                                                        reinterpret_cast<unsigned long long*>(table), mask);
     B200_CUDA(cudaGetLastError());

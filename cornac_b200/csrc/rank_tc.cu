@@ -226,7 +226,9 @@ __global__ void norm_kernel(const float* __restrict__ src, const int64_t* __rest
         const float nrm = sqrtf(s) * 1.0001f;
         if (lane == 0) {
             if (norm_out) norm_out[row] = nrm;
-            if (max_out) atomicMax(max_out, __float_as_uint(nrm));
+            // one shared maximum: look before the atomic, or a million rows serialise on one address
+            if (max_out && __float_as_uint(nrm) > *reinterpret_cast<volatile unsigned int*>(max_out))
+                atomicMax(max_out, __float_as_uint(nrm));
         }
     }
 }

@@ -136,7 +136,16 @@ def bpr_train_host(indptr, indices, n_neg, U, V, B, lr, reg, use_bias, max_iter,
     require_cuda()
     data = BprData.from_host(indptr, indices)
     nnz = data.nnz
-    dU, dV, dB = to_device(U, torch.float32), to_device(V, torch.float32), to_device(B, torch.float32)
+    if replay_seeds is None and weighted_seed is None:
+        data.prepare()                  # pair store + membership table: runs while the factors are still copying
+    # the factor matrices go up on a side stream so that the copy engine overlaps b200_bpr_prepare
+    main = torch.cuda.current_stream()
+    side = _copy_stream()               # no dependency on `main`: the uploads may start right away
+    with torch.cuda.stream(side):
+        dU, dV, dB = to_device(U, torch.float32), to_device(V, torch.float32), to_device(B, torch.float32)
+    main.wait_stream(side)
+    for t in (dU, dV, dB):
+        t.record_stream(main)
     stats = torch.zeros(2, dtype=torch.int64, device="cuda")
     lr, reg = float(np.float32(lr)), float(np.float32(reg))
     history = []
@@ -188,6 +197,16 @@ def bpr_train_host(indptr, indices, n_neg, U, V, B, lr, reg, use_bias, max_iter,
     for host, dev in ((U, dU), (V, dV), (B, dB)):
         _to_host_into(host, dev)
     return history, ((dU, dV, dB) if keep_device else None)
+
+
+_COPY_STREAMS = {}
+
+
+def _copy_stream():
+    dev = torch.cuda.current_device()
+    if dev not in _COPY_STREAMS:
+        _COPY_STREAMS[dev] = torch.cuda.Stream(device=dev)
+    return _COPY_STREAMS[dev]
 
 
 def _to_host_into(host, dev):
