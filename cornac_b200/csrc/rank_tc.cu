@@ -843,7 +843,8 @@ int rank_tc(const float* U, const int64_t* user_idx, int64_t n_q, const float* V
         f.excl_indptr = p.excl_indptr; f.excl_indices = p.excl_indices;
         f.out_ids = out_ids + (size_t)q0 * topk; f.out_scores = out_scores + (size_t)q0 * topk;
         f.overflow_rows = reinterpret_cast<int*>(ws + L.off_over);
-        const int fgrid = (int)(rows < (int64_t)sm_count() * 8 ? rows : (int64_t)sm_count() * 8);
+        // latency-bound gathers: as many rows in flight per SM as the thread limit allows (16 x 128 threads)
+        const int fgrid = (int)(rows < (int64_t)sm_count() * 16 ? rows : (int64_t)sm_count() * 16);
         rank_tc_finish_kernel<<<fgrid, 128, 0, st>>>(f);
         B200_CUDA(cudaGetLastError());
         // rows whose candidate list overflowed: exact path, one row at a time (rare; needs the count on the host)
