@@ -8,7 +8,7 @@ Layers:  include/b200cornac.h (C ABI)  <-  cornac_b200/csrc (CUDA)  <-  cornac_b
 plug-ins).  The plug-in classes need the `cornac` package importable (they subclass its
 Recommender so that cornac.Experiment accepts them); the engine does not.
 """
-__all__ = ["BPR", "WBPR", "MF", "engine", "B200Error"]
+__all__ = ["BPR", "WBPR", "MMMF", "MF", "engine", "B200Error"]
 
 from ._lib import B200Error  # noqa: F401
 
@@ -20,6 +20,9 @@ def __getattr__(name):
     if name == "WBPR":
         from .recom_bpr import WBPR
         return WBPR
+    if name == "MMMF":
+        from .recom_bpr import MMMF
+        return MMMF
     if name == "MF":
         from .recom_mf import MF
         return MF

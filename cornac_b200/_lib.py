@@ -30,7 +30,7 @@ SIGNATURES = {
                               _u64, _u64, _u64, _c.c_uint, _vp, _vp]),
     "b200_bpr_draw_host": (_int, [_u64, _u64, _u64, _i64, _i64, _i64, _vp, _vp]),
     "b200_bpr_epoch_replay": (_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _int, _f32, _f32, _int,
-                                     _vp, _vp]),
+                                     _c.c_uint, _vp, _vp]),
     "b200_mt_sampler_create": (_vp, [_u32]),
     "b200_mt_sampler_destroy": (None, [_vp]),
     "b200_mt_sampler_fill_i64": (_int, [_vp, _i64, _i64, _vp]),
@@ -51,6 +51,7 @@ SGD_ATOMIC = 1
 SGD_EXACT_EXP = 2
 SGD_UNBOUNDED = 4
 BPR_NEG_WEIGHTED = 8
+BPR_LOSS_HINGE = 16
 
 _lib = None
 

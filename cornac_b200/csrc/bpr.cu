@@ -46,6 +46,7 @@ struct BprParams {
     int64_t max_groups;          // cap on concurrently running samples (Hogwild staleness bound)
     int exact_exp;               // B200_SGD_EXACT_EXP
     int debug_skip;              // profiling only (B200_BPR_DEBUG_SKIP): bit0 U, bit1 V+, bit2 V- scatter off
+    int hinge;                   // MMMF (recom_mmmf.pyx:129-154): skip correctly ranked pairs, z = 1 otherwise
     int neg_weighted;            // WBPR: negatives drawn from the interaction list (popularity-weighted)
     float* U;
     float* V;
@@ -151,8 +152,14 @@ __global__ void __launch_bounds__(256, MINB) bpr_hogwild_kernel(const BprParams 
             for (int e = 0; e < E; ++e) part = fmaf(fu[t].v[e], fi[t].v[e] - fj[t].v[e], part);
             const float score = (bi[t] - bj[t]) + group_sum<G>(part);
             if (!live[t]) continue;     // group-uniform
-            const float z = bpr_z(score, p.exact_exp);
-            n_correct += (z < .5f);
+            float z;
+            if (p.hinge) {
+                if (score > 0.f) { ++n_correct; continue; }
+                z = 1.f;
+            } else {
+                z = bpr_z(score, p.exact_exp);
+                n_correct += (z < .5f);
+            }
             const float lr = p.lr, reg = p.reg;
             float* pu = p.U + (size_t)u[t] * k;
             float* pi = p.V + (size_t)it[t] * k;
@@ -289,8 +296,14 @@ __global__ void __launch_bounds__(256, MINB) bpr_hogwild_chunk_kernel(const BprP
 #pragma unroll
             for (int e = 0; e < E; ++e) part = fmaf(fu[cur].v[e], fi[cur].v[e] - fj[cur].v[e], part);
             const float score = (bi[cur] - bj[cur]) + group_sum<G>(part);      // recom_bpr.pyx:249-251
-            const float z = bpr_z(score, p.exact_exp);
-            n_correct += (z < .5f);
+            float z;
+            if (p.hinge) {                              // recom_mmmf.pyx:137-139
+                if (score > 0.f) { ++n_correct; continue; }
+                z = 1.f;
+            } else {
+                z = bpr_z(score, p.exact_exp);
+                n_correct += (z < .5f);
+            }
             float* pu = p.U + (size_t)cu[cur] * k;
             float* pi = p.V + (size_t)ci[cur] * k;
             float* pj = p.V + (size_t)cj[cur] * k;
@@ -362,6 +375,7 @@ struct ReplayParams {
     int k;
     float lr, reg;
     int use_bias;
+    int hinge;
     unsigned long long* stats;
 };
 
@@ -397,8 +411,14 @@ __global__ void __launch_bounds__(32) bpr_replay_kernel(const ReplayParams p)
             for (int f = lane; f < p.k; f += 32)
                 part = __fadd_rn(part, __fmul_rn(__ldcg(pu + f), __fsub_rn(__ldcg(pi + f), __ldcg(pj + f))));
             const float score = __fadd_rn(__fsub_rn(bi, bj), group_sum<32>(part));
-            const float z = (float)(1.0 / (1.0 + exp((double)score)));
-            n_correct += (z < .5f);
+            float z;
+            if (p.hinge) {                              // recom_mmmf.pyx:137-139 (warp-uniform)
+                if (score > 0.f) { ++n_correct; continue; }
+                z = 1.f;
+            } else {
+                z = (float)(1.0 / (1.0 + exp((double)score)));
+                n_correct += (z < .5f);
+            }
             const float lr = p.lr, reg = p.reg;
             for (int f = lane; f < p.k; f += 32) {
                 const float uf = __ldcg(pu + f), vi = __ldcg(pi + f), vj = __ldcg(pj + f);
@@ -594,6 +614,8 @@ extern "C" int b200_bpr_epoch(const int32_t* pairs, const uint64_t* table, int64
         if (flags & B200_SGD_UNBOUNDED) p.max_groups = INT64_MAX / 1024;
     }
     p.neg_weighted = (flags & B200_BPR_NEG_WEIGHTED) ? 1 : 0;
+    p.hinge = (flags & B200_BPR_LOSS_HINGE) ? 1 : 0;
+    if (p.hinge) p.use_bias = 1;
     p.debug_skip = 0;
     if (const char* e = getenv("B200_BPR_DEBUG_SKIP")) p.debug_skip = atoi(e);
     p.U = U; p.V = V; p.B = B; p.k = k; p.lr = lr; p.reg = reg; p.use_bias = use_bias;
@@ -618,7 +640,7 @@ extern "C" int b200_bpr_epoch(const int32_t* pairs, const uint64_t* table, int64
 extern "C" int b200_bpr_epoch_replay(const int64_t* i_index, const int32_t* j_id, int64_t n_samples,
                                      const int32_t* indptr, const int32_t* indices, const int32_t* coo_row,
                                      float* U, float* V, float* B, int k,
-                                     float lr, float reg, int use_bias,
+                                     float lr, float reg, int use_bias, unsigned flags,
                                      int64_t* stats, void* stream)
 {
     B200_REQUIRE(i_index && j_id && indptr && indices && coo_row && U && V && B && stats,
@@ -629,6 +651,8 @@ extern "C" int b200_bpr_epoch_replay(const int64_t* i_index, const int32_t* j_id
     p.i_index = i_index; p.j_id = j_id; p.n_samples = n_samples;
     p.indptr = indptr; p.indices = indices; p.coo_row = coo_row;
     p.U = U; p.V = V; p.B = B; p.k = k; p.lr = lr; p.reg = reg; p.use_bias = use_bias;
+    p.hinge = (flags & B200_BPR_LOSS_HINGE) ? 1 : 0;
+    if (p.hinge) p.use_bias = 1;
     p.stats = reinterpret_cast<unsigned long long*>(stats);
     bpr_replay_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(p);
     B200_CUDA(cudaGetLastError());

@@ -81,7 +81,7 @@ class BprData:
 
 
 def bpr_epoch(data, n_neg, U, V, B, lr, reg, use_bias, seed, epoch, stats, n_samples=None,
-              sample_base=0, atomic=True, exact_exp=False, unbounded=False, neg_weighted=False):
+              sample_base=0, atomic=True, exact_exp=False, unbounded=False, neg_weighted=False, hinge=False):
     """One Hogwild BPR epoch on the current stream; `stats` (int64[2] CUDA) accumulates
     (correct, skipped)."""
     L = require_cuda()
@@ -89,7 +89,8 @@ def bpr_epoch(data, n_neg, U, V, B, lr, reg, use_bias, seed, epoch, stats, n_sam
     _dev(U, torch.float32, "U"), _dev(V, torch.float32, "V"), _dev(B, torch.float32, "B")
     _dev(stats, torch.int64, "stats")
     flags = ((_lib.SGD_ATOMIC if atomic else 0) | (_lib.SGD_EXACT_EXP if exact_exp else 0)
-             | (_lib.SGD_UNBOUNDED if unbounded else 0) | (_lib.BPR_NEG_WEIGHTED if neg_weighted else 0))
+             | (_lib.SGD_UNBOUNDED if unbounded else 0) | (_lib.BPR_NEG_WEIGHTED if neg_weighted else 0)
+             | (_lib.BPR_LOSS_HINGE if hinge else 0))
     n = data.nnz if n_samples is None else int(n_samples)
     data.prepare()
     check(L.b200_bpr_epoch(ptr(data.pairs), ptr(data.table), data.table.numel(), data.nnz, data.n_users, int(n_neg), n,
@@ -108,20 +109,21 @@ def bpr_draw_host(seed, epoch, n, nnz, n_neg, sample_base=0):
     return ii, jj
 
 
-def bpr_epoch_replay(data, i_index, j_id, U, V, B, lr, reg, use_bias, stats):
+def bpr_epoch_replay(data, i_index, j_id, U, V, B, lr, reg, use_bias, stats, hinge=False):
     """Serial-equivalent application of an explicit sample stream (parity mode)."""
     L = require_cuda()
     _dev(i_index, torch.int64, "i_index"), _dev(j_id, torch.int32, "j_id")
     _dev(U, torch.float32, "U"), _dev(V, torch.float32, "V"), _dev(B, torch.float32, "B")
     check(L.b200_bpr_epoch_replay(ptr(i_index), ptr(j_id), i_index.numel(), ptr(data.indptr), ptr(data.indices),
                                   ptr(data.coo_row), ptr(U), ptr(V), ptr(B), int(U.shape[1]), float(lr), float(reg),
-                                  int(bool(use_bias)), ptr(_dev(stats, torch.int64, "stats")), current_stream()),
+                                  int(bool(use_bias)), _lib.BPR_LOSS_HINGE if hinge else 0,
+                                  ptr(_dev(stats, torch.int64, "stats")), current_stream()),
           "b200_bpr_epoch_replay")
 
 
 def bpr_train_host(indptr, indices, n_neg, U, V, B, lr, reg, use_bias, max_iter, key=0, replay_seeds=None,
                    atomic=True, on_epoch=None, keep_device=False, replica_sync=False, weighted_seed=None,
-                   neg_weighted=False):
+                   neg_weighted=False, hinge=False):
     """Host-buffer entry of BPR training (what BPR.fit calls): uploads the CSR matrix and the
     factors, runs `max_iter` epochs, writes the trained factors back INTO the given numpy
     arrays U, V, B (pinned staging both ways).
@@ -167,7 +169,7 @@ def bpr_train_host(indptr, indices, n_neg, U, V, B, lr, reg, use_bias, max_iter,
             h_j.numpy()[:] = host_indices[h_ij[1::2]]
             d_i, d_j = h_i.cuda(non_blocking=True), h_j.cuda(non_blocking=True)
             stats.zero_()
-            bpr_epoch_replay(data, d_i, d_j, dU, dV, dB, lr, reg, use_bias, stats)
+            bpr_epoch_replay(data, d_i, d_j, dU, dV, dB, lr, reg, use_bias, stats, hinge=hinge)
             history.append(tuple(stats.cpu().tolist()))
             if on_epoch:
                 on_epoch(epoch, *history[-1])
@@ -180,7 +182,7 @@ def bpr_train_host(indptr, indices, n_neg, U, V, B, lr, reg, use_bias, max_iter,
             g_neg.fill(int(n_neg) - 1, nnz, out=h_j.numpy())
             d_i, d_j = h_i.cuda(non_blocking=True), h_j.cuda(non_blocking=True)
             stats.zero_()
-            bpr_epoch_replay(data, d_i, d_j, dU, dV, dB, lr, reg, use_bias, stats)
+            bpr_epoch_replay(data, d_i, d_j, dU, dV, dB, lr, reg, use_bias, stats, hinge=hinge)
             history.append(tuple(stats.cpu().tolist()))      # also fences the staging buffers
             if on_epoch:
                 on_epoch(epoch, *history[-1])
@@ -188,7 +190,7 @@ def bpr_train_host(indptr, indices, n_neg, U, V, B, lr, reg, use_bias, max_iter,
         for epoch in range(max_iter):
             stats.zero_()
             bpr_epoch(data, n_neg, dU, dV, dB, lr, reg, use_bias, key, epoch, stats, atomic=atomic,
-                      neg_weighted=neg_weighted)
+                      neg_weighted=neg_weighted, hinge=hinge)
             if sync is not None:
                 sync.exchange()
             if on_epoch:

@@ -28,6 +28,8 @@ DTYPE = np.float32
 
 
 class BPR(DeviceScoringMixin, Recommender, ANNMixin):
+    _b200_hinge = False          # MMMF switches the loop body to the hinge variant
+
     """Bayesian Personalized Ranking trained and served on a B200.
 
     Parameters are those of cornac.models.BPR (k, max_iter, learning_rate, lambda_reg,
@@ -102,6 +104,7 @@ class BPR(DeviceScoringMixin, Recommender, ANNMixin):
             X.indptr, X.indices, train_set.num_items, self.u_factors, self.i_factors, self.i_biases,
             self.learning_rate, self.lambda_reg, self.use_bias, self.max_iter,
             key=(int(s_pos) << 31) | int(s_neg), replay_seeds=replay_seeds, atomic=self.atomic_updates,
+            hinge=self._b200_hinge,
             on_epoch=on_epoch if (self.verbose or replay) else None, keep_device=True)
         self._b200_adopt_device(dev[0], dev[1], dev[2], None, self.total_items)
         if self.verbose:
@@ -183,3 +186,17 @@ class WBPR(BPR):
             atomic=self.atomic_updates, on_epoch=(lambda *a: None) if replay else None, keep_device=True)
         self._b200_adopt_device(dev[0], dev[1], dev[2], None, self.total_items)
         return self
+
+
+class MMMF(BPR):
+    """Maximum Margin Matrix Factorization: drop-in for cornac.models.MMMF
+    (cornac/models/mmmf/recom_mmmf.pyx:33-156) -- BPR's sampler and kernels with the hinge loop body
+    (pairs already ranked correctly are left alone, otherwise the BPR update with z = 1; item biases are
+    always trained)."""
+    _b200_hinge = True
+
+    def __init__(self, name="MMMF", k=10, max_iter=100, learning_rate=0.001, lambda_reg=0.01, num_threads=0,
+                 trainable=True, verbose=False, init_params=None, seed=None, mode="auto", atomic_updates=True):
+        super().__init__(name=name, k=k, max_iter=max_iter, learning_rate=learning_rate, lambda_reg=lambda_reg,
+                         use_bias=True, num_threads=num_threads, trainable=trainable, verbose=verbose,
+                         init_params=init_params, seed=seed, mode=mode, atomic_updates=atomic_updates)

@@ -43,6 +43,7 @@ extern "C" {
 #define B200_SGD_ATOMIC 1u   /* scatter with red.global.add.f32 (no lost updates) instead of plain stores */
 #define B200_SGD_EXACT_EXP 2u /* z = 1/(1+exp(double)) like the reference instead of the fast f32 path */
 #define B200_BPR_NEG_WEIGHTED 8u /* WBPR (recom_wbpr.pyx:125-136): j = item of a uniformly drawn INTERACTION */
+#define B200_BPR_LOSS_HINGE 16u  /* MMMF (cornac/models/mmmf/recom_mmmf.pyx:129-154): hinge loss, biases always trained */
 #define B200_SGD_UNBOUNDED 4u /* do not cap the number of concurrently running samples (see b200_bpr_epoch) */
 
 B200_API const char* b200_last_error(void);
@@ -94,12 +95,12 @@ B200_API int b200_bpr_draw_host(uint64_t seed, uint64_t epoch, uint64_t sample_b
 /* BPR, parity mode.  Applies an explicit sample stream (i_index[s], j_id[s]),
  * s = 0..n_samples-1, with the SAME RESULT AS APPLYING IT SEQUENTIALLY in stream order,
  * i.e. the seeded single-thread reference (recom_bpr.pyx:132-133).  The stream normally
- * comes from b200_mt_sampler_* below.
+ * comes from b200_mt_sampler_* below.  flags: B200_BPR_LOSS_HINGE selects the MMMF loop body.
  *   i_index device int64[n_samples], j_id device int32[n_samples]                          */
 B200_API int b200_bpr_epoch_replay(const int64_t* i_index, const int32_t* j_id, int64_t n_samples,
                                    const int32_t* indptr, const int32_t* indices, const int32_t* coo_row,
                                    float* U, float* V, float* B, int k,
-                                   float lr, float reg, int use_bias,
+                                   float lr, float reg, int use_bias, unsigned flags,
                                    int64_t* stats, void* stream);
 
 /* Host-side restatement of RNGVector (recom_bpr.pyx:54-62): boost::random::mt19937 seeded

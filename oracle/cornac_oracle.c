@@ -137,11 +137,15 @@ static inline int ora_has_non_zero(const int32_t *indptr, const int32_t *indices
 /* One BPR triplet update, exactly the body of the prange loop in
  * BPR._fit_sgd (cornac/models/bpr/recom_bpr.pyx:241-267).  Returns 1 when the
  * sample was skipped, else 0; *correct is incremented when z < .5.            */
+static int ora_mmmf_one(const int32_t *indptr, const int32_t *indices, int64_t u, int32_t i_id, int32_t j_id,
+                        float *U, float *V, float *B, int k, float lr, float reg, int64_t *correct);
+
 static inline int ora_bpr_one(const int32_t *indptr, const int32_t *indices,
                               int64_t u, int32_t i_id, int32_t j_id,
                               float *U, float *V, float *B, int k,
                               float lr, float reg, int use_bias, int64_t *correct)
 {
+    if (use_bias == 2) return ora_mmmf_one(indptr, indices, u, i_id, j_id, U, V, B, k, lr, reg, correct);
     if (ora_has_non_zero(indptr, indices, u, j_id)) return 1;      /* :241-243 */
     float *user = U + (size_t)u * k, *item_i = V + (size_t)i_id * k, *item_j = V + (size_t)j_id * k;
     float score = B[i_id] - B[j_id];                                /* :249 */
@@ -159,6 +163,30 @@ static inline int ora_bpr_one(const int32_t *indptr, const int32_t *indices,
         B[i_id] += lr * (z - reg * B[i_id]);
         B[j_id] += lr * (-z - reg * B[j_id]);
     }
+    return 0;
+}
+
+/* MMMF variant of the loop body (cornac/models/mmmf/recom_mmmf.pyx:129-154): hinge instead of the
+ * logistic loss -- a pair that is already ranked correctly (score > 0) is counted and left alone,
+ * otherwise the update of BPR with z = 1; the item biases are always trained.  Selected by passing
+ * use_bias == 2 to the epoch functions.                                                        */
+static int ora_mmmf_one(const int32_t *indptr, const int32_t *indices, int64_t u, int32_t i_id, int32_t j_id,
+                        float *U, float *V, float *B, int k, float lr, float reg, int64_t *correct)
+{
+    if (ora_has_non_zero(indptr, indices, u, j_id)) return 1;      /* :125-127 */
+    float *user = U + (size_t)u * k, *item_i = V + (size_t)i_id * k, *item_j = V + (size_t)j_id * k;
+    float score = B[i_id] - B[j_id];                                /* :133 */
+    for (int f = 0; f < k; ++f)
+        score = score + user[f] * (item_i[f] - item_j[f]);
+    if (score > 0) { ++*correct; return 0; }                        /* :137-139 */
+    for (int f = 0; f < k; ++f) {                                   /* :142-146 */
+        float temp = user[f];
+        user[f] += lr * (item_i[f] - item_j[f] - reg * user[f]);
+        item_i[f] += lr * (temp - reg * item_i[f]);
+        item_j[f] += lr * (-temp - reg * item_j[f]);
+    }
+    B[i_id] += lr * (1 - reg * B[i_id]);                            /* :149-150 */
+    B[j_id] += lr * (-1 - reg * B[j_id]);
     return 0;
 }
 

@@ -26,7 +26,7 @@ from cornac.data import Dataset  # noqa: E402
 from cornac.eval_methods import RatioSplit  # noqa: E402
 from cornac.eval_methods.base_method import ranking_eval  # noqa: E402
 from cornac.metrics import AUC, MAP, NDCG, Precision, Recall  # noqa: E402
-from cornac.models import BPR, MF, WBPR  # noqa: E402
+from cornac.models import BPR, MF, MMMF, WBPR  # noqa: E402
 
 
 def synth_uir(n_users, n_items, nnz, seed):
@@ -96,6 +96,20 @@ def wbpr_case(name, n_users, n_items, nnz, k, max_iter, lr, reg, seed, dseed):
     print(name, "ok")
 
 
+def mmmf_case(name, n_users, n_items, nnz, k, max_iter, lr, reg, seed, dseed):
+    u, i, r = synth_uir(n_users, n_items, nnz, dseed)
+    ds = dataset_from(u, i, r)
+    m = MMMF(k=k, max_iter=max_iter, learning_rate=lr, lambda_reg=reg, seed=seed).fit(ds)
+    X = ds.matrix
+    np.savez_compressed(
+        os.path.join(HERE, name + ".npz"),
+        indptr=X.indptr.astype(np.int32), indices=X.indices.astype(np.int32), data=X.data.astype(np.float32),
+        num_users=ds.num_users, num_items=ds.num_items, total_users=m.total_users, total_items=m.total_items,
+        k=k, max_iter=max_iter, lr=lr, reg=reg, use_bias=True, seed=seed,
+        U=m.u_factors, V=m.i_factors, B=m.i_biases)
+    print(name, "ok")
+
+
 def mf_case(name, n_users, n_items, nnz, k, max_iter, lr, reg, use_bias, early_stop, seed, dseed):
     u, i, r = synth_uir(n_users, n_items, nnz, dseed)
     ds = dataset_from(u, i, r)
@@ -155,3 +169,4 @@ if __name__ == "__main__":
     mf_case("mf_nobias_k16", 120, 90, 1500, k=16, max_iter=8, lr=0.02, reg=0.01, use_bias=False, early_stop=False, seed=42, dseed=3)
     eval_case("eval_ratio_split", 200, 150, 6000, dseed=5)
     wbpr_case("wbpr_mid_k16", 150, 100, 2000, k=16, max_iter=10, lr=0.05, reg=0.01, seed=11, dseed=6)
+    mmmf_case("mmmf_mid_k16", 150, 100, 2000, k=16, max_iter=10, lr=0.02, reg=0.01, seed=13, dseed=7)

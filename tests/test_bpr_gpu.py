@@ -309,3 +309,42 @@ def test_sharded_fit_entry_single_process_and_host_rank_entry():
     for q, u in enumerate(users):
         wi, ws, _ = O.topk(want[q], 10, indices[indptr[u]:indptr[u + 1]])
         assert np.array_equal(ids[q], wi) and np.array_equal(sc[q], ws)
+
+
+@pytest.mark.parametrize("k", [10, 64])
+def test_hinge_loss_kernels_match_oracle(k):
+    """MMMF loop body in both kernels: replay == oracle on an arbitrary stream; Hogwild == oracle when conflict-free."""
+    import torch
+    from cornac_b200 import engine
+    n_users, n_items = 40000, 30000
+    indptr, indices = synth_csr(n_users, n_items, 120000, seed=3, zipf=0.0)
+    nnz = len(indices)
+    coo = O.coo_rows(indptr)
+    rng = np.random.RandomState(k)
+    U0 = rng.normal(0, 0.3, (n_users, k)).astype(np.float32)
+    V0 = rng.normal(0, 0.3, (n_items, k)).astype(np.float32)
+    B0 = rng.normal(0, 0.3, n_items).astype(np.float32)
+    data = _data(indptr, indices)
+    # replay, 20k samples with conflicts
+    ii = rng.randint(nnz, size=20000).astype(np.int64)
+    jj = rng.randint(n_items, size=20000).astype(np.int32)
+    Ur, Vr, Br = U0.copy(), V0.copy(), B0.copy()
+    c_ref, s_ref = O.bpr_replay(ii, jj, indptr, indices, Ur, Vr, Br, 0.05, 0.02, True, mmmf=True)
+    U, V, B = _dev(U0), _dev(V0), _dev(B0)
+    stats = torch.zeros(2, dtype=torch.int64, device="cuda")
+    engine.bpr_epoch_replay(data, _dev(ii), _dev(jj), U, V, B, 0.05, 0.02, True, stats, hinge=True)
+    c, s = stats.cpu().tolist()
+    assert s == s_ref and abs(c - c_ref) <= 2 and 0.2 * 20000 < c < 0.8 * 20000
+    assert rel_err(U.cpu().numpy(), Ur) < 1e-5 and rel_err(V.cpu().numpy(), Vr) < 1e-5 and rel_err(B.cpu().numpy(), Br) < 1e-5
+    # Hogwild on a conflict-free window
+    seed, epoch = 777 + k, 1
+    base, n = conflict_free_window(seed, epoch, nnz, n_items, coo, indices)
+    ii, jj = engine.bpr_draw_host(seed, epoch, n, nnz, n_items, sample_base=base)
+    Ur, Vr, Br = U0.copy(), V0.copy(), B0.copy()
+    c_ref, s_ref = O.bpr_replay(ii, jj, indptr, indices, Ur, Vr, Br, 0.05, 0.02, True, mmmf=True)
+    U, V, B = _dev(U0), _dev(V0), _dev(B0)
+    stats.zero_()
+    engine.bpr_epoch(data, n_items, U, V, B, 0.05, 0.02, True, seed, epoch, stats, n_samples=n, sample_base=base, hinge=True)
+    assert tuple(stats.cpu().tolist()) == (c_ref, s_ref)
+    for got, want in ((U, Ur), (V, Vr), (B, Br)):
+        assert np.allclose(got.cpu().numpy(), want, rtol=2e-5, atol=1e-6)

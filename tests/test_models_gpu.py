@@ -214,3 +214,15 @@ def test_batched_ranking_eval_equals_reference_loop():
     a = ref_eval(mdl, [AUC()], train_set, test_set, rating_threshold=4.0)[0]
     b = b200_eval(mdl, [AUC()], train_set, test_set, rating_threshold=4.0)[0]
     assert a == b
+
+
+def test_mmmf_plugin_reproduces_seeded_reference_and_trains_hogwild():
+    """row (f)3 of SURVEY 8: MMMF = BPR's kernels with the hinge loop body (B200_BPR_LOSS_HINGE)"""
+    from cornac_b200 import MMMF
+    g = golden("mmmf_mid_k16")
+    ds = _dataset_from_csr(g)
+    m = MMMF(k=16, max_iter=10, learning_rate=0.02, lambda_reg=0.01, seed=13).fit(ds)
+    assert rel_err(m.u_factors, g["U"]) < TOL and rel_err(m.i_factors, g["V"]) < TOL and rel_err(m.i_biases, g["B"]) < TOL
+    assert m.clone().name == "MMMF" and "use_bias" not in m._get_init_params()
+    h = MMMF(k=16, max_iter=10, learning_rate=0.02, lambda_reg=0.01).fit(ds)           # Hogwild
+    assert np.isfinite(h.u_factors).all() and np.abs(h.i_biases).max() > 1e-3

@@ -111,3 +111,10 @@ def test_wbpr_fit_matches_compiled_reference():
     r = O.wbpr_fit(g["indptr"], g["indices"], int(g["total_users"]), int(g["total_items"]), int(g["k"]),
                    int(g["max_iter"]), float(g["lr"]), float(g["reg"]), True, int(g["seed"]))
     assert rel_err(r["U"], g["U"]) < TOL and rel_err(r["V"], g["V"]) < TOL and rel_err(r["B"], g["B"]) < TOL
+
+
+def test_mmmf_fit_matches_compiled_reference():
+    g = golden("mmmf_mid_k16")
+    r = O.bpr_fit(g["indptr"], g["indices"], int(g["num_items"]), int(g["total_users"]), int(g["total_items"]), int(g["k"]),
+                  int(g["max_iter"]), float(g["lr"]), float(g["reg"]), True, int(g["seed"]), mmmf=True)
+    assert rel_err(r["U"], g["U"]) < TOL and rel_err(r["V"], g["V"]) < TOL and rel_err(r["B"], g["B"]) < TOL
