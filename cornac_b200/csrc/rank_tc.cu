@@ -38,11 +38,11 @@ constexpr int TN = 256;            // items per stage (UMMA N)
 constexpr int THREADS = 384;       // 12 warps: TMA, MMA, TMEM-alloc, idle, 8 x epilogue
 constexpr int EPI_WARPS = 8;       // warps 4-7 take accumulator columns [0,128), warps 8-11 columns [128,256)
 constexpr int HALF_N = TN / 2;
-constexpr int NB = 4;              // item-base ring slots
+constexpr int KX = 16;             // extra K slice carrying the item base: U gets (1, 1, 0...), V gets (hi, lo, 0...)
 constexpr int CAP = 1024;          // candidate-list capacity per row
 constexpr int TRIGGER = 512;       // raise the threshold when a list reaches this length
 constexpr int MAX_TOPK = 256;
-constexpr int MAX_KP = 128;
+constexpr int MAX_KP = 128 + KX;
 constexpr uint32_t TMEM_COLS = 512;
 constexpr int CHUNK_TILES = 148 * 4;   // user tiles per chunk
 
@@ -171,7 +171,7 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N)
 // V-tile ring depth that fits next to the U tile in 220 KB of shared memory (2..4)
 __host__ __device__ __forceinline__ int num_stages(int kp)
 {
-    const int budget = 220 * 1024 - TM * kp * 2 - NB * TN * 4;
+    const int budget = 220 * 1024 - TM * kp * 2;
     int ns = budget / (TN * kp * 2);
     return ns > 4 ? 4 : (ns < 2 ? 2 : ns);
 }
@@ -183,12 +183,16 @@ __host__ __device__ __forceinline__ size_t packed_offset(int r, int c, int kp)
 }
 
 // ---------------------------------------------------------------- pack kernels
-// one thread per (row, 16-byte chunk): 8 consecutive factors -> 8 bf16
-template <int TR>
+// one thread per (row, 16-byte chunk): 8 consecutive factors -> 8 bf16.  The last KX columns are the
+// base slice: user rows carry (1, 1, 0, ...), item rows carry (hi, lo, 0, ...) with hi + lo = item base split
+// into two bf16 (relative error 2^-16), so the MMA itself adds the base and the epilogue has no bias add.
+// Padding item rows get a hugely negative base so that they are never nominated.
+template <int TR, bool ITEMS>
 __global__ void pack_kernel(const float* __restrict__ src, const int64_t* __restrict__ row_idx, int64_t n_rows,
-                            int64_t n_rows_padded, int k, int kp, uint8_t* __restrict__ dst)
+                            int64_t n_rows_padded, int k, int kp, const float* __restrict__ base, uint8_t* __restrict__ dst)
 {
     const int chunks = kp >> 3;
+    const int k16 = kp - KX;                    // first column of the base slice
     const int64_t total = n_rows_padded * chunks;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
@@ -197,7 +201,21 @@ __global__ void pack_kernel(const float* __restrict__ src, const int64_t* __rest
         __nv_bfloat16 v[8];
 #pragma unroll
         for (int x = 0; x < 8; ++x) v[x] = __float2bfloat16_rn(0.f);
-        if (row < n_rows) {
+        if (kc * 8 == k16) {                    // base slice, first chunk (the second one stays zero)
+            if (ITEMS) {
+                if (row < n_rows) {
+                    const float b = base ? __ldg(base + row) : 0.f;
+                    const __nv_bfloat16 hi = __float2bfloat16_rn(b);
+                    v[0] = hi;
+                    v[1] = __float2bfloat16_rn(b - __bfloat162float(hi));
+                } else {
+                    v[0] = __float2bfloat16_rn(-3.0e38f);
+                }
+            } else if (row < n_rows) {
+                v[0] = __float2bfloat16_rn(1.f);
+                v[1] = __float2bfloat16_rn(1.f);
+            }
+        } else if (kc * 8 < k16 && row < n_rows) {
             const int64_t srow = row_idx ? row_idx[row] : row;
             const float* p = src + (size_t)srow * k + kc * 8;
 #pragma unroll
@@ -213,7 +231,8 @@ __global__ void pack_kernel(const float* __restrict__ src, const int64_t* __rest
 
 // warp per row: L2 norm (f32 rows); optionally max-reduced into *max_out (as uint bits, values >= 0)
 __global__ void norm_kernel(const float* __restrict__ src, const int64_t* __restrict__ row_idx, int64_t n_rows, int k,
-                            float* __restrict__ norm_out, unsigned int* __restrict__ max_out)
+                            float* __restrict__ norm_out, unsigned int* __restrict__ max_out,
+                            const float* __restrict__ base, unsigned int* __restrict__ base_absmax_out)
 {
     const int lane = threadIdx.x & 31;
     const int64_t wstride = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -229,30 +248,18 @@ __global__ void norm_kernel(const float* __restrict__ src, const int64_t* __rest
             // one shared maximum: look before the atomic, or a million rows serialise on one address
             if (max_out && __float_as_uint(nrm) > *reinterpret_cast<volatile unsigned int*>(max_out))
                 atomicMax(max_out, __float_as_uint(nrm));
+            if (base && base_absmax_out) {
+                const unsigned int ab = __float_as_uint(fabsf(__ldg(base + row)));
+                if (ab > *reinterpret_cast<volatile unsigned int*>(base_absmax_out)) atomicMax(base_absmax_out, ab);
+            }
         }
     }
-}
-
-// item base padded to a multiple of TN with -inf (padding items can never be nominated); also max |base|
-__global__ void base_pad_kernel(const float* __restrict__ base, int64_t n_items, int64_t n_pad, float* __restrict__ out,
-                                unsigned int* __restrict__ absmax_out)
-{
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    float m = 0.f;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += stride) {
-        float b = -INFINITY;
-        if (i < n_items) { b = base ? __ldg(base + i) : 0.f; m = fmaxf(m, fabsf(b)); }
-        out[i] = b;
-    }
-    m = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(m)));
-    if ((threadIdx.x & 31) == 0 && absmax_out) atomicMax(absmax_out, __float_as_uint(m));
 }
 
 // ---------------------------------------------------------------- main kernel
 struct RankTcParams {
     const uint8_t* __restrict__ Upack;     // [n_ut][TM x kp bf16 tile image]
     const uint8_t* __restrict__ Vpack;     // [n_it][TN x kp bf16 tile image]
-    const float* __restrict__ base_pad;    // [n_it * TN]
     const float* __restrict__ unorm;       // [n_ut * TM] |u| per chunk row
     const unsigned int* __restrict__ scal; // [0] = max |v| bits, [1] = max |base| bits
     const int64_t* __restrict__ excl_indptr;   // already offset to the chunk's first row (may be null)
@@ -344,7 +351,7 @@ __device__ __forceinline__ void raise_threshold(RowState& st, int K, float eps2,
     if (L < K) return;
     // ---- (2) score range, then two rounds of 16-way bisection (resolution (hi - lo) / 256)
     float lo = st.tau_f, hi = st.hi;
-    if (!(lo > -INFINITY)) {                     // first raise of this list: the range is unknown
+    if (!(hi > -INFINITY) || !(lo > -1.0e37f)) {  // this list's score range is not known yet
         lo = INFINITY; hi = -INFINITY;
         scan_list(list, L, [&](unsigned long long ent) {
             const float sc = ent_score(ent);
@@ -385,19 +392,19 @@ __device__ __forceinline__ void raise_threshold(RowState& st, int K, float eps2,
     st.checked = w;
 }
 
-// one 32-column chunk of the accumulator: add the item base and append every score above tau_f.
-// Scores are screened four at a time: max of the four against the row's filter, one warp vote, and only
-// when some lane of the warp has a hit (a few percent of the groups once the thresholds have risen) does
-// the warp run the predicated appends for that group.  ~2 instructions per score on the common path.
+// one 32-column chunk of the accumulator (the item base is already in it: extra K slice of the MMA):
+// append every score above tau_f.  Scores are screened four at a time -- max of the four against the
+// row's filter, one warp vote -- and only when some lane of the warp has a hit (a few percent of the
+// groups once the thresholds have risen) does the warp run the predicated appends for that group.
+// ~1.25 instructions per score on the common path.
 template <bool DUMP>
-__device__ __forceinline__ void epilogue_chunk(uint32_t (&r)[32], const float* __restrict__ bias, RowState& st,
-                                               int32_t id0, float* __restrict__ dump_row, bool valid)
+__device__ __forceinline__ void epilogue_chunk(uint32_t (&r)[32], RowState& st, int32_t id0,
+                                               float* __restrict__ dump_row, bool valid)
 {
 #pragma unroll
     for (int j4 = 0; j4 < 8; ++j4) {
-        const float4 b = *reinterpret_cast<const float4*>(bias + j4 * 4);
-        const float sc[4] = {__uint_as_float(r[j4 * 4 + 0]) + b.x, __uint_as_float(r[j4 * 4 + 1]) + b.y,
-                             __uint_as_float(r[j4 * 4 + 2]) + b.z, __uint_as_float(r[j4 * 4 + 3]) + b.w};
+        const float sc[4] = {__uint_as_float(r[j4 * 4 + 0]), __uint_as_float(r[j4 * 4 + 1]),
+                             __uint_as_float(r[j4 * 4 + 2]), __uint_as_float(r[j4 * 4 + 3])};
         if (DUMP) {
             if (valid) {
 #pragma unroll
@@ -423,31 +430,27 @@ __global__ void __launch_bounds__(THREADS, 1) rank_tc_kernel(const RankTcParams 
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int kp = p.kp;
-    const uint32_t u_bytes = TM * kp * 2, v_bytes = TN * kp * 2, b_bytes = TN * 4;
+    const uint32_t u_bytes = TM * kp * 2, v_bytes = TN * kp * 2;
     const int NS = num_stages(kp);
     uint8_t* sU = smem;
     uint8_t* sV = sU + u_bytes;
-    float* sB = reinterpret_cast<float*>(sV + (size_t)NS * v_bytes);      // [NB][TN] item-base ring
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sB) + (size_t)NB * b_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + (size_t)NS * v_bytes);
     uint64_t* full = bars;            // [NS]  V tile landed                 TMA -> MMA
     uint64_t* empty = bars + 4;       // [NS]  MMAs reading the tile retired MMA commit -> TMA
     uint64_t* u_full = bars + 8;      // U tile landed
     uint64_t* u_empty = bars + 9;     // all MMAs of the user tile retired
     uint64_t* acc_full = bars + 10;   // [2] accumulator ready               MMA commit -> epilogue
     uint64_t* acc_empty = bars + 12;  // [2] accumulator drained             8 epilogue warps -> MMA
-    uint64_t* bfull = bars + 14;      // [NB] item-base slice landed         TMA -> epilogue
-    uint64_t* bempty = bars + 18;     // [NB] slice consumed                 8 epilogue warps -> TMA
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 22);
     // [2 halves][TM rows] last published row threshold, tagged with the tile it belongs to: (tile << 32) | f32 bits
     unsigned long long* tau_share = reinterpret_cast<unsigned long long*>(bars + 24);
-    // The V ring is released by the tensor pipe alone, so the TMA producer runs NS tiles ahead of
-    // the MMAs whatever the epilogue does; the (tiny) item-base ring is what the epilogue releases.
+    // The V ring is released by the tensor pipe alone, so the TMA producer runs NS tiles ahead of the
+    // MMAs whatever the epilogue does; the epilogue only hands the TMEM accumulators back.
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        for (int s = 0; s < NB; ++s) { mbar_init(bfull + s, 1); mbar_init(bempty + s, EPI_WARPS); }
         mbar_init(u_full, 1);
         mbar_init(u_empty, 1);
         for (int a = 0; a < 2; ++a) { mbar_init(acc_full + a, 1); mbar_init(acc_empty + a, EPI_WARPS); }
@@ -473,11 +476,6 @@ __global__ void __launch_bounds__(THREADS, 1) rank_tc_kernel(const RankTcParams 
                     if (round > 0) mbar_wait_backoff(empty + s, (round - 1) & 1);
                     mbar_expect_tx(full + s, v_bytes);
                     bulk_g2s(sV + (size_t)s * v_bytes, p.Vpack + (size_t)it * v_bytes, v_bytes, full + s);
-                    const int bs = it_global % NB;
-                    const uint32_t bround = it_global / NB;
-                    if (bround > 0) mbar_wait_backoff(bempty + bs, (bround - 1) & 1);
-                    mbar_expect_tx(bfull + bs, b_bytes);
-                    bulk_g2s(sB + (size_t)bs * TN, p.base_pad + (size_t)it * TN, b_bytes, bfull + bs);
                 }
             }
         }
@@ -520,7 +518,8 @@ __global__ void __launch_bounds__(THREADS, 1) rank_tc_kernel(const RankTcParams 
             const bool valid = row < p.n_rows;
             const float un = valid ? p.unorm[row] : 0.f;
             // |approx - exact| <= eps: bf16 rounding of both operands (2^-8 each) + f32 accumulation
-            const float eps = 0.0083f * un * vmax + 2e-6f * (un * vmax + bmax);
+            // + 2^-16 relative for the base carried as two bf16 in the extra K slice
+            const float eps = 0.0083f * un * vmax + 2e-6f * (un * vmax + bmax) + 1.6e-5f * bmax;
             const float eps2 = 2.f * eps;
             RowState st;
             st.list = p.lists + ((size_t)(ut * EPI_WARPS + half * 4 + q) * CAP) * 32 + lane;
@@ -541,16 +540,13 @@ __global__ void __launch_bounds__(THREADS, 1) rank_tc_kernel(const RankTcParams 
             st.cnt = 0; st.checked = 0;
             st.tau = -INFINITY; st.hi = -INFINITY;
             tau_share[half * TM + q * 32 + lane] = ((unsigned long long)(uint32_t)ut << 32) | 0xff800000u;   // -inf
-            st.tau_f = valid ? -INFINITY : INFINITY;
+            st.tau_f = valid ? -1.0e38f : INFINITY;       // padding items carry a base of -3e38: never above the filter
             int flag = 0;
             float* dump_row = DUMP ? p.dump + (size_t)(valid ? row : 0) * ((size_t)p.n_it * TN) : nullptr;
             for (int it = 0; it < p.n_it; ++it, ++it_global) {
-                const int bs = it_global % NB;
                 const int acc = it_global & 1;
-                mbar_wait(bfull + bs, (it_global / NB) & 1);        // item-base values visible
                 mbar_wait(acc_full + acc, (it_global >> 1) & 1);
                 tc_fence_after();
-                const float* bias = sB + (size_t)bs * TN + half * HALF_N;
                 const int32_t item0 = it * TN + half * HALF_N;
                 const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN + half * HALF_N);
                 uint32_t r0[32], r1[32];
@@ -560,17 +556,17 @@ __global__ void __launch_bounds__(THREADS, 1) rank_tc_kernel(const RankTcParams 
 #pragma unroll
                 for (int c0 = 0; c0 < HALF_N; c0 += 64) {
                     tmem_ld32_issue(t0 + c0 + 32, r1);                        // in flight while r0 is processed
-                    epilogue_chunk<DUMP>(r0, bias + c0, st, item0 + c0, dump_row, valid);
+                    epilogue_chunk<DUMP>(r0, st, item0 + c0, dump_row, valid);
                     tmem_ld_wait(r1);
                     if (c0 + 64 < HALF_N) tmem_ld32_issue(t0 + c0 + 64, r0);
-                    epilogue_chunk<DUMP>(r1, bias + c0 + 32, st, item0 + c0 + 32, dump_row, valid);
+                    epilogue_chunk<DUMP>(r1, st, item0 + c0 + 32, dump_row, valid);
                     if (c0 + 64 < HALF_N) tmem_ld_wait(r0);
                 }
                 st.cnt = (int)((st.wp - st.list) >> 5);
                 // accumulator and stage are free again
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) { mbar_arrive(acc_empty + acc); mbar_arrive(bempty + bs); }
+                if (lane == 0) mbar_arrive(acc_empty + acc);
                 if (!DUMP) {
                     // Raise schedule: after stages 2, 4, 8, 16, ... for EVERY warp at once (a raise stalls the
                     // accumulator hand-off; doing it in all warps at the same stage costs one stall instead of
@@ -734,7 +730,7 @@ struct Layout {
 static Layout make_layout(int64_t n_q, int64_t n_items, int k)
 {
     Layout L;
-    L.kp = (k + 15) / 16 * 16;
+    L.kp = (k + 15) / 16 * 16 + KX;
     L.n_it = (n_items + TN - 1) / TN;
     int64_t n_ut = (n_q + TM - 1) / TM;
     L.chunk_ut = n_ut < CHUNK_TILES ? n_ut : CHUNK_TILES;
@@ -758,7 +754,7 @@ static Layout make_layout(int64_t n_q, int64_t n_items, int k)
 static size_t smem_bytes_for(int kp)
 {
     const int NS = num_stages(kp);
-    return (size_t)TM * kp * 2 + (size_t)NS * (TN * kp * 2) + (size_t)NB * TN * 4 + 32 * 8 + 2 * TM * 8 + 1024;
+    return (size_t)TM * kp * 2 + (size_t)NS * (TN * kp * 2) + 32 * 8 + 2 * TM * 8 + 1024;
 }
 
 }  // namespace tc
@@ -770,7 +766,7 @@ int rank_tc_supported(int64_t n_q, int64_t n_items, int k, int topk)
     if (const char* e = getenv("B200_RANK_TC")) {
         if (e[0] == '0') return 0;
     }
-    if (k < 8 || (k + 15) / 16 * 16 > MAX_KP) return 0;
+    if (k < 8 || (k + 15) / 16 * 16 + KX > MAX_KP) return 0;
     if (topk < 1 || topk > MAX_TOPK) return 0;
     if (n_items < 4 * TN || n_items >= (1ll << 31) - TN) return 0;     // tiny catalogues: the exact path is fine
     if (n_q < 1) return 0;
@@ -789,13 +785,11 @@ static int pack_items(const float* V, int64_t n_items, int k, const float* item_
     const int64_t n_pad = L.n_it * TN;
     B200_CUDA(cudaMemsetAsync(ws + L.off_scal, 0, 64, st));
     const int grid = sm_count() * 8;
-    pack_kernel<TN><<<grid, 256, 0, st>>>(V, nullptr, n_items, n_pad, k, L.kp, ws + L.off_vpack);
+    pack_kernel<TN, true><<<grid, 256, 0, st>>>(V, nullptr, n_items, n_pad, k, L.kp, item_base, ws + L.off_vpack);
     // one warp per row and a row is only 4k bytes: launch enough warps to cover the latency
     const int64_t ngrid = (n_items + 7) / 8 < (1 << 20) ? (n_items + 7) / 8 : (1 << 20);
-    norm_kernel<<<(unsigned)(ngrid < grid ? grid : ngrid), 256, 0, st>>>(V, nullptr, n_items, k, nullptr,
-                                                                        reinterpret_cast<unsigned int*>(ws + L.off_scal));
-    base_pad_kernel<<<grid, 256, 0, st>>>(item_base, n_items, n_pad, reinterpret_cast<float*>(ws + L.off_base),
-                                          reinterpret_cast<unsigned int*>(ws + L.off_scal) + 1);
+    unsigned int* scal = reinterpret_cast<unsigned int*>(ws + L.off_scal);
+    norm_kernel<<<(unsigned)(ngrid < grid ? grid : ngrid), 256, 0, st>>>(V, nullptr, n_items, k, nullptr, scal, item_base, scal + 1);
     B200_CUDA(cudaGetLastError());
     return B200_OK;
 }
@@ -818,12 +812,11 @@ int rank_tc(const float* U, const int64_t* user_idx, int64_t n_q, const float* V
         const int64_t n_ut = (rows + TM - 1) / TM;
         const int64_t* uidx = user_idx ? user_idx + q0 : nullptr;
         const float* Usrc = user_idx ? U : U + (size_t)q0 * k;
-        pack_kernel<TM><<<grid_aux, 256, 0, st>>>(Usrc, uidx, rows, n_ut * TM, k, L.kp, ws + L.off_upack);
-        norm_kernel<<<grid_aux, 256, 0, st>>>(Usrc, uidx, rows, k, reinterpret_cast<float*>(ws + L.off_unorm), nullptr);
+        pack_kernel<TM, false><<<grid_aux, 256, 0, st>>>(Usrc, uidx, rows, n_ut * TM, k, L.kp, nullptr, ws + L.off_upack);
+        norm_kernel<<<grid_aux, 256, 0, st>>>(Usrc, uidx, rows, k, reinterpret_cast<float*>(ws + L.off_unorm), nullptr, nullptr, nullptr);
         B200_CUDA(cudaMemsetAsync(ws + L.off_over, 0, 4, st));
         RankTcParams p;
         p.Upack = ws + L.off_upack; p.Vpack = ws + L.off_vpack;
-        p.base_pad = reinterpret_cast<const float*>(ws + L.off_base);
         p.unorm = reinterpret_cast<const float*>(ws + L.off_unorm);
         p.scal = reinterpret_cast<const unsigned int*>(ws + L.off_scal);
         p.excl_indptr = excl_indptr ? excl_indptr + q0 : nullptr;
@@ -884,7 +877,7 @@ extern "C" int b200_rank_tc_debug_scores(const float* U, int64_t n_q, const floa
                                          void* workspace, int64_t workspace_bytes, void* stream)
 {
     B200_REQUIRE(U && V && out && workspace, "b200_rank_tc_debug_scores: null pointer argument");
-    B200_REQUIRE(k >= 8 && (k + 15) / 16 * 16 <= MAX_KP, "b200_rank_tc_debug_scores: k=%d unsupported", k);
+    B200_REQUIRE(k >= 8 && (k + 15) / 16 * 16 + KX <= MAX_KP, "b200_rank_tc_debug_scores: k=%d unsupported", k);
     const Layout L = make_layout(n_q, n_items, k);
     B200_REQUIRE(n_q <= L.chunk_rows, "b200_rank_tc_debug_scores: n_q too large for one chunk");
     B200_REQUIRE((int64_t)L.total <= workspace_bytes, "b200_rank_tc_debug_scores: workspace too small (%lld needed)", (long long)L.total);
@@ -897,11 +890,10 @@ extern "C" int b200_rank_tc_debug_scores(const float* U, int64_t n_q, const floa
     int rc = pack_items(V, n_items, k, item_base, L, ws, st);
     if (rc) return rc;
     const int grid_aux = sm_count() * 8;
-    pack_kernel<TM><<<grid_aux, 256, 0, st>>>(U, nullptr, n_q, n_ut * TM, k, L.kp, ws + L.off_upack);
-    norm_kernel<<<grid_aux, 256, 0, st>>>(U, nullptr, n_q, k, reinterpret_cast<float*>(ws + L.off_unorm), nullptr);
+    pack_kernel<TM, false><<<grid_aux, 256, 0, st>>>(U, nullptr, n_q, n_ut * TM, k, L.kp, nullptr, ws + L.off_upack);
+    norm_kernel<<<grid_aux, 256, 0, st>>>(U, nullptr, n_q, k, reinterpret_cast<float*>(ws + L.off_unorm), nullptr, nullptr, nullptr);
     RankTcParams p;
     p.Upack = ws + L.off_upack; p.Vpack = ws + L.off_vpack;
-    p.base_pad = reinterpret_cast<const float*>(ws + L.off_base);
     p.unorm = reinterpret_cast<const float*>(ws + L.off_unorm);
     p.scal = reinterpret_cast<const unsigned int*>(ws + L.off_scal);
     p.excl_indptr = nullptr; p.excl_indices = nullptr;

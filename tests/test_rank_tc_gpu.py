@@ -64,8 +64,9 @@ def test_tensor_pass_matches_bf16_matmul(k, n_items, n_q):
     want = Ub @ Vb.T + base[None, :].astype(np.float64)
     scale = np.abs(Ub) @ np.abs(Vb).T + np.abs(base)[None, :]
     err = np.abs(got[:, :n_items] - want)
-    assert np.all(err <= 2e-6 * scale + 1e-6), float((err / (scale + 1e-9)).max())
-    assert np.all(np.isneginf(got[:, n_items:]))            # padding items carry -inf
+    # f32 accumulation of exact bf16 products + the item base carried as two bf16 (2^-16 relative)
+    assert np.all(err <= 2e-6 * scale + 2e-5 * np.abs(base)[None, :] + 1e-6), float((err / (scale + 1e-9)).max())
+    assert np.all(got[:, n_items:] < -1e38)                 # padding items carry a hugely negative base
 
 
 @pytest.mark.parametrize("k,n_items,n_q,topk", [(64, 20000, 300, 100), (128, 5000, 64, 100), (128, 100003, 130, 100),
