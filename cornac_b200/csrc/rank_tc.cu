@@ -7,18 +7,20 @@
 //
 // Plan of one call (users are processed in chunks so the candidate lists stay small):
 //   1. pack   V (and the chunk's U rows) to bf16 in the UMMA "K-major, no swizzle" core-matrix
-//             layout, tile by tile, so that one tile is ONE contiguous cp.async.bulk (UBLKCP);
-//             per-row norms give the rigorous bf16 error bound eps(u) = 2^-7 * 1.06 * |u| * max|v|;
+//             layout, tile by tile, so that one tile is ONE contiguous cp.async.bulk (UBLKCP); an
+//             extra K slice carries the item base (two bf16 per item against a constant 1 on the
+//             user side), so the MMA adds it; per-row norms give the rigorous error bound
+//             eps(u) = 2^-7 * 1.06 * |u| * max|v| + 2^-16 * max|base| of the bf16 pass;
 //   2. rank_tc_kernel  persistent, one CTA per SM, warp-specialised:
-//               warp 0   TMA producer: U tile once per 128 users, V tiles (256 items) + the
-//                        matching 256 item-base values through a ring of smem stages (mbarriers)
+//               warp 0   TMA producer: U tile once per 128 users, V tiles (256 items) through a
+//                        ring of smem stages released by tcgen05.commit (mbarriers)
 //               warp 1   one elected thread issues tcgen05.mma (M=128, N=256, K=16 per
 //                        instruction, bf16 x bf16 -> f32) into a double-buffered TMEM accumulator
 //               warp 2   TMEM allocation
-//               warps 4-7 epilogue: tcgen05.ld the accumulator (one user row per thread), add
-//                        the item base, keep every score above the row's running threshold in
-//                        the row's candidate list; the threshold is raised (never above the
-//                        approximate k-th best minus 2*eps) by warp-synchronous scans of the list
+//               warps 4-11 epilogue: tcgen05.ld the accumulator (one (user row, 128-column half)
+//                        per thread), keep every score above the row's running threshold in the
+//                        thread's candidate list; the threshold is raised (never above the
+//                        approximate k-th best minus 2*eps) by lock-step scans of the lists
 //   3. rank_tc_finish_kernel  per row: exact re-score of the candidates (the f64-accumulated
 //             arithmetic of score_batch_kernel), total order (score desc, id asc), top-k.
 // The tensor pass only NOMINATES: every item whose exact score can reach the top-k is provably
@@ -724,7 +726,7 @@ __global__ void __launch_bounds__(128) rank_tc_finish_kernel(const FinishParams 
 struct Layout {
     int kp;
     int64_t n_it, chunk_rows, chunk_ut;
-    size_t off_vpack, off_base, off_scal, off_upack, off_unorm, off_lists, off_cnt, off_flag, off_over, off_slab, total;
+    size_t off_vpack, off_scal, off_upack, off_unorm, off_lists, off_cnt, off_flag, off_over, off_slab, total;
 };
 
 static Layout make_layout(int64_t n_q, int64_t n_items, int k)
@@ -738,7 +740,6 @@ static Layout make_layout(int64_t n_q, int64_t n_items, int k)
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t at = o; o += (bytes + 1023) / 1024 * 1024; return at; };
     L.off_vpack = take((size_t)L.n_it * TN * L.kp * 2);
-    L.off_base = take((size_t)L.n_it * TN * 4);
     L.off_scal = take(64);
     L.off_upack = take((size_t)L.chunk_ut * TM * L.kp * 2);
     L.off_unorm = take((size_t)L.chunk_rows * 4);
