@@ -1,5 +1,5 @@
 #!/usr/bin/env bash
-# GPU trip 18: base folded into the MMA (no bias ring) + MMMF kernels
+# GPU trip 19: full validation of the round-1 state: tests (incl. full-size properties), smoke, example, bench
 mkdir -p gpurun_out
 python -c "
 import torch, sys
@@ -7,14 +7,9 @@ sys.path.insert(0, '.')
 torch.zeros(1).cuda(); torch.cuda.synchronize()
 from cornac_b200 import _lib; _lib.load(); print('warm ok')
 " > gpurun_out/warm.log 2>&1
-timeout -s KILL 400 python -m pytest tests/test_rank_tc_gpu.py tests/test_rank_gpu.py -m gpu -q --timeout 120 > gpurun_out/pytest_tc.log 2>&1
-echo "pytest tc exit $?" >> gpurun_out/pytest_tc.log
-timeout -s KILL 600 python tools/tune_rank.py > gpurun_out/tune_rank.log 2>&1
-timeout -s KILL 900 python -m pytest tests -m gpu -q --timeout 300 --deselect tests/test_rank_tc_gpu.py --deselect tests/test_rank_gpu.py > gpurun_out/pytest.log 2>&1
+( time timeout -s KILL 1500 python -m pytest tests -m gpu -q --timeout 400 --durations=8 ) > gpurun_out/pytest.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest.log
-timeout -s KILL 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'rank_tc|pack_|norm_' -s 120 -c 6 --csv --log-file gpurun_out/launches_rank_c5.csv python tools/tune_rank.py > gpurun_out/tune_rank_ncu.log 2>&1
-tail -12 gpurun_out/pytest_tc.log; cat gpurun_out/tune_rank.log; tail -5 gpurun_out/pytest.log; python - <<'PY'
-import csv
-rows=[r for r in csv.reader(open('gpurun_out/launches_rank_c5.csv')) if len(r)>14 and r[12]=='gpu__time_duration.sum']
-for r in rows[:6]: print(r[4][:50], r[8], r[14])
-PY
+timeout -s KILL 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
+( time timeout -s KILL 600 python examples/bpr_experiment.py ) > gpurun_out/example.log 2>&1
+timeout -s KILL 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err
+tail -22 gpurun_out/pytest.log; tail -2 gpurun_out/smoke.log; tail -22 gpurun_out/example.log; cat gpurun_out/bench.json | cut -c1-400

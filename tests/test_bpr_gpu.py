@@ -348,3 +348,45 @@ def test_hinge_loss_kernels_match_oracle(k):
     assert tuple(stats.cpu().tolist()) == (c_ref, s_ref)
     for got, want in ((U, Ur), (V, Vr), (B, Br)):
         assert np.allclose(got.cpu().numpy(), want, rtol=2e-5, atol=1e-6)
+
+
+def test_edge_cases_empty_rows_tiny_shapes_zero_samples():
+    """ragged / empty inputs: users without interactions, a single interaction, k = 1, zero samples"""
+    import torch
+    from cornac_b200 import engine
+    # 6 users, rows 0, 2, 5 empty; 4 items
+    indptr = np.array([0, 0, 2, 2, 3, 5, 5], dtype=np.int32)
+    indices = np.array([1, 3, 0, 0, 2], dtype=np.int32)
+    for k in (1, 3, 8):
+        rng = np.random.RandomState(k)
+        U0 = rng.normal(0, 0.3, (6, k)).astype(np.float32)
+        V0 = rng.normal(0, 0.3, (4, k)).astype(np.float32)
+        B0 = rng.normal(0, 0.3, 4).astype(np.float32)
+        data = _data(indptr, indices)
+        U, V, B = _dev(U0), _dev(V0), _dev(B0)
+        stats = torch.zeros(2, dtype=torch.int64, device="cuda")
+        engine.bpr_epoch(data, 4, U, V, B, 0.05, 0.01, True, 9, 0, stats, n_samples=0)          # nothing to do
+        assert stats.cpu().tolist() == [0, 0] and np.array_equal(U.cpu().numpy(), U0)
+        # sequential semantics on the tiny matrix: replay == oracle, empty rows untouched
+        ii = rng.randint(5, size=200).astype(np.int64)
+        jj = rng.randint(4, size=200).astype(np.int32)
+        Ur, Vr, Br = U0.copy(), V0.copy(), B0.copy()
+        c_ref, s_ref = O.bpr_replay(ii, jj, indptr, indices, Ur, Vr, Br, 0.05, 0.01, True)
+        engine.bpr_epoch_replay(data, _dev(ii), _dev(jj), U, V, B, 0.05, 0.01, True, stats)
+        assert stats.cpu().tolist() == [c_ref, s_ref]
+        assert rel_err(U.cpu().numpy(), Ur) < 1e-5 and rel_err(V.cpu().numpy(), Vr) < 1e-5
+        assert np.array_equal(U.cpu().numpy()[[0, 2, 5]], U0[[0, 2, 5]])
+        # Hogwild on the same matrix only ever touches users that have interactions
+        U, V, B = _dev(U0), _dev(V0), _dev(B0)
+        stats.zero_()
+        engine.bpr_epoch(data, 4, U, V, B, 0.05, 0.01, True, 9, 1, stats, n_samples=500)
+        c, s = stats.cpu().tolist()
+        assert 0 <= c and 0 < s < 500 and np.array_equal(U.cpu().numpy()[[0, 2, 5]], U0[[0, 2, 5]])
+        assert np.isfinite(V.cpu().numpy()).all()
+    # a matrix with a single interaction: every sample has u=0, i=0; j=0 is always skipped
+    data = _data(np.array([0, 1], np.int32), np.array([0], np.int32))
+    U, V, B = _dev(np.ones((1, 4), np.float32)), _dev(np.ones((2, 4), np.float32)), _dev(np.zeros(2, np.float32))
+    stats = torch.zeros(2, dtype=torch.int64, device="cuda")
+    engine.bpr_epoch(data, 2, U, V, B, 0.01, 0.0, True, 1, 0, stats, n_samples=64)
+    c, s = stats.cpu().tolist()
+    assert c + s <= 64 and s > 0 and B.cpu().numpy()[0] > 0 > B.cpu().numpy()[1]
