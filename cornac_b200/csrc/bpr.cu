@@ -487,6 +487,86 @@ static HogwildTune read_tune()
     return t;
 }
 
+// ---------------------------------------------------------------------------------------
+// Parity mode, windowed: one CTA of 32 warps.  32 consecutive samples are resolved at a time (one per
+// warp) and executed in dependency order: a sample may run as soon as no EARLIER still-pending sample
+// of the window touches one of its rows (its user row, or either of its two item rows).  Samples that
+// share no row commute exactly, so the result is bit-identical to bpr_replay_kernel (strictly serial)
+// while independent samples run in parallel -- on a matrix with thousands of rows a window needs 1-3
+// rounds instead of 32 serial updates.
+__global__ void __launch_bounds__(1024) bpr_replay_window_kernel(const ReplayParams p)
+{
+    __shared__ int s_u[32], s_i[32], s_j[32], s_pending[32];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t k = (size_t)p.k;
+    unsigned long long n_correct = 0, n_skipped = 0;
+    for (int64_t base = 0; base < p.n_samples; base += 32) {
+        const int64_t s = base + w;
+        int32_t mu = 0, mi = 0, mj = 0;
+        bool todo = false;
+        if (s < p.n_samples) {                      // warp-uniform; all lanes resolve the same sample
+            const int64_t ii = p.i_index[s];
+            mj = p.j_id[s];
+            mu = __ldg(p.coo_row + ii);
+            mi = __ldg(p.indices + ii);
+            todo = !row_contains(p.indices, __ldg(p.indptr + mu), __ldg(p.indptr + mu + 1), mj);
+            if (!todo) ++n_skipped;
+        }
+        __syncthreads();                            // previous window fully retired
+        if (lane == 0) { s_u[w] = mu; s_i[w] = mi; s_j[w] = mj; s_pending[w] = todo ? 1 : 0; }
+        for (;;) {
+            if (!__syncthreads_or(todo)) break;     // also publishes the state written in the last round
+            bool run = false;
+            if (todo) {
+                bool conflict = false;
+                if (lane < w && s_pending[lane]) {
+                    const int ou = s_u[lane], oi = s_i[lane], oj = s_j[lane];
+                    conflict = (ou == mu) | (oi == mi) | (oi == mj) | (oj == mi) | (oj == mj);
+                }
+                run = !__any_sync(0xffffffffu, conflict);
+            }
+            __syncthreads();                        // everybody has read the snapshot of s_pending
+            if (run) {
+                float* pu = p.U + (size_t)mu * k;
+                float* pi = p.V + (size_t)mi * k;
+                float* pj = p.V + (size_t)mj * k;
+                const float bi = __ldcg(p.B + mi), bj = __ldcg(p.B + mj);
+                float part = 0.f;
+                for (int f = lane; f < p.k; f += 32)
+                    part = __fadd_rn(part, __fmul_rn(__ldcg(pu + f), __fsub_rn(__ldcg(pi + f), __ldcg(pj + f))));
+                const float score = __fadd_rn(__fsub_rn(bi, bj), group_sum<32>(part));
+                float z = 1.f;
+                bool update = true;
+                if (p.hinge) {                      // recom_mmmf.pyx:137-139
+                    if (score > 0.f) { ++n_correct; update = false; }
+                } else {
+                    z = (float)(1.0 / (1.0 + exp((double)score)));
+                    n_correct += (z < .5f);
+                }
+                if (update) {
+                    const float lr = p.lr, reg = p.reg;
+                    for (int f = lane; f < p.k; f += 32) {
+                        const float uf = __ldcg(pu + f), vi = __ldcg(pi + f), vj = __ldcg(pj + f);
+                        __stcg(pu + f, __fadd_rn(uf, __fmul_rn(lr, __fsub_rn(__fmul_rn(z, __fsub_rn(vi, vj)), __fmul_rn(reg, uf)))));
+                        __stcg(pi + f, __fadd_rn(vi, __fmul_rn(lr, __fsub_rn(__fmul_rn(z, uf), __fmul_rn(reg, vi)))));
+                        __stcg(pj + f, __fadd_rn(vj, __fmul_rn(lr, __fsub_rn(__fmul_rn(-z, uf), __fmul_rn(reg, vj)))));
+                    }
+                    if (p.use_bias && lane == 0) {
+                        __stcg(p.B + mi, __fadd_rn(bi, __fmul_rn(lr, __fsub_rn(z, __fmul_rn(reg, bi)))));
+                        __stcg(p.B + mj, __fadd_rn(bj, __fmul_rn(lr, __fsub_rn(-z, __fmul_rn(reg, bj)))));
+                    }
+                }
+                todo = false;
+                if (lane == 0) s_pending[w] = 0;
+            }
+        }
+    }
+    if (lane == 0) {
+        atomicAdd(p.stats + 0, n_correct);
+        atomicAdd(p.stats + 1, n_skipped);
+    }
+}
+
 template <int G, int NPL, bool VEC, bool ATOMIC, int S, int MINB>
 static int launch_hogwild_s(const BprParams& p, cudaStream_t st, const HogwildTune& tune)
 {
@@ -654,7 +734,9 @@ extern "C" int b200_bpr_epoch_replay(const int64_t* i_index, const int32_t* j_id
     p.hinge = (flags & B200_BPR_LOSS_HINGE) ? 1 : 0;
     if (p.hinge) p.use_bias = 1;
     p.stats = reinterpret_cast<unsigned long long*>(stats);
-    bpr_replay_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(p);
+    const char* serial = getenv("B200_REPLAY_SERIAL");
+    if (serial && serial[0] == '1') bpr_replay_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(p);
+    else bpr_replay_window_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(p);
     B200_CUDA(cudaGetLastError());
     return B200_OK;
 }

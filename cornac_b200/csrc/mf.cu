@@ -6,6 +6,8 @@
 //     scatter-update (plain stores or red.global.add), per-epoch sum(err^2) reduced per block.
 //   * mf_replay_kernel  : one warp, ratings applied strictly in stored order (the seeded
 //     single-thread reference, mf/recom_mf.py:124-125), loss accumulated in the same order.
+#include <stdlib.h>
+
 #include "sgd_common.cuh"
 
 namespace b200 {
@@ -156,6 +158,70 @@ __global__ void __launch_bounds__(32) mf_replay_kernel(const MfParams<IdT> p)
     if (lane == 0) *p.loss = loss;
 }
 
+// Ordered mode, windowed (same idea as bpr_replay_window_kernel): 32 consecutive ratings are resolved at a
+// time, one per warp, and applied as soon as no EARLIER pending rating of the window has the same user or
+// the same item.  Ratings that share neither commute exactly; the per-epoch loss is summed in rating order
+// afterwards from the per-rating squared errors so that it matches the reference's f32 accumulator.
+template <typename IdT>
+__global__ void __launch_bounds__(1024) mf_replay_window_kernel(const MfParams<IdT> p)
+{
+    __shared__ long long s_u[32], s_i[32];
+    __shared__ int s_pending[32];
+    __shared__ float s_err2[32];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t k = (size_t)p.k;
+    float loss = 0.f;                               // meaningful in thread 0 only
+    for (int64_t base = 0; base < p.n; base += 32) {
+        const int64_t s = base + w;
+        long long mu = -1, mi = -1;
+        float mr = 0.f;
+        bool todo = false;
+        if (s < p.n) { mu = (long long)p.rid[s]; mi = (long long)p.cid[s]; mr = p.val[s]; todo = true; }
+        __syncthreads();
+        if (lane == 0) { s_u[w] = mu; s_i[w] = mi; s_pending[w] = todo ? 1 : 0; s_err2[w] = 0.f; }
+        for (;;) {
+            if (!__syncthreads_or(todo)) break;
+            bool run = false;
+            if (todo) {
+                bool conflict = false;
+                if (lane < w && s_pending[lane]) conflict = (s_u[lane] == mu) | (s_i[lane] == mi);
+                run = !__any_sync(0xffffffffu, conflict);
+            }
+            __syncthreads();
+            if (run) {
+                float* pu = p.U + (size_t)mu * k;
+                float* pi = p.V + (size_t)mi * k;
+                const float bu = __ldcg(p.Bu + mu), bi = __ldcg(p.Bi + mi);
+                float part = 0.f;
+                for (int f = lane; f < p.k; f += 32) part = __fadd_rn(part, __fmul_rn(__ldcg(pu + f), __ldcg(pi + f)));
+                const float r_pred = __fadd_rn(__fadd_rn(__fadd_rn(p.mu, bu), bi), group_sum<32>(part));
+                const float err = __fsub_rn(mr, r_pred);
+                const float lr = p.lr, reg = p.reg;
+                for (int f = lane; f < p.k; f += 32) {
+                    const float uf = __ldcg(pu + f), vf = __ldcg(pi + f);
+                    __stcg(pu + f, __fadd_rn(uf, __fmul_rn(lr, __fsub_rn(__fmul_rn(err, vf), __fmul_rn(reg, uf)))));
+                    __stcg(pi + f, __fadd_rn(vf, __fmul_rn(lr, __fsub_rn(__fmul_rn(err, uf), __fmul_rn(reg, vf)))));
+                }
+                if (lane == 0) {
+                    if (p.use_bias) {
+                        __stcg(p.Bu + mu, __fadd_rn(bu, __fmul_rn(lr, __fsub_rn(err, __fmul_rn(reg, bu)))));
+                        __stcg(p.Bi + mi, __fadd_rn(bi, __fmul_rn(lr, __fsub_rn(err, __fmul_rn(reg, bi)))));
+                    }
+                    s_err2[w] = __fmul_rn(err, err);
+                    s_pending[w] = 0;
+                }
+                todo = false;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {                     // loss += err^2 in rating order (backend_cpu.pyx:72)
+            const int n_here = (int)min((int64_t)32, p.n - base);
+            for (int t = 0; t < n_here; ++t) loss = __fadd_rn(loss, s_err2[t]);
+        }
+    }
+    if (threadIdx.x == 0) *p.loss = loss;
+}
+
 template <typename IdT, int G, int NPL, bool VEC, bool ATOMIC>
 static int launch_mf(const MfParams<IdT>& p, cudaStream_t st)
 {
@@ -196,7 +262,9 @@ static int mf_epoch_impl(const IdT* rid, const IdT* cid, const float* val, int64
     B200_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
     if (n == 0) return B200_OK;
     if (ordered) {
-        mf_replay_kernel<IdT><<<1, 32, 0, st>>>(p);
+        const char* serial = getenv("B200_REPLAY_SERIAL");
+        if (serial && serial[0] == '1') mf_replay_kernel<IdT><<<1, 32, 0, st>>>(p);
+        else mf_replay_window_kernel<IdT><<<1, 1024, 0, st>>>(p);
         B200_CUDA(cudaGetLastError());
         return B200_OK;
     }

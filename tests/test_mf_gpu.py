@@ -112,3 +112,31 @@ def test_hogwild_training_tracks_cpu_hogwild():
         gpu.append(0.5 * loss.item())
     assert gpu[-1] < 0.5 * gpu[0]
     assert abs(gpu[-1] - cpu[-1]) < 0.25 * cpu[-1]      # Hogwild vs Hogwild: same regime, not the same trajectory
+
+
+@pytest.mark.parametrize("hot", [False, True])
+def test_windowed_ordered_epoch_is_bit_identical_to_serial(hot, monkeypatch):
+    import torch
+    from cornac_b200 import engine
+    n_users, n_items = (30, 9) if hot else (4000, 2500)
+    n, k = 20007, 20
+    rng = np.random.RandomState(8)
+    rid = rng.randint(n_users, size=n).astype(np.int64)
+    cid = rng.randint(n_items, size=n).astype(np.int64)
+    val = rng.randint(1, 6, size=n).astype(np.float32)
+    U0, V0, Bu0, Bi0 = O.mf_init(3, n_users, n_items, k)
+    outs = []
+    for serial in ("1", "0"):
+        monkeypatch.setenv("B200_REPLAY_SERIAL", serial)
+        U, V, Bu, Bi = _dev(U0), _dev(V0), _dev(Bu0), _dev(Bi0)
+        loss = torch.zeros(1, dtype=torch.float32, device="cuda")
+        for _ in range(2):
+            engine.mf_epoch(_dev(rid), _dev(cid), _dev(val), U, V, Bu, Bi, 0.01, 0.02, 3.0, True, loss, ordered=True)
+        outs.append((U.cpu().numpy(), V.cpu().numpy(), Bu.cpu().numpy(), Bi.cpu().numpy(), loss.item()))
+    for a, b in zip(outs[0][:4], outs[1][:4]):
+        assert np.array_equal(a, b)
+    assert outs[0][4] == outs[1][4]
+    Ur, Vr, Bur, Bir = U0.copy(), V0.copy(), Bu0.copy(), Bi0.copy()
+    for _ in range(2):
+        l_ref = O.mf_epoch(rid, cid, val, Ur, Vr, Bur, Bir, 0.01, 0.02, 3.0, True)
+    assert rel_err(outs[1][0], Ur) < 1e-5 and abs(0.5 * outs[1][4] - l_ref) < 1e-4 * l_ref
