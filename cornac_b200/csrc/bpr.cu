@@ -531,8 +531,21 @@ __global__ void __launch_bounds__(1024) bpr_replay_window_kernel(const ReplayPar
                 float* pi = p.V + (size_t)mi * k;
                 float* pj = p.V + (size_t)mj * k;
                 const float bi = __ldcg(p.B + mi), bj = __ldcg(p.B + mj);
+                // the first RC elements per lane stay in registers between the dot and the update (k <= 128:
+                // the rows are read from L2 once per sample instead of twice)
+                constexpr int RC = 4;
+                float ru[RC], ri[RC], rj[RC];
                 float part = 0.f;
-                for (int f = lane; f < p.k; f += 32)
+#pragma unroll
+                for (int t = 0; t < RC; ++t) {
+                    const int f = lane + 32 * t;
+                    ru[t] = ri[t] = rj[t] = 0.f;
+                    if (f < p.k) { ru[t] = __ldcg(pu + f); ri[t] = __ldcg(pi + f); rj[t] = __ldcg(pj + f); }
+                }
+#pragma unroll
+                for (int t = 0; t < RC; ++t)
+                    if (lane + 32 * t < p.k) part = __fadd_rn(part, __fmul_rn(ru[t], __fsub_rn(ri[t], rj[t])));
+                for (int f = lane + 32 * RC; f < p.k; f += 32)
                     part = __fadd_rn(part, __fmul_rn(__ldcg(pu + f), __fsub_rn(__ldcg(pi + f), __ldcg(pj + f))));
                 const float score = __fadd_rn(__fsub_rn(bi, bj), group_sum<32>(part));
                 float z = 1.f;
@@ -545,7 +558,17 @@ __global__ void __launch_bounds__(1024) bpr_replay_window_kernel(const ReplayPar
                 }
                 if (update) {
                     const float lr = p.lr, reg = p.reg;
-                    for (int f = lane; f < p.k; f += 32) {
+#pragma unroll
+                    for (int t = 0; t < RC; ++t) {
+                        const int f = lane + 32 * t;
+                        if (f < p.k) {
+                            const float uf = ru[t], vi = ri[t], vj = rj[t];
+                            __stcg(pu + f, __fadd_rn(uf, __fmul_rn(lr, __fsub_rn(__fmul_rn(z, __fsub_rn(vi, vj)), __fmul_rn(reg, uf)))));
+                            __stcg(pi + f, __fadd_rn(vi, __fmul_rn(lr, __fsub_rn(__fmul_rn(z, uf), __fmul_rn(reg, vi)))));
+                            __stcg(pj + f, __fadd_rn(vj, __fmul_rn(lr, __fsub_rn(__fmul_rn(-z, uf), __fmul_rn(reg, vj)))));
+                        }
+                    }
+                    for (int f = lane + 32 * RC; f < p.k; f += 32) {
                         const float uf = __ldcg(pu + f), vi = __ldcg(pi + f), vj = __ldcg(pj + f);
                         __stcg(pu + f, __fadd_rn(uf, __fmul_rn(lr, __fsub_rn(__fmul_rn(z, __fsub_rn(vi, vj)), __fmul_rn(reg, uf)))));
                         __stcg(pi + f, __fadd_rn(vi, __fmul_rn(lr, __fsub_rn(__fmul_rn(z, uf), __fmul_rn(reg, vi)))));
