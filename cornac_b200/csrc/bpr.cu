@@ -496,22 +496,36 @@ static HogwildTune read_tune()
 // rounds instead of 32 serial updates.
 __global__ void __launch_bounds__(1024) bpr_replay_window_kernel(const ReplayParams p)
 {
+    __shared__ int m_u[1024], m_i[1024], m_j[1024];
+    __shared__ unsigned char m_todo[1024];
     __shared__ int s_u[32], s_i[32], s_j[32], s_pending[32];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t k = (size_t)p.k;
     unsigned long long n_correct = 0, n_skipped = 0;
-    for (int64_t base = 0; base < p.n_samples; base += 32) {
-        const int64_t s = base + w;
-        int32_t mu = 0, mi = 0, mj = 0;
-        bool todo = false;
-        if (s < p.n_samples) {                      // warp-uniform; all lanes resolve the same sample
-            const int64_t ii = p.i_index[s];
-            mj = p.j_id[s];
-            mu = __ldg(p.coo_row + ii);
-            mi = __ldg(p.indices + ii);
-            todo = !row_contains(p.indices, __ldg(p.indptr + mu), __ldg(p.indptr + mu + 1), mj);
-            if (!todo) ++n_skipped;
+    for (int64_t base0 = 0; base0 < p.n_samples; base0 += 1024) {
+        // ---- resolve 1024 samples at once, one per THREAD (read-only inputs => order-free): the ~10
+        //      dependent gathers of (u, i, skip test) are paid once per 32 windows
+        __syncthreads();
+        {
+            const int64_t s = base0 + threadIdx.x;
+            int32_t mu = 0, mi = 0, mj = 0;
+            bool todo = false;
+            if (s < p.n_samples) {
+                const int64_t ii = p.i_index[s];
+                mj = p.j_id[s];
+                mu = __ldg(p.coo_row + ii);
+                mi = __ldg(p.indices + ii);
+                todo = !row_contains(p.indices, __ldg(p.indptr + mu), __ldg(p.indptr + mu + 1), mj);
+                if (!todo) ++n_skipped;             // counted per thread, summed at the end
+            }
+            m_u[threadIdx.x] = mu; m_i[threadIdx.x] = mi; m_j[threadIdx.x] = mj; m_todo[threadIdx.x] = todo ? 1 : 0;
         }
+        __syncthreads();
+        const int n_win = (int)min((int64_t)32, (p.n_samples - base0 + 31) / 32);
+      for (int win = 0; win < n_win; ++win) {
+        const int slot = win * 32 + w;              // this warp's sample of the window
+        const int32_t mu = m_u[slot], mi = m_i[slot], mj = m_j[slot];
+        bool todo = m_todo[slot] != 0;
         __syncthreads();                            // previous window fully retired
         if (lane == 0) { s_u[w] = mu; s_i[w] = mi; s_j[w] = mj; s_pending[w] = todo ? 1 : 0; }
         for (;;) {
@@ -583,10 +597,13 @@ __global__ void __launch_bounds__(1024) bpr_replay_window_kernel(const ReplayPar
                 if (lane == 0) s_pending[w] = 0;
             }
         }
+      }
     }
+    // correct: one count per warp (lane 0); skipped: one count per resolving thread
+    const unsigned long long sk = __reduce_add_sync(0xffffffffu, (unsigned)n_skipped);
     if (lane == 0) {
         atomicAdd(p.stats + 0, n_correct);
-        atomicAdd(p.stats + 1, n_skipped);
+        atomicAdd(p.stats + 1, sk);
     }
 }
 
