@@ -33,6 +33,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOAD = dict(n_users=1_000_000, n_items=100_000, nnz=100_000_000, k=64, lr=0.05, reg=0.01, use_bias=True)
+# one GPU's share of BASELINE.json configs[2] (10M users x 1M items x 1B interactions, k=128, over 8 GPUs); `--workload c3shard`
+WORKLOAD_C3_SHARD = dict(n_users=1_250_000, n_items=1_000_000, nnz=125_000_000, k=128, lr=0.05, reg=0.01, use_bias=True)
 RANK_WORKLOAD = dict(n_q=75776, topk=100)          # secondary metric: ranked users/s on the same model
 CPU_SAMPLE = dict(n_users=100_000, nnz_target=10_000_000)   # bounded sample for the CPU legs (same k, same items)
 
@@ -231,6 +233,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debug only; result then INVALID)")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3shard"],
+                    help="c2 = BASELINE configs[1] per GPU (default, the quoted metric); c3shard = one GPU's share of configs[2]")
     ap.add_argument("--atomic", type=int, default=1, help="1: red.global.add scatter (default), 0: plain racy stores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -244,7 +248,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    W = dict(WORKLOAD)
+    W = dict(WORKLOAD if args.workload == "c2" else WORKLOAD_C3_SHARD)
     if args.scale != 1.0:
         W["n_users"] = max(1000, int(W["n_users"] * args.scale))
         W["nnz"] = max(10000, int(W["nnz"] * args.scale))
@@ -336,7 +340,7 @@ def main():
             traffic = json.load(open(prof)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"kernel": "bpr_hogwild_chunk_kernel<G=16,NPL=1,VEC,%s>" % ("ATOMIC" if args.atomic else "PLAIN"), "bound": "hbm", "achieved": round(achieved, 1),
+    roofline = {"kernel": "bpr_hogwild_chunk_kernel<G=%d,NPL=1,VEC,%s>" % (min(32, max(4, k // 4)), "ATOMIC" if args.atomic else "PLAIN"), "bound": "hbm", "achieved": round(achieved, 1),
                 "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_update": 24 * k + 32 + 4 * math.ceil(math.log2(mean_deg + 1)),
                 "kernel_ms": round(kern_ms, 3)}
@@ -370,11 +374,13 @@ def main():
             "metric": "BPR triplet-updates/sec", "value": round(value, 1), "unit": "updates/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "BASELINE.json configs[1]: %d users x %d items x %d interactions per GPU, BPR k=%d, "
+            "config": {"workload": ("BASELINE.json configs[1]" if args.workload == "c2" else "1/8 of BASELINE.json configs[2]")
+                                   + ": %d users x %d items x %d interactions per GPU, BPR k=%d, "
                                    "lr=%g reg=%g use_bias; user activity log-normal, item popularity Zipf(1.0), unique pairs"
                                    % (W["n_users"], W["n_items"], nnz, k, W["lr"], W["reg"]),
                        "step": "one epoch = nnz sampled triplets (Hogwild, on-device Philox sampling)",
-                       "l2": "working set (U 256 MB + CSR 800 MB per GPU) exceeds the 126 MB L2; no flush needed",
+                       "l2": "working set (U %d MB + pair store %d MB + membership table per GPU) exceeds the 126 MB L2; no flush needed"
+                             % (W["n_users"] * k * 4 // 1000000, nnz * 8 // 1000000),
                        "parallelism": "users sharded x%d, items replicated, 1 all-reduce of item deltas per epoch" % world,
                        "scatter": "red.global.add.v4.f32" if args.atomic else "st.global.cg.v4.f32 (Hogwild)"},
             "samples_per_s": round((nnz * args.steps * world) / (ms_total * 1e-3), 1),
@@ -477,7 +483,7 @@ def run_rank(W, engine, data, U, V, B, dev):
     ms_h = (time.perf_counter() - t0) / 3 * 1e3
     h2d = h_u.numel() * 8 + h_p.numel() * 8 + h_i.numel() * 4
     return {"metric": "ranked users/sec", "value": round(n_q / (ms * 1e-3), 1), "unit": "users/s",
-            "config": "%d users x %d items k=%d top-%d, train positives excluded (BASELINE configs[1] model)" % (n_q, W["n_items"], k, topk),
+            "config": "%d users x %d items k=%d top-%d, train positives excluded (the bench's BPR model)" % (n_q, W["n_items"], k, topk),
             "ms": round(ms, 3), "tflops": round(2.0 * k * W["n_items"] * n_q / (ms * 1e-3) / 1e12, 2),
             "e2e": {"value": round(n_q / (ms_h * 1e-3), 1), "unit": "users/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(n_q * topk * 8), "ms": round(ms_h, 3),
