@@ -335,7 +335,7 @@ def main():
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
     traffic = None
     prof = os.path.join(ROOT, "profiles", "bpr_hogwild_dram_bytes.json")
-    if os.path.exists(prof):
+    if os.path.exists(prof) and args.workload == "c2" and args.scale == 1.0:      # the capture is of this workload
         try:
             traffic = json.load(open(prof)).get("dram_bytes_per_launch")
         except Exception:

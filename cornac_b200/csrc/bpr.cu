@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(256, MINB) bpr_hogwild_kernel(const BprParams 
 // instructions per sample.  The G resolved triplets are then broadcast one by one with warp
 // shuffles and applied by the whole group (row gathers of sample t+1 are issued before the
 // arithmetic of sample t).
-template <int G, int NPL, bool VEC, bool ATOMIC, int MINB>
+template <int G, int NPL, bool VEC, bool ATOMIC, int MINB, int DEPTH>
 __global__ void __launch_bounds__(256, MINB) bpr_hogwild_chunk_kernel(const BprParams p)
 {
     using Frag = RowFrag<NPL, VEC>;
@@ -268,11 +268,12 @@ __global__ void __launch_bounds__(256, MINB) bpr_hogwild_chunk_kernel(const BprP
             } while (!found && full);              // rare: the bucket overflowed into the next one
             if (mlive && found) { mlive = 0; ++n_skipped; }          // recom_bpr.pyx:241-243
         }
-        // ---- phase 2: apply the G samples one after the other, one row-gather ahead
-        Frag fu[2], fi[2], fj[2];
-        float bi[2], bj[2];
-        int32_t cu[2], ci[2], cj[2];
-        int cl[2];
+        // ---- phase 2: apply the G samples one after the other, DEPTH row-gathers ahead
+        constexpr int NSLOT = DEPTH + 1;
+        Frag fu[NSLOT], fi[NSLOT], fj[NSLOT];
+        float bi[NSLOT], bj[NSLOT];
+        int32_t cu[NSLOT], ci[NSLOT], cj[NSLOT];
+        int cl[NSLOT];
         auto fetch = [&](int t, int slot) {
             cu[slot] = __shfl_sync(gmask, mu, gbase + t);
             ci[slot] = __shfl_sync(gmask, mi, gbase + t);
@@ -286,11 +287,13 @@ __global__ void __launch_bounds__(256, MINB) bpr_hogwild_chunk_kernel(const BprP
                 bj[slot] = __ldcg(p.B + cj[slot]);
             }
         };
-        fetch(0, 0);
+#pragma unroll
+        for (int t = 0; t < DEPTH; ++t)
+            if (t < G) fetch(t, t % NSLOT);
 #pragma unroll
         for (int t = 0; t < G; ++t) {
-            const int cur = t & 1, nxt = cur ^ 1;
-            if (t + 1 < G) fetch(t + 1, nxt);
+            const int cur = t % NSLOT;
+            if (t + DEPTH < G) fetch(t + DEPTH, (t + DEPTH) % NSLOT);
             if (!cl[cur]) continue;                 // group-uniform
             float part = 0.f;
 #pragma unroll
@@ -631,10 +634,10 @@ static int launch_hogwild_s(const BprParams& p, cudaStream_t st, const HogwildTu
     return B200_OK;
 }
 
-template <int G, int NPL, bool VEC, bool ATOMIC, int MINB>
+template <int G, int NPL, bool VEC, bool ATOMIC, int MINB, int DEPTH>
 static int launch_hogwild_chunk(const BprParams& p, cudaStream_t st, const HogwildTune& tune)
 {
-    auto kern = bpr_hogwild_chunk_kernel<G, NPL, VEC, ATOMIC, MINB>;
+    auto kern = bpr_hogwild_chunk_kernel<G, NPL, VEC, ATOMIC, MINB, DEPTH>;
     const int threads = tune.threads;
     int occ = 0;
     B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, 0));
@@ -660,11 +663,15 @@ static int launch_hogwild(const BprParams& p, cudaStream_t st)
     constexpr int E = NPL * (VEC ? 4 : 1);
     const HogwildTune tune = read_tune();
     if constexpr (E <= 8) {
-        // measured on B200 (profiles/): 64-register variant wins for 16-lane groups, 80 registers
-        // (no spills) for 32-lane groups
+        // measured on B200 (profiles/r01_bpr_scatter_experiments.txt): 16-lane groups run best two row-gathers
+        // ahead at 3 blocks/SM (4.14 vs 3.90 G samples/s on C2); 32-lane groups gain nothing from the second slot
         if (tune.S == 0) {
-            if (G >= 32) return launch_hogwild_chunk<G, NPL, VEC, ATOMIC, 3>(p, st, tune);
-            return launch_hogwild_chunk<G, NPL, VEC, ATOMIC, 4>(p, st, tune);
+            if (G >= 32) return launch_hogwild_chunk<G, NPL, VEC, ATOMIC, 3, 1>(p, st, tune);
+            return launch_hogwild_chunk<G, NPL, VEC, ATOMIC, 3, 2>(p, st, tune);
+        }
+        if (tune.S == 32) {              // the other combination, for A/B runs
+            if (G >= 32) return launch_hogwild_chunk<G, NPL, VEC, ATOMIC, 3, 2>(p, st, tune);
+            return launch_hogwild_chunk<G, NPL, VEC, ATOMIC, 4, 1>(p, st, tune);
         }
     }
     if constexpr (E <= 4) {

@@ -1,5 +1,5 @@
 #!/usr/bin/env bash
-# GPU trip 23: one GPU's share of BASELINE configs[2] (1.25M users x 1M items x 125M interactions, k=128)
+# GPU trip 24: prefetch depth experiment at the C3-shard shape and at C2
 mkdir -p gpurun_out
 python -c "
 import torch, sys
@@ -7,5 +7,7 @@ sys.path.insert(0, '.')
 torch.zeros(1).cuda(); torch.cuda.synchronize()
 from cornac_b200 import _lib; _lib.load(); print('warm ok')
 " > gpurun_out/warm.log 2>&1
-( time timeout -s KILL 1200 python bench.py --workload c3shard --steps 10 --warmup 3 ) > gpurun_out/bench_c3shard.json 2> gpurun_out/bench_c3shard.err
-cat gpurun_out/bench_c3shard.json; tail -5 gpurun_out/bench_c3shard.err
+export B200_TUNE_DEPTH=1
+timeout -s KILL 600 python tools/tune_bpr.py --k 128 --users 1250000 --items 1000000 --nnz 125000000 > gpurun_out/tune_depth_c3.log 2>&1
+timeout -s KILL 600 python tools/tune_bpr.py --k 64 > gpurun_out/tune_depth_c2.log 2>&1
+cat gpurun_out/tune_depth_c3.log gpurun_out/tune_depth_c2.log

@@ -18,11 +18,20 @@ def main():
     ap.add_argument("--k", type=int, default=64)
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--uniform", type=int, default=0)
+    ap.add_argument("--items", type=int, default=0)
+    ap.add_argument("--users", type=int, default=0)
+    ap.add_argument("--nnz", type=int, default=0)
     args = ap.parse_args()
     W = dict(bench.WORKLOAD)
     W["k"] = args.k
     W["n_users"] = int(W["n_users"] * args.scale)
     W["nnz"] = int(W["nnz"] * args.scale)
+    if args.items:
+        W["n_items"] = args.items
+    if args.users:
+        W["n_users"] = args.users
+    if args.nnz:
+        W["nnz"] = args.nnz
     dev = torch.device("cuda", 0)
     indptr, indices = bench.synth_interactions(W["n_users"], W["n_items"], W["nnz"], 1234, dev)
     if args.uniform:
@@ -35,6 +44,9 @@ def main():
                 ("chunk minb4 plain-stores", "0,256,0", 0)]
     if os.environ.get("B200_TUNE_EXPERIMENT"):
         configs = [("default", "0,256,0", 1)]
+    if os.environ.get("B200_TUNE_DEPTH"):
+        configs = [("depth1 (default)", "0,256,0", 1), ("depth2 minb3", "32,256,0", 1), ("depth1 blk=2", "0,256,2", 1),
+                   ("depth2 blk=2", "32,256,2", 1)]
     for name, tune, at in configs:
         os.environ["B200_BPR_TUNE"] = tune
         for e in range(2):
