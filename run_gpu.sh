@@ -1,5 +1,5 @@
 #!/usr/bin/env bash
-# GPU trip 24: prefetch depth experiment at the C3-shard shape and at C2
+# GPU trip 25: full validation of HEAD
 mkdir -p gpurun_out
 python -c "
 import torch, sys
@@ -7,7 +7,8 @@ sys.path.insert(0, '.')
 torch.zeros(1).cuda(); torch.cuda.synchronize()
 from cornac_b200 import _lib; _lib.load(); print('warm ok')
 " > gpurun_out/warm.log 2>&1
-export B200_TUNE_DEPTH=1
-timeout -s KILL 600 python tools/tune_bpr.py --k 128 --users 1250000 --items 1000000 --nnz 125000000 > gpurun_out/tune_depth_c3.log 2>&1
-timeout -s KILL 600 python tools/tune_bpr.py --k 64 > gpurun_out/tune_depth_c2.log 2>&1
-cat gpurun_out/tune_depth_c3.log gpurun_out/tune_depth_c2.log
+( time timeout -s KILL 1500 python -m pytest tests -x -q -m gpu ) > gpurun_out/pytest.log 2>&1
+echo "pytest exit $?" >> gpurun_out/pytest.log
+timeout -s KILL 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
+( time timeout -s KILL 900 python bench.py ) > gpurun_out/bench.json 2> gpurun_out/bench.err
+tail -8 gpurun_out/pytest.log; tail -2 gpurun_out/smoke.log; cat gpurun_out/bench.json; tail -4 gpurun_out/bench.err
