@@ -43,6 +43,7 @@ SIGNATURES = {
     "b200_rank_topk": (_int, [_vp, _vp, _i64, _vp, _i64, _int, _vp, _vp, _vp, _vp, _int, _vp, _vp,
                               _vp, _i64, _vp]),
     "b200_rank_tc_debug_scores": (_int, [_vp, _i64, _vp, _i64, _int, _vp, _vp, _i64, _vp, _i64, _vp]),
+    "b200_topk_metrics": (_int, [_vp, _i64, _int, _i64, _vp, _vp, _vp, _vp, _vp, _int, _vp, _vp]),
     "b200_delta_make": (_int, [_vp, _vp, _vp, _i64, _vp]),
     "b200_delta_apply": (_int, [_vp, _vp, _vp, _i64, _vp]),
 }
@@ -52,6 +53,7 @@ SGD_EXACT_EXP = 2
 SGD_UNBOUNDED = 4
 BPR_NEG_WEIGHTED = 8
 BPR_LOSS_HINGE = 16
+METRIC_NDCG, METRIC_PRECISION, METRIC_RECALL, METRIC_FMEASURE, METRIC_HIT, METRIC_NCRR = range(6)
 
 _lib = None
 

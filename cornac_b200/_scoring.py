@@ -67,25 +67,37 @@ class DeviceScoringMixin:
         """
         d = self._b200_device()
         user_indices = np.asarray(user_indices, dtype=np.int64)
-        n_q = len(user_indices)
-        ex_ptr = ex_idx = None
-        if exclude is not None:
-            sub = exclude[user_indices] if n_q != exclude.shape[0] or not np.array_equal(
-                user_indices, np.arange(exclude.shape[0])) else exclude
-            sub = sub.tocsr()
-            sub.sort_indices()
-            ex_ptr, ex_idx = sub.indptr.astype(np.int64), sub.indices.astype(np.int32)
-        uidx = torch.from_numpy(user_indices).cuda()
-        uoff = None if d["user_off"] is None else d["user_off"][uidx].contiguous()
-        if uoff is None:
+        ex_ptr, ex_idx = self._b200_exclusion_rows(user_indices, exclude)
+        if d["user_off"] is None:
             return engine.rank_topk_host(d["U"], d["V"][: d["n_items"]], int(k), user_indices, item_base=d["item_base"],
                                          excl_indptr=ex_ptr, excl_indices=ex_idx)
+        ids, sc = self.rank_batch_device(user_indices, k, exclude=exclude, _rows=(ex_ptr, ex_idx))
+        return ids.cpu().numpy(), sc.cpu().numpy()
+
+    @staticmethod
+    def _b200_exclusion_rows(user_indices, exclude):
+        if exclude is None:
+            return None, None
+        n_q = len(user_indices)
+        sub = exclude[user_indices] if n_q != exclude.shape[0] or not np.array_equal(
+            user_indices, np.arange(exclude.shape[0])) else exclude
+        sub = sub.tocsr()
+        sub.sort_indices()
+        return sub.indptr.astype(np.int64), sub.indices.astype(np.int32)
+
+    def rank_batch_device(self, user_indices, k, exclude=None, _rows=None):
+        """`rank_batch` leaving the result on the GPU: (ids int32 [n_q, k], scores f32 [n_q, k]) CUDA tensors
+        (what the device-side metric reduction of cornac_b200.evaluation consumes)."""
+        d = self._b200_device()
+        user_indices = np.asarray(user_indices, dtype=np.int64)
+        ex_ptr, ex_idx = _rows if _rows is not None else self._b200_exclusion_rows(user_indices, exclude)
+        uidx = engine.to_device(user_indices, torch.int64)
+        uoff = None if d["user_off"] is None else d["user_off"][uidx].contiguous()
         ep = None if ex_ptr is None else engine.to_device(ex_ptr, torch.int64)
         ei = None if ex_ptr is None else (engine.to_device(ex_idx, torch.int32) if len(ex_idx) else
                                           torch.zeros(1, dtype=torch.int32, device="cuda"))
-        ids, sc = engine.rank_topk(d["U"], d["V"], int(k), user_idx=uidx, item_base=d["item_base"], user_off=uoff,
-                                   excl_indptr=ep, excl_indices=ei, n_items=d["n_items"])
-        return ids.cpu().numpy(), sc.cpu().numpy()
+        return engine.rank_topk(d["U"], d["V"], int(k), user_idx=uidx, item_base=d["item_base"], user_off=uoff,
+                                excl_indptr=ep, excl_indices=ei, n_items=d["n_items"])
 
     # ---- Recommender.rank ------------------------------------------------------------
     def _b200_rank(self, all_scores_dev, item_indices, k):

@@ -294,9 +294,9 @@ extern "C" int b200_mf_epoch(const void* rid, const void* cid, const float* val,
                              float lr, float reg, float mu, int use_bias, int ordered,
                              unsigned flags, float* loss, void* stream)
 {
-    B200_REQUIRE(U && V && Bu && Bi && loss, "b200_mf_epoch: null pointer argument");
+    B200_REQUIRE(Bu && Bi && loss && (k == 0 || (U && V)), "b200_mf_epoch: null pointer argument");
     B200_REQUIRE(n >= 0 && (n == 0 || (rid && cid && val)), "b200_mf_epoch: bad rating arrays");
-    B200_REQUIRE(k >= 1 && k <= 1024, "b200_mf_epoch: k=%d out of range [1, 1024]", k);
+    B200_REQUIRE(k >= 0 && k <= 1024, "b200_mf_epoch: k=%d out of range [0, 1024]", k);
     B200_REQUIRE(n_users >= 1 && n_items >= 1, "b200_mf_epoch: bad n_users/n_items");
     cudaStream_t st = (cudaStream_t)stream;
     if (ids_are_i32)

@@ -403,24 +403,31 @@ template <bool DUMP>
 __device__ __forceinline__ void epilogue_chunk(uint32_t (&r)[32], RowState& st, int32_t id0,
                                                float* __restrict__ dump_row, bool valid)
 {
+    if (DUMP) {
+        if (valid) {
+#pragma unroll
+            for (int x = 0; x < 32; ++x) dump_row[id0 + x] = __uint_as_float(r[x]);
+        }
+        return;
+    }
+    // phase 1: the eight group votes back to back (no branch between them, so their latencies overlap)
+    bool hit[8];
 #pragma unroll
     for (int j4 = 0; j4 < 8; ++j4) {
-        const float sc[4] = {__uint_as_float(r[j4 * 4 + 0]), __uint_as_float(r[j4 * 4 + 1]),
-                             __uint_as_float(r[j4 * 4 + 2]), __uint_as_float(r[j4 * 4 + 3])};
-        if (DUMP) {
-            if (valid) {
+        const float m = fmaxf(fmaxf(__uint_as_float(r[j4 * 4 + 0]), __uint_as_float(r[j4 * 4 + 1])),
+                              fmaxf(__uint_as_float(r[j4 * 4 + 2]), __uint_as_float(r[j4 * 4 + 3])));
+        hit[j4] = __any_sync(0xffffffffu, m > st.tau_f);          // warp-uniform
+    }
+    // phase 2: predicated appends for the groups some lane of the warp has a hit in
 #pragma unroll
-                for (int x = 0; x < 4; ++x) dump_row[id0 + j4 * 4 + x] = sc[x];
-            }
-        } else {
-            const float m = fmaxf(fmaxf(sc[0], sc[1]), fmaxf(sc[2], sc[3]));
-            if (__any_sync(0xffffffffu, m > st.tau_f)) {          // warp-uniform
+    for (int j4 = 0; j4 < 8; ++j4) {
+        if (hit[j4]) {
 #pragma unroll
-                for (int x = 0; x < 4; ++x) {
-                    if (sc[x] > st.tau_f) {
-                        *st.wp = ((unsigned long long)__float_as_uint(sc[x]) << 32) | (uint32_t)(id0 + j4 * 4 + x);
-                        st.wp += 32;
-                    }
+            for (int x = 0; x < 4; ++x) {
+                const float sc = __uint_as_float(r[j4 * 4 + x]);
+                if (sc > st.tau_f) {
+                    *st.wp = ((unsigned long long)__float_as_uint(sc) << 32) | (uint32_t)(id0 + j4 * 4 + x);
+                    st.wp += 32;
                 }
             }
         }
@@ -613,12 +620,25 @@ struct FinishParams {
     int* __restrict__ overflow_rows;           // [0] = count, [1..] = global query indices
 };
 
+// STAGED: the candidates' item rows are gathered warp-cooperatively (one coalesced 16-byte cp.async per lane
+// and row, 32 rows in flight per warp) into shared memory, then every lane runs the serial f64 chain of ITS
+// candidate out of shared memory (row stride = k*4 + 16 bytes: conflict-free 16-byte reads).  A thread
+// gathering its own row from global memory touches 32 different lines per load instruction and thrashes L1.
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
+
+template <bool STAGED>
 __global__ void __launch_bounds__(128) rank_tc_finish_kernel(const FinishParams p)
 {
+    extern __shared__ __align__(16) unsigned char fin_stage[];      // STAGED: [128 rows][k*4 + 16 bytes]
     __shared__ unsigned long long sort_buf[2 * CAP];
     __shared__ double su[MAX_KP];                   // the user's factors, widened once per row
     const int tid = threadIdx.x;
     const bool vec4 = (p.k % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.V) & 15) == 0);
+    const int stride = p.k * 4 + 16;
     for (int64_t row = blockIdx.x; row < p.n_rows; row += gridDim.x) {
         __syncthreads();
         if (p.row_flag[row * 2] | p.row_flag[row * 2 + 1]) {
@@ -650,46 +670,73 @@ __global__ void __launch_bounds__(128) rank_tc_finish_kernel(const FinishParams 
         __syncthreads();
         for (int e = tid; e < sort_n; e += 128) {
             unsigned long long key = 0ull;
+            int32_t id = -1;
             if (e < L) {
                 const unsigned long long ent = e < L0 ? list0[(size_t)e * 32] : list1[(size_t)(e - L0) * 32];
-                const int32_t id = (int32_t)(ent & 0xffffffffull);
-                bool excluded = false;
+                id = (int32_t)(ent & 0xffffffffull);
                 if (n_ex) {                         // entries appended after the last merge are still unfiltered
                     int lo = 0, hi = n_ex;
                     while (lo < hi) {
                         const int mid = (lo + hi) >> 1;
                         if (__ldg(ex + mid) < id) lo = mid + 1; else hi = mid;
                     }
-                    excluded = lo < n_ex && __ldg(ex + lo) == id;
+                    if (lo < n_ex && __ldg(ex + lo) == id) id = -1;
                 }
-                if (!excluded) {
-                    const float* v = p.V + (size_t)id * p.k;
-                    double acc = 0.0;                      // f ascending, one f64 fma per factor: == score_batch_kernel
-                    if (vec4) {
-                        // the row gather is latency bound: keep 8 independent 16-byte loads in flight
-                        for (int f = 0; f < p.k; f += 32) {
-                            float4 x[8];
+            }
+            double acc = 0.0;                      // f ascending, one f64 fma per factor: == score_batch_kernel
+            if (STAGED) {
+                // sort_n is a multiple of 32 and e advances by 128: whole warps stay together in this loop
+                const int lane = tid & 31;
+                unsigned char* wstage = fin_stage + (size_t)(tid & ~31) * stride;
+                if (__any_sync(0xffffffffu, id >= 0)) {
+#pragma unroll 8
+                    for (int c = 0; c < 32; ++c) {
+                        const int32_t idc = __shfl_sync(0xffffffffu, id, c);
+                        if (idc >= 0 && lane * 4 < p.k)
+                            cp_async16(wstage + (size_t)c * stride + lane * 16, p.V + (size_t)idc * p.k + lane * 4);
+                    }
+                    cp_async_wait_all();
+                    __syncwarp();
+                    if (id >= 0) {
+                        const float4* rowp = reinterpret_cast<const float4*>(wstage + (size_t)lane * stride);
+                        for (int f = 0; f < p.k; f += 4) {
+                            const float4 x = rowp[f >> 2];
+                            acc = fma(su[f], (double)x.x, acc);
+                            acc = fma(su[f + 1], (double)x.y, acc);
+                            acc = fma(su[f + 2], (double)x.z, acc);
+                            acc = fma(su[f + 3], (double)x.w, acc);
+                        }
+                    }
+                    __syncwarp();                   // the stage is rewritten by the next batch
+                }
+            } else if (id >= 0) {
+                const float* v = p.V + (size_t)id * p.k;
+                if (vec4) {
+                    // the row gather is latency bound: keep 8 independent 16-byte loads in flight
+                    for (int f = 0; f < p.k; f += 32) {
+                        float4 x[8];
 #pragma unroll
-                            for (int i = 0; i < 8; ++i)
-                                x[i] = (f + 4 * i < p.k) ? __ldg(reinterpret_cast<const float4*>(v + f + 4 * i))
-                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int i = 0; i < 8; ++i)
+                            x[i] = (f + 4 * i < p.k) ? __ldg(reinterpret_cast<const float4*>(v + f + 4 * i))
+                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                if (f + 4 * i < p.k) {
-                                    acc = fma(su[f + 4 * i], (double)x[i].x, acc);
-                                    acc = fma(su[f + 4 * i + 1], (double)x[i].y, acc);
-                                    acc = fma(su[f + 4 * i + 2], (double)x[i].z, acc);
-                                    acc = fma(su[f + 4 * i + 3], (double)x[i].w, acc);
-                                }
+                        for (int i = 0; i < 8; ++i) {
+                            if (f + 4 * i < p.k) {
+                                acc = fma(su[f + 4 * i], (double)x[i].x, acc);
+                                acc = fma(su[f + 4 * i + 1], (double)x[i].y, acc);
+                                acc = fma(su[f + 4 * i + 2], (double)x[i].z, acc);
+                                acc = fma(su[f + 4 * i + 3], (double)x[i].w, acc);
                             }
                         }
-                    } else {
-                        for (int f = 0; f < p.k; ++f) acc = fma(su[f], (double)__ldg(v + f), acc);
                     }
-                    const float base = p.item_base ? __ldg(p.item_base + id) : 0.f;
-                    const float sc = __fadd_rn(__fadd_rn(base, uo), __double2float_rn(acc));      // == score_batch_kernel
-                    key = ((unsigned long long)float_key(sc) << 32) | (unsigned)(0xffffffffu - (unsigned)id);
+                } else {
+                    for (int f = 0; f < p.k; ++f) acc = fma(su[f], (double)__ldg(v + f), acc);
                 }
+            }
+            if (id >= 0) {
+                const float base = p.item_base ? __ldg(p.item_base + id) : 0.f;
+                const float sc = __fadd_rn(__fadd_rn(base, uo), __double2float_rn(acc));      // == score_batch_kernel
+                key = ((unsigned long long)float_key(sc) << 32) | (unsigned)(0xffffffffu - (unsigned)id);
             }
             sort_buf[e] = key;
         }
@@ -838,8 +885,19 @@ int rank_tc(const float* U, const int64_t* user_idx, int64_t n_q, const float* V
         f.out_ids = out_ids + (size_t)q0 * topk; f.out_scores = out_scores + (size_t)q0 * topk;
         f.overflow_rows = reinterpret_cast<int*>(ws + L.off_over);
         // latency-bound gathers: as many rows in flight per SM as the thread limit allows (16 x 128 threads)
-        const int fgrid = (int)(rows < (int64_t)sm_count() * 16 ? rows : (int64_t)sm_count() * 16);
-        rank_tc_finish_kernel<<<fgrid, 128, 0, st>>>(f);
+        const bool staged = (k % 4 == 0) && k <= 128 && ((reinterpret_cast<uintptr_t>(V) & 15) == 0) && !getenv("B200_RANK_FINISH_DIRECT");
+        if (staged) {
+            const size_t fsmem = (size_t)128 * (k * 4 + 16);
+            B200_CUDA(cudaFuncSetAttribute(rank_tc_finish_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+            int occ = 1;
+            B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rank_tc_finish_kernel<true>, 128, fsmem));
+            if (occ < 1) occ = 1;
+            const int64_t cap = (int64_t)sm_count() * occ;
+            rank_tc_finish_kernel<true><<<(int)(rows < cap ? rows : cap), 128, fsmem, st>>>(f);
+        } else {
+            const int fgrid = (int)(rows < (int64_t)sm_count() * 16 ? rows : (int64_t)sm_count() * 16);
+            rank_tc_finish_kernel<false><<<fgrid, 128, 0, st>>>(f);
+        }
         B200_CUDA(cudaGetLastError());
         // rows whose candidate list overflowed: exact path, one row at a time (rare; needs the count on the host)
         int n_over = 0;

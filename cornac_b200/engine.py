@@ -243,15 +243,20 @@ class MTSampler:
 
 
 def mf_epoch(rid, cid, val, U, V, Bu, Bi, lr, reg, mu, use_bias, loss, ordered=False, atomic=True, unbounded=False):
-    """One MF epoch; `loss` (float32[1] CUDA) receives sum(err^2)."""
+    """One MF epoch; `loss` (float32[1] CUDA) receives sum(err^2).  U = V = None: the bias-only model
+    (BaselineOnly), sized by Bu / Bi."""
     L = require_cuda()
     if rid.dtype not in (torch.int32, torch.int64) or cid.dtype != rid.dtype:
         raise B200Error("rid/cid must both be int32 or int64")
     _dev(rid, rid.dtype, "rid"), _dev(cid, rid.dtype, "cid"), _dev(val, torch.float32, "val")
     for n_, t_ in (("U", U), ("V", V), ("Bu", Bu), ("Bi", Bi), ("loss", loss)):
-        _dev(t_, torch.float32, n_)
+        if t_ is not None or n_ not in ("U", "V"):
+            _dev(t_, torch.float32, n_)
+    if (U is None) != (V is None):
+        raise B200Error("U and V must both be given or both be None")
+    k = 0 if U is None else int(U.shape[1])
     check(L.b200_mf_epoch(ptr(rid), ptr(cid), ptr(val), val.numel(), int(rid.dtype == torch.int32),
-                          int(U.shape[0]), int(V.shape[0]), ptr(U), ptr(V), ptr(Bu), ptr(Bi), int(U.shape[1]), float(lr), float(reg), float(mu),
+                          int(Bu.shape[0]), int(Bi.shape[0]), ptr(U), ptr(V), ptr(Bu), ptr(Bi), k, float(lr), float(reg), float(mu),
                           int(bool(use_bias)), int(bool(ordered)),
                           (_lib.SGD_ATOMIC if atomic else 0) | (_lib.SGD_UNBOUNDED if unbounded else 0), ptr(loss),
                           current_stream()), "b200_mf_epoch")
@@ -326,6 +331,24 @@ def rank_topk_host(U, V, topk, user_idx, item_base=None, excl_indptr=None, excl_
     torch.from_numpy(out_ids).copy_(ids)
     torch.from_numpy(out_scores).copy_(sc)
     return out_ids, out_scores
+
+
+def topk_metrics(ids, pos_indptr, pos_indices, kinds, ks, user_idx=None, topk=None):
+    """Per-user values of the @k ranking metrics for device ranked lists (b200_topk_metrics).
+    ids int32 [n_q, >=topk] CUDA; pos_* the test-positives CSR (int64 / int32 CUDA); kinds / ks python lists.
+    Returns a float64 CUDA tensor [n_metrics, n_q]."""
+    L = require_cuda()
+    _dev(ids, torch.int32, "ids"), _dev(pos_indptr, torch.int64, "pos_indptr"), _dev(pos_indices, torch.int32, "pos_indices")
+    n_q, stride = ids.shape
+    topk = stride if topk is None else int(topk)
+    if user_idx is not None:
+        _dev(user_idx, torch.int64, "user_idx")
+    mk = torch.tensor(list(kinds), dtype=torch.int32).to(ids.device)
+    kk = torch.tensor(list(ks), dtype=torch.int32).to(ids.device)
+    out = torch.empty((len(kinds), n_q), dtype=torch.float64, device=ids.device)
+    check(L.b200_topk_metrics(ptr(ids), n_q, topk, stride, ptr(user_idx), ptr(pos_indptr), ptr(pos_indices), ptr(mk),
+                              ptr(kk), len(kinds), ptr(out), current_stream()), "b200_topk_metrics")
+    return out
 
 
 def delta_make(x, snapshot, delta):

@@ -119,7 +119,10 @@ B200_API int b200_mt_sampler_fill_i32(b200_mt_sampler* s, int64_t hi, int64_t n,
  *   ordered = 1: ratings are applied with the same result as the stored-order sequential
  *                loop (seeded reference); ordered = 0: Hogwild over the whole GPU.
  *   loss device f32[1]: receives sum(err^2) of the epoch (caller multiplies by 0.5,
- *                backend_cpu.pyx:85); it is overwritten, not accumulated.                   */
+ *                backend_cpu.pyx:85); it is overwritten, not accumulated.
+ *   k = 0: the bias-only model -- one epoch of BaselineOnly._fit_sgd
+ *                (baseline_only/recom_bo.pyx:121-131: r_pred = mu + Bu[u] + Bi[i]); U and V are
+ *                not read and may be NULL, n_users / n_items are then given explicitly.     */
 B200_API int b200_mf_epoch(const void* rid, const void* cid, const float* val, int64_t n, int ids_are_i32,
                            int64_t n_users, int64_t n_items, float* U, float* V, float* Bu, float* Bi, int k,
                            float lr, float reg, float mu, int use_bias, int ordered,
@@ -166,6 +169,29 @@ B200_API int b200_rank_topk(const float* U, const int64_t* user_idx, int64_t n_q
 B200_API int b200_rank_tc_debug_scores(const float* U, int64_t n_q, const float* V, int64_t n_items, int k,
                                        const float* item_base, float* out, int64_t out_elems,
                                        void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Top-k ranking metrics of a batch of ranked lists (the metric half of the per-user loop of
+ * `ranking_eval`, cornac/eval_methods/base_method.py:200-220, for the metrics that only read
+ * pd_rank[:k]: cornac/metrics/ranking.py:67-123 NDCG, :126-178 NCRR, :240-275 MeasureAtK ->
+ * HitRatio / Precision / Recall / FMeasure).  A hit is `ids[q, r] in positives of user q`.
+ *   ids          device int32[n_q, ids_stride], the first `topk` of each row are the ranked
+ *                list (b200_rank_topk output; -1 = padding, never a hit)
+ *   user_idx     device int64[n_q] row of the positives CSR for list q (NULL = q)
+ *   pos_indptr / pos_indices  device int64[.] / int32[.] CSR of the test positives, ids sorted
+ *                per row; every listed user must have >= 1 positive (base_method.py:180-182)
+ *   metric_kind / metric_k    device int32[n_metrics]: B200_METRIC_* and its k (1 <= k)
+ *   out          device f64[n_metrics, n_q]: the value metric.compute() returns for each user */
+#define B200_METRIC_NDCG 0
+#define B200_METRIC_PRECISION 1
+#define B200_METRIC_RECALL 2
+#define B200_METRIC_FMEASURE 3
+#define B200_METRIC_HIT 4
+#define B200_METRIC_NCRR 5
+B200_API int b200_topk_metrics(const int32_t* ids, int64_t n_q, int topk, int64_t ids_stride,
+                               const int64_t* user_idx, const int64_t* pos_indptr, const int32_t* pos_indices,
+                               const int32_t* metric_kind, const int32_t* metric_k, int n_metrics,
+                               double* out, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Multi-GPU item-factor exchange (no reference counterpart: the reference is a single

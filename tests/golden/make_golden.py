@@ -130,6 +130,25 @@ def mf_case(name, n_users, n_items, nnz, k, max_iter, lr, reg, use_bias, early_s
     print(name, "ok")
 
 
+def bo_case(name, n_users, n_items, nnz, max_iter, lr, reg, seed, dseed):
+    """BaselineOnly (baseline_only/recom_bo.pyx): biases after a seeded (single-thread) fit + scores."""
+    from cornac.models import BaselineOnly
+    u, i, r = synth_uir(n_users, n_items, nnz, dseed)
+    ds = dataset_from(u, i, r)
+    m = BaselineOnly(max_iter=max_iter, learning_rate=lr, lambda_reg=reg, seed=seed).fit(ds)
+    rid, cid, val = ds.uir_tuple
+    qs = np.arange(0, ds.num_users, max(1, ds.num_users // 8))[:8]
+    np.savez_compressed(
+        os.path.join(HERE, name + ".npz"),
+        rid=rid.astype(np.int64), cid=cid.astype(np.int64), val=val.astype(np.float32),
+        num_users=ds.num_users, num_items=ds.num_items, global_mean=ds.global_mean,
+        max_iter=max_iter, lr=lr, reg=reg, seed=seed, Bu=m.u_biases, Bi=m.i_biases,
+        query_users=qs.astype(np.int64), query_scores=np.stack([m.score(int(q)) for q in qs]).astype(np.float32),
+        query_item_scores=np.array([m.score(int(q), 3) for q in qs], dtype=np.float64),
+    )
+    print(name, "ok")
+
+
 def eval_case(name, n_users, n_items, nnz, dseed):
     """BPR + MF through RatioSplit + ranking_eval: golden metric values and the
     split itself (so the GPU box can rebuild identical train/test sets without
@@ -169,4 +188,5 @@ if __name__ == "__main__":
     mf_case("mf_nobias_k16", 120, 90, 1500, k=16, max_iter=8, lr=0.02, reg=0.01, use_bias=False, early_stop=False, seed=42, dseed=3)
     eval_case("eval_ratio_split", 200, 150, 6000, dseed=5)
     wbpr_case("wbpr_mid_k16", 150, 100, 2000, k=16, max_iter=10, lr=0.05, reg=0.01, seed=11, dseed=6)
+    bo_case("bo_mid", 150, 100, 2000, max_iter=15, lr=0.01, reg=0.02, seed=5, dseed=8)
     mmmf_case("mmmf_mid_k16", 150, 100, 2000, k=16, max_iter=10, lr=0.02, reg=0.01, seed=13, dseed=7)

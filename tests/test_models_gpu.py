@@ -196,11 +196,11 @@ def test_batched_ranking_eval_equals_reference_loop():
     """cornac_b200.evaluation.ranking_eval (one fused rank over all users + vectorised metrics)
     returns the numbers of the reference's per-user Python loop for every top-k metric, user by user."""
     from cornac.eval_methods.base_method import ranking_eval as ref_eval
-    from cornac.metrics import AUC, FMeasure, HitRatio, NDCG, Precision, Recall
+    from cornac.metrics import AUC, FMeasure, HitRatio, NCRR, NDCG, Precision, Recall
     from cornac_b200 import BPR, MF
     from cornac_b200.evaluation import ranking_eval as b200_eval
     _, train_set, test_set, _, _ = _split_sets()
-    metrics = [NDCG(k=10), Precision(k=10), Recall(k=10), FMeasure(k=10), HitRatio(k=5), Recall(k=20)]
+    metrics = [NDCG(k=10), Precision(k=10), Recall(k=10), FMeasure(k=10), HitRatio(k=5), Recall(k=20), NCRR(k=7)]
     for mdl in (BPR(k=10, max_iter=30, learning_rate=0.05, seed=123), MF(k=10, max_iter=20, seed=123)):
         mdl.fit(train_set)
         for thr in (1.0, 4.0):
@@ -214,6 +214,78 @@ def test_batched_ranking_eval_equals_reference_loop():
     a = ref_eval(mdl, [AUC()], train_set, test_set, rating_threshold=4.0)[0]
     b = b200_eval(mdl, [AUC()], train_set, test_set, rating_threshold=4.0)[0]
     assert a == b
+
+
+@pytest.mark.parametrize("topk,n_items,n_q", [(10, 50, 300), (100, 2000, 500), (257, 600, 64), (4096, 5000, 9)])
+def test_topk_metrics_kernel_equals_reference_metric_classes(topk, n_items, n_q):
+    """b200_topk_metrics against metric.compute(gt_pos, pd_rank) of the reference (cornac/metrics/ranking.py) on
+    random ranked lists: short (padded with -1) lists, users sharing positives rows through user_idx, k > len."""
+    import torch
+    from cornac.metrics import FMeasure, HitRatio, NCRR, NDCG, Precision, Recall
+    from cornac_b200 import _lib, engine
+    rng = np.random.RandomState(topk)
+    n_users = n_q // 2 + 1
+    pos_rows = [np.sort(rng.choice(n_items, size=rng.randint(1, min(n_items, 3 * topk) + 1), replace=False))
+                for _ in range(n_users)]
+    pos_ptr = np.concatenate([[0], np.cumsum([len(r) for r in pos_rows])]).astype(np.int64)
+    pos_idx = np.concatenate(pos_rows).astype(np.int32)
+    uidx = rng.randint(0, n_users, size=n_q).astype(np.int64)
+    ids = np.full((n_q, topk), -1, dtype=np.int32)
+    for q in range(n_q):
+        n_valid = topk if q % 5 else rng.randint(0, topk + 1)           # some short lists
+        perm = rng.permutation(n_items)[:n_valid]
+        # bias towards hits so that every metric is exercised
+        hot = pos_rows[uidx[q]]
+        take = rng.rand(len(perm)) < 0.3
+        perm[take] = rng.choice(hot, size=int(take.sum()))
+        _, first = np.unique(perm, return_index=True)                   # a ranked list has no duplicates
+        perm = perm[np.sort(first)]
+        ids[q, :len(perm)] = perm
+    ks = [1, 3, 10, topk, topk + 7]
+    ms = [cls(k=k) for k in ks for cls in (NDCG, NCRR, Precision, Recall, FMeasure, HitRatio)][:32]
+    kind = {NDCG: _lib.METRIC_NDCG, NCRR: _lib.METRIC_NCRR, Precision: _lib.METRIC_PRECISION,
+            Recall: _lib.METRIC_RECALL, FMeasure: _lib.METRIC_FMEASURE, HitRatio: _lib.METRIC_HIT}
+    out = engine.topk_metrics(torch.from_numpy(ids).cuda(), torch.from_numpy(pos_ptr).cuda(),
+                              torch.from_numpy(pos_idx).cuda(), [kind[type(m)] for m in ms], [m.k for m in ms],
+                              user_idx=torch.from_numpy(uidx).cuda()).cpu().numpy()
+    for q in range(n_q):
+        row = ids[q][ids[q] >= 0]
+        # the reference ranks ALL candidates: pad the list with non-positive filler up to max k like rank() does
+        filler = np.setdiff1d(np.arange(n_items + topk + 8, n_items + 2 * topk + 16), row)
+        pd_rank = np.concatenate([row, filler])
+        for mi, m in enumerate(ms):
+            if m.k > topk:
+                continue                                                    # needs more than the list holds
+            want = m.compute(gt_pos=pos_rows[uidx[q]], pd_rank=pd_rank)
+            assert abs(out[mi, q] - want) <= 1e-12 * max(1.0, abs(want)), (q, m.name, out[mi, q], want)
+
+
+def test_baseline_only_plugin_reproduces_seeded_reference_and_trains_hogwild():
+    """row (f)3 of SURVEY 8: BaselineOnly = b200_mf_epoch with k = 0 (bias-only loop of recom_bo.pyx:118-131)."""
+    from cornac.data import Dataset
+    from cornac_b200 import BaselineOnly
+    g = golden("bo_mid")
+    n_users, n_items = int(g["num_users"]), int(g["num_items"])
+    uid_map = OrderedDict((str(u), u) for u in range(n_users))
+    iid_map = OrderedDict((str(i), i) for i in range(n_items))
+    triples = [(str(u), str(i), float(r)) for u, i, r in zip(g["rid"], g["cid"], g["val"])]
+    ds = Dataset.build(triples, global_uid_map=uid_map, global_iid_map=iid_map)
+    assert np.array_equal(ds.uir_tuple[0], g["rid"]) and np.array_equal(ds.uir_tuple[1], g["cid"])
+    m = BaselineOnly(max_iter=int(g["max_iter"]), learning_rate=float(g["lr"]), lambda_reg=float(g["reg"]), seed=5).fit(ds)
+    assert rel_err(m.u_biases, g["Bu"]) < TOL and rel_err(m.i_biases, g["Bi"]) < TOL
+    qs = g["query_users"]
+    assert rel_err(np.stack([m.score(int(q)) for q in qs]), g["query_scores"]) < TOL
+    assert np.allclose([m.score(int(q), 3) for q in qs], g["query_item_scores"], rtol=1e-5)
+    ranked, scores = m.rank(int(qs[0]), k=10)
+    assert len(ranked) == n_items and np.all(np.diff(scores[ranked[:10]]) <= 0)
+    ids, _ = m.rank_batch(qs, 5)
+    assert np.array_equal(ids[0], ranked[:5]) and np.array_equal(ids[0], ids[-1])     # same item order for every user
+    # Hogwild (seed=None): same fixed point up to the update order; early_stop path reads the loss
+    h = BaselineOnly(max_iter=int(g["max_iter"]), learning_rate=float(g["lr"]), lambda_reg=float(g["reg"]),
+                     early_stop=True).fit(ds)
+    assert np.abs(h.i_biases - g["Bi"]).max() < 0.05 and np.abs(h.u_biases - g["Bu"]).max() < 0.05
+    assert h.loss_history[-1] < h.loss_history[0]
+    assert m.clone().name == "BaselineOnly"
 
 
 def test_mmmf_plugin_reproduces_seeded_reference_and_trains_hogwild():

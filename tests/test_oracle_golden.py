@@ -86,6 +86,15 @@ def test_mf_fit_matches_compiled_reference(name):
         assert np.array_equal(ids, g["top10"][qi])
 
 
+def test_baseline_only_fit_matches_compiled_reference():
+    """BaselineOnly._fit_sgd (recom_bo.pyx:101-140) = the MF loop with zero-width factors."""
+    g = golden("bo_mid")
+    r = O.bo_fit(g["rid"], g["cid"], g["val"], int(g["num_users"]), int(g["num_items"]), int(g["max_iter"]),
+                 float(g["lr"]), float(g["reg"]), float(g["global_mean"]))
+    assert rel_err(r["Bu"], g["Bu"]) < TOL and rel_err(r["Bi"], g["Bi"]) < TOL
+    assert r["losses"][-1] < r["losses"][0]
+
+
 def test_topk_total_order_and_edges():
     s = np.array([1, 3, 3, 2, 3, -1], dtype=np.float32)
     ids, sc, w = O.topk(s, 4)
