@@ -6,16 +6,19 @@
 // driven once per test user by ranking_eval (cornac/eval_methods/base_method.py:177-220).
 //
 // Plan of one call (users are processed in chunks so the candidate lists stay small):
-//   1. pack   V (and the chunk's U rows) to bf16 in the UMMA "K-major, no swizzle" core-matrix
-//             layout, tile by tile, so that one tile is ONE contiguous cp.async.bulk (UBLKCP); an
-//             extra K slice carries the item base (two bf16 per item against a constant 1 on the
-//             user side), so the MMA adds it; per-row norms give the rigorous error bound
-//             eps(u) = 2^-7 * 1.06 * |u| * max|v| + 2^-16 * max|base| of the bf16 pass;
+//   1. pack   V (and the chunk's U rows) to fp16 in the UMMA "K-major, no swizzle" core-matrix
+//             layout, tile by tile, so that one tile is ONE contiguous cp.async.bulk (UBLKCP).  Both
+//             sides are first multiplied by a power of two (exact) that brings their largest element
+//             to [2^13, 2^14), so the fp16 range is never left and the rounding error is the 2^-11
+//             relative one (8x smaller than bf16's: 8x tighter candidate filter); an extra K slice
+//             carries the item base (two fp16 per item against a constant on the user side), so the
+//             MMA adds it; per-row norms give the rigorous error bound eps(u) ~ 2^-10 |u| max|v|
+//             (+ subnormal, accumulation and base terms, see `row_eps`) of the fp16 pass;
 //   2. rank_tc_kernel  persistent, one CTA per SM, warp-specialised:
 //               warp 0   TMA producer: U tile once per 128 users, V tiles (256 items) through a
 //                        ring of smem stages released by tcgen05.commit (mbarriers)
 //               warp 1   one elected thread issues tcgen05.mma (M=128, N=256, K=16 per
-//                        instruction, bf16 x bf16 -> f32) into a double-buffered TMEM accumulator
+//                        instruction, fp16 x fp16 -> f32) into a double-buffered TMEM accumulator
 //               warp 2   TMEM allocation
 //               warps 4-11 epilogue: tcgen05.ld the accumulator (one (user row, 128-column half)
 //                        per thread), keep every score above the row's running threshold in the
@@ -26,7 +29,7 @@
 // The tensor pass only NOMINATES: every item whose exact score can reach the top-k is provably
 // in the list, so ids and scores are identical to the exact path (score.cu).  Rows whose list
 // overflows (degenerate score distributions) are redone by the exact path.
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -40,7 +43,7 @@ constexpr int TN = 256;            // items per stage (UMMA N)
 constexpr int THREADS = 384;       // 12 warps: TMA, MMA, TMEM-alloc, idle, 8 x epilogue
 constexpr int EPI_WARPS = 8;       // warps 4-7 take accumulator columns [0,128), warps 8-11 columns [128,256)
 constexpr int HALF_N = TN / 2;
-constexpr int KX = 16;             // extra K slice carrying the item base: U gets (1, 1, 0...), V gets (hi, lo, 0...)
+constexpr int KX = 16;             // extra K slice carrying the item base: U gets (cA, cA, 1, 0...), V gets (hi, lo, pad ? -inf : 0, 0...)
 constexpr int CAP = 1024;          // candidate-list capacity per row
 constexpr int TRIGGER = 512;       // raise the threshold when a list reaches this length
 constexpr int MAX_TOPK = 256;
@@ -164,10 +167,10 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_b
     d |= (uint64_t)1 << 46;          // descriptor version (sm_100)
     return d;                        // base_offset = 0, lbo_mode = 0, layout_type = SWIZZLE_NONE (0)
 }
-// instruction descriptor: D = f32, A = B = bf16, both K-major, M x N
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N)
+// instruction descriptor: D = f32 (bit 4), A = B = fp16 (format fields 7-9 / 10-12 = 0), both K-major, M x N
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N)
 {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // V-tile ring depth that fits next to the U tile in 220 KB of shared memory (2..4)
@@ -184,15 +187,75 @@ __host__ __device__ __forceinline__ size_t packed_offset(int r, int c, int kp)
     return ((size_t)(r >> 3) * (kp >> 3) + (c >> 3)) * 128 + (size_t)(r & 7) * 16 + (size_t)(c & 7) * 2;
 }
 
-// ---------------------------------------------------------------- pack kernels
-// one thread per (row, 16-byte chunk): 8 consecutive factors -> 8 bf16.  The last KX columns are the
-// base slice: user rows carry (1, 1, 0, ...), item rows carry (hi, lo, 0, ...) with hi + lo = item base split
-// into two bf16 (relative error 2^-16), so the MMA itself adds the base and the epilogue has no bias add.
-// Padding item rows get a hugely negative base so that they are never nominated.
+// ---------------------------------------------------------------- scales, norms, pack kernels
+// Scalars of one call, device resident (workspace `scal`, 16 x 32 bit):
+//   [0] max |v| (L2 norm, bits)   [1] max |base| (bits)   [2] max |V element| (bits)   [4] sV   [5] sB  (floats)
+// The tensor pass computes, for user row r,  S_r * (u.v + base)  with  S_r = sU_r * sV  from  u * sU_r,  v * sV,
+// base * sB (hi + lo)  and the user-side constant  cA_r = S_r / sB.  All scales are powers of two (exact); every
+// user row has its own (thresholds are per row, so rows of very different magnitude each keep full fp16 precision).
+constexpr int SC_VNORM = 0, SC_BMAX = 1, SC_VABS = 2, SC_SV = 4, SC_SB = 5;
+
+// power of two s with m * s in [2^13, 2^14) (1 for m == 0); exponent clamped so that products of two scales stay
+// finite (operands beyond 2^+-46 are not brought into range: eps grows and such rows end up on the exact path)
+__device__ __forceinline__ float pow2_scale(float m)
+{
+    if (!(m > 0.f)) return 1.f;
+    int e;
+    frexpf(m, &e);                              // m = fr * 2^e, fr in [0.5, 1)
+    int x = 14 - e;
+    x = x > 60 ? 60 : (x < -60 ? -60 : x);
+    return ldexpf(1.f, x);
+}
+
+__global__ void scale_items_kernel(unsigned int* scal)
+{
+    float* f = reinterpret_cast<float*>(scal);
+    f[SC_SV] = pow2_scale(__uint_as_float(scal[SC_VABS]));
+    f[SC_SB] = pow2_scale(__uint_as_float(scal[SC_BMAX]));
+}
+
+// scales of one user row from its largest |element|
+struct UserScale { float sU, cA, S; };
+__device__ __forceinline__ UserScale user_scale(const unsigned int* scal, float row_absmax)
+{
+    const float* f = reinterpret_cast<const float*>(scal);
+    const float sV = f[SC_SV], sB = f[SC_SB];
+    UserScale r;
+    r.sU = pow2_scale(row_absmax);
+    r.cA = 0.f;
+    if (__uint_as_float(scal[SC_BMAX]) > 0.f) {
+        r.cA = r.sU * sV / sB;                  // powers of two: exact
+        if (r.cA > 32768.f) { r.sU *= 32768.f / r.cA; r.cA = 32768.f; }      // keep cA an fp16 power of two
+        if (r.cA < 5.9604645e-8f) r.cA = 0.f;   // below 2^-24: the base is left out and charged to eps
+    }
+    r.S = r.sU * sV;
+    return r;
+}
+
+// |approx / S - exact| <= row_eps for every item, `un` = |u| (x 1.0001):
+//   fp16 rounding of both operands (2^-11 each; 2^-25 absolute in the subnormal range, in scaled units)
+//   + f32 accumulation inside the tensor core + the base carried as two fp16 (2^-22 relative)
+__device__ __forceinline__ float row_eps(const unsigned int* scal, const UserScale& us, float un, int k)
+{
+    const float* f = reinterpret_cast<const float*>(scal);
+    const float vmax = __uint_as_float(scal[SC_VNORM]), bmax = __uint_as_float(scal[SC_BMAX]);
+    float eps = 0.00098f * un * vmax + 2.99e-8f * sqrtf((float)k) * (vmax / us.sU + un / f[SC_SV])
+                + 2e-6f * (un * vmax + bmax) + 4.8e-7f * bmax + 6e-8f * us.cA / us.S;
+    if (us.cA == 0.f) eps += bmax * 1.0001f;
+    return eps;
+}
+
+// one thread per (row, 16-byte chunk): 8 consecutive factors -> 8 fp16.  The last KX columns are the
+// base slice: user rows carry (cA, cA, 1, 0, ...), item rows carry (hi, lo, 0, ...) with hi + lo = base * sB split
+// into two fp16, so the MMA itself adds S * base and the epilogue has no bias add.  Padding item rows carry
+// -inf in the third slot (against the users' 1): they are never nominated.
 template <int TR, bool ITEMS>
 __global__ void pack_kernel(const float* __restrict__ src, const int64_t* __restrict__ row_idx, int64_t n_rows,
-                            int64_t n_rows_padded, int k, int kp, const float* __restrict__ base, uint8_t* __restrict__ dst)
+                            int64_t n_rows_padded, int k, int kp, const float* __restrict__ base,
+                            const unsigned int* __restrict__ scal, const float* __restrict__ row_absmax,
+                            uint8_t* __restrict__ dst)
 {
+    const float* sf = reinterpret_cast<const float*>(scal);
     const int chunks = kp >> 3;
     const int k16 = kp - KX;                    // first column of the base slice
     const int64_t total = n_rows_padded * chunks;
@@ -200,29 +263,35 @@ __global__ void pack_kernel(const float* __restrict__ src, const int64_t* __rest
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
         const int64_t row = t / chunks;
         const int kc = (int)(t % chunks);
-        __nv_bfloat16 v[8];
+        float s = sf[SC_SV], sb = sf[SC_SB];
+        if (!ITEMS) {
+            const UserScale us = user_scale(scal, row < n_rows ? row_absmax[row] : 0.f);
+            s = us.sU; sb = us.cA;
+        }
+        __half v[8];
 #pragma unroll
-        for (int x = 0; x < 8; ++x) v[x] = __float2bfloat16_rn(0.f);
+        for (int x = 0; x < 8; ++x) v[x] = __float2half_rn(0.f);
         if (kc * 8 == k16) {                    // base slice, first chunk (the second one stays zero)
             if (ITEMS) {
                 if (row < n_rows) {
-                    const float b = base ? __ldg(base + row) : 0.f;
-                    const __nv_bfloat16 hi = __float2bfloat16_rn(b);
+                    const float b = (base ? __ldg(base + row) : 0.f) * sb;
+                    const __half hi = __float2half_rn(b);
                     v[0] = hi;
-                    v[1] = __float2bfloat16_rn(b - __bfloat162float(hi));
+                    v[1] = __float2half_rn(b - __half2float(hi));
                 } else {
-                    v[0] = __float2bfloat16_rn(-3.0e38f);
+                    v[2] = __float2half_rn(-INFINITY);
                 }
             } else if (row < n_rows) {
-                v[0] = __float2bfloat16_rn(1.f);
-                v[1] = __float2bfloat16_rn(1.f);
+                v[0] = __float2half_rn(sb);
+                v[1] = __float2half_rn(sb);
+                v[2] = __float2half_rn(1.f);
             }
         } else if (kc * 8 < k16 && row < n_rows) {
             const int64_t srow = row_idx ? row_idx[row] : row;
             const float* p = src + (size_t)srow * k + kc * 8;
 #pragma unroll
             for (int x = 0; x < 8; ++x)
-                if (kc * 8 + x < k) v[x] = __float2bfloat16_rn(__ldg(p + x));
+                if (kc * 8 + x < k) v[x] = __float2half_rn(__ldg(p + x) * s);
         }
         const int64_t tile = row / TR;
         const int r = (int)(row % TR);
@@ -231,30 +300,55 @@ __global__ void pack_kernel(const float* __restrict__ src, const int64_t* __rest
     }
 }
 
-// warp per row: L2 norm (f32 rows); optionally max-reduced into *max_out (as uint bits, values >= 0)
+// warp per row, four rows in flight per warp: L2 norm (f32 rows) -> norm_out; the maxima over all rows of the norm,
+// of |element| and of |base| are max-reduced into scal[] (as uint bits, values >= 0)
 __global__ void norm_kernel(const float* __restrict__ src, const int64_t* __restrict__ row_idx, int64_t n_rows, int k,
-                            float* __restrict__ norm_out, unsigned int* __restrict__ max_out,
+                            float* __restrict__ norm_out, float* __restrict__ rowabs_out,
+                            unsigned int* __restrict__ max_out, unsigned int* __restrict__ absmax_out,
                             const float* __restrict__ base, unsigned int* __restrict__ base_absmax_out)
 {
     const int lane = threadIdx.x & 31;
-    const int64_t wstride = (int64_t)gridDim.x * (blockDim.x >> 5);
-    for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n_rows; row += wstride) {
-        const int64_t srow = row_idx ? row_idx[row] : row;
-        const float* p = src + (size_t)srow * k;
-        float s = 0.f;
-        for (int f = lane; f < k; f += 32) { const float x = __ldg(p + f); s = fmaf(x, x, s); }
-        s = group_sum<32>(s);
-        const float nrm = sqrtf(s) * 1.0001f;
-        if (lane == 0) {
-            if (norm_out) norm_out[row] = nrm;
-            // one shared maximum: look before the atomic, or a million rows serialise on one address
-            if (max_out && __float_as_uint(nrm) > *reinterpret_cast<volatile unsigned int*>(max_out))
-                atomicMax(max_out, __float_as_uint(nrm));
-            if (base && base_absmax_out) {
-                const unsigned int ab = __float_as_uint(fabsf(__ldg(base + row)));
-                if (ab > *reinterpret_cast<volatile unsigned int*>(base_absmax_out)) atomicMax(base_absmax_out, ab);
+    const int64_t wstride = (int64_t)gridDim.x * (blockDim.x >> 5) * 4;
+    float m_norm = 0.f, m_abs = 0.f, m_base = 0.f;
+    for (int64_t row0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 4; row0 < n_rows; row0 += wstride) {
+        float s[4] = {0.f, 0.f, 0.f, 0.f}, a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int64_t row = row0 + r;
+            if (row < n_rows) {
+                const int64_t srow = row_idx ? row_idx[row] : row;
+                const float* p = src + (size_t)srow * k;
+                for (int f = lane; f < k; f += 32) {
+                    const float x = __ldg(p + f);
+                    s[r] = fmaf(x, x, s[r]);
+                    a[r] = fmaxf(a[r], fabsf(x));
+                }
             }
         }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int64_t row = row0 + r;
+            const float nrm = sqrtf(group_sum<32>(s[r])) * 1.0001f;
+            float ra = a[r];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ra = fmaxf(ra, __shfl_xor_sync(0xffffffffu, ra, o));
+            m_abs = fmaxf(m_abs, ra);
+            if (row < n_rows && lane == 0) {
+                if (norm_out) norm_out[row] = nrm;
+                if (rowabs_out) rowabs_out[row] = ra;
+                m_norm = fmaxf(m_norm, nrm);
+                if (base) m_base = fmaxf(m_base, fabsf(__ldg(base + row)));
+            }
+        }
+    }
+    // one shared maximum each: reduce per warp and look before the atomic, or a million rows serialise on one address
+    if (lane == 0) {
+        if (max_out && __float_as_uint(m_norm) > *reinterpret_cast<volatile unsigned int*>(max_out))
+            atomicMax(max_out, __float_as_uint(m_norm));
+        if (absmax_out && __float_as_uint(m_abs) > *reinterpret_cast<volatile unsigned int*>(absmax_out))
+            atomicMax(absmax_out, __float_as_uint(m_abs));
+        if (base_absmax_out && __float_as_uint(m_base) > *reinterpret_cast<volatile unsigned int*>(base_absmax_out))
+            atomicMax(base_absmax_out, __float_as_uint(m_base));
     }
 }
 
@@ -263,6 +357,7 @@ struct RankTcParams {
     const uint8_t* __restrict__ Upack;     // [n_ut][TM x kp bf16 tile image]
     const uint8_t* __restrict__ Vpack;     // [n_it][TN x kp bf16 tile image]
     const float* __restrict__ unorm;       // [n_ut * TM] |u| per chunk row
+    const float* __restrict__ uabs;        // [n_ut * TM] max |element| per chunk row (-> the row's scales)
     const unsigned int* __restrict__ scal; // [0] = max |v| bits, [1] = max |base| bits
     const int64_t* __restrict__ excl_indptr;   // already offset to the chunk's first row (may be null)
     const int32_t* __restrict__ excl_indices;
@@ -272,6 +367,7 @@ struct RankTcParams {
     int* __restrict__ row_cnt;             // [n_ut * TM][2 halves]
     int* __restrict__ row_flag;            // [n_ut * TM][2] 1 = list overflow -> exact path
     float* __restrict__ dump;              // debug: dense approximate scores [n_ut*TM][n_it*TN] or null
+    int debug;                             // B200_RANK_DEBUG: 1 = epilogue drains TMEM but skips the screening (timing only)
 };
 
 __device__ __forceinline__ float ent_score(unsigned long long e) { return __uint_as_float((unsigned)(e >> 32)); }
@@ -330,21 +426,29 @@ __device__ __forceinline__ void raise_threshold(RowState& st, int K, float eps2,
     //      per sweep; it is read four entries per round trip (independent loads) into a register window.
     if (st.n_ex > 0 && st.checked < st.cnt) {
         int w = st.checked;
-        for (int e = st.checked; e < st.cnt; ++e) {
-            const unsigned long long ent = list[(size_t)e * 32];
-            const int32_t id = (int32_t)(ent & 0xffffffffull);
-            while (st.ex_w0 < id) {                       // advance the window past ids below `id`
-                st.ex_w0 = st.ex_w1; st.ex_w1 = st.ex_w2; st.ex_w2 = st.ex_w3; st.ex_w3 = 0x7fffffff;
-                if (st.ex_w0 == 0x7fffffff && st.ex_c < st.n_ex) {      // window empty: refill
-                    const int c = st.ex_c;
-                    st.ex_w0 = __ldg(st.ex + c);
-                    st.ex_w1 = c + 1 < st.n_ex ? __ldg(st.ex + c + 1) : 0x7fffffff;
-                    st.ex_w2 = c + 2 < st.n_ex ? __ldg(st.ex + c + 2) : 0x7fffffff;
-                    st.ex_w3 = c + 3 < st.n_ex ? __ldg(st.ex + c + 3) : 0x7fffffff;
-                    st.ex_c = c + 4;
+        for (int e0 = st.checked; e0 < st.cnt; e0 += 8) {       // 8 independent entry loads per round trip;
+            unsigned long long v[8];                              // a batch is read before it is written (w <= e0)
+            const int nb = st.cnt - e0 < 8 ? st.cnt - e0 : 8;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = i < nb ? list[(size_t)(e0 + i) * 32] : 0ull;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (i < nb) {
+                    const int32_t id = (int32_t)(v[i] & 0xffffffffull);
+                    while (st.ex_w0 < id) {                       // advance the window past ids below `id`
+                        st.ex_w0 = st.ex_w1; st.ex_w1 = st.ex_w2; st.ex_w2 = st.ex_w3; st.ex_w3 = 0x7fffffff;
+                        if (st.ex_w0 == 0x7fffffff && st.ex_c < st.n_ex) {      // window empty: refill
+                            const int c = st.ex_c;
+                            st.ex_w0 = __ldg(st.ex + c);
+                            st.ex_w1 = c + 1 < st.n_ex ? __ldg(st.ex + c + 1) : 0x7fffffff;
+                            st.ex_w2 = c + 2 < st.n_ex ? __ldg(st.ex + c + 2) : 0x7fffffff;
+                            st.ex_w3 = c + 3 < st.n_ex ? __ldg(st.ex + c + 3) : 0x7fffffff;
+                            st.ex_c = c + 4;
+                        }
+                    }
+                    if (st.ex_w0 != id) { list[(size_t)w * 32] = v[i]; ++w; }
                 }
             }
-            if (st.ex_w0 != id) { list[(size_t)w * 32] = ent; ++w; }
         }
         st.cnt = w;
     }
@@ -401,15 +505,14 @@ __device__ __forceinline__ void raise_threshold(RowState& st, int K, float eps2,
 // ~1.25 instructions per score on the common path.
 template <bool DUMP>
 __device__ __forceinline__ void epilogue_chunk(uint32_t (&r)[32], RowState& st, int32_t id0,
-                                               float* __restrict__ dump_row, bool valid)
+                                               float* __restrict__ dump_row, bool valid, float invS)
 {
     if (DUMP) {
         if (valid) {
 #pragma unroll
-            for (int x = 0; x < 32; ++x) dump_row[id0 + x] = __uint_as_float(r[x]);
+            for (int x = 0; x < 32; ++x) dump_row[id0 + x] = __uint_as_float(r[x]) * invS;
         }
-        return;
-    }
+    } else {
     // phase 1: the eight group votes back to back (no branch between them, so their latencies overlap)
     bool hit[8];
 #pragma unroll
@@ -431,6 +534,7 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t (&r)[32], RowState& st, 
                 }
             }
         }
+    }
     }
 }
 
@@ -491,7 +595,7 @@ __global__ void __launch_bounds__(THREADS, 1) rank_tc_kernel(const RankTcParams 
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(TM, TN);
+            const uint32_t idesc = umma_idesc_f16(TM, TN);
             const uint32_t lbo = 128, sbo = (uint32_t)(kp >> 3) * 128;
             uint32_t it_global = 0, tile_no = 0;
             for (int ut = blockIdx.x; ut < p.n_ut; ut += gridDim.x, ++tile_no) {
@@ -520,15 +624,15 @@ __global__ void __launch_bounds__(THREADS, 1) rank_tc_kernel(const RankTcParams 
         // ===================== epilogue: one (user row, column half) per thread =====================
         const int q = warp & 3;                          // TMEM lane quarter == warp % 4
         const int half = (warp - 4) >> 2;                // 0: columns [0,128), 1: columns [128,256)
-        const float vmax = __uint_as_float(p.scal[0]), bmax = __uint_as_float(p.scal[1]);
         uint32_t it_global = 0;
         for (int ut = blockIdx.x; ut < p.n_ut; ut += gridDim.x) {
             const int64_t row = (int64_t)ut * TM + q * 32 + lane;
             const bool valid = row < p.n_rows;
             const float un = valid ? p.unorm[row] : 0.f;
-            // |approx - exact| <= eps: bf16 rounding of both operands (2^-8 each) + f32 accumulation
-            // + 2^-16 relative for the base carried as two bf16 in the extra K slice
-            const float eps = 0.0083f * un * vmax + 2e-6f * (un * vmax + bmax) + 1.6e-5f * bmax;
+            // scores, thresholds and eps live in the scaled units of the accumulator (x S, a power of two)
+            const UserScale us = user_scale(p.scal, valid ? p.uabs[row] : 0.f);
+            const float eps = us.S * row_eps(p.scal, us, un, p.kp - KX);
+            const float invS = 1.f / us.S;
             const float eps2 = 2.f * eps;
             RowState st;
             st.list = p.lists + ((size_t)(ut * EPI_WARPS + half * 4 + q) * CAP) * 32 + lane;
@@ -549,7 +653,7 @@ __global__ void __launch_bounds__(THREADS, 1) rank_tc_kernel(const RankTcParams 
             st.cnt = 0; st.checked = 0;
             st.tau = -INFINITY; st.hi = -INFINITY;
             tau_share[half * TM + q * 32 + lane] = ((unsigned long long)(uint32_t)ut << 32) | 0xff800000u;   // -inf
-            st.tau_f = valid ? -1.0e38f : INFINITY;       // padding items carry a base of -3e38: never above the filter
+            st.tau_f = valid ? -1.0e38f : INFINITY;       // padding items score -inf: never above the filter
             int flag = 0;
             float* dump_row = DUMP ? p.dump + (size_t)(valid ? row : 0) * ((size_t)p.n_it * TN) : nullptr;
             for (int it = 0; it < p.n_it; ++it, ++it_global) {
@@ -560,15 +664,21 @@ __global__ void __launch_bounds__(THREADS, 1) rank_tc_kernel(const RankTcParams 
                 const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN + half * HALF_N);
                 uint32_t r0[32], r1[32];
                 st.wp = st.list + (size_t)st.cnt * 32;
+                if (p.debug & 1) {                 // timing experiment: MMA / TMA feed rate without the screening
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty + acc);
+                    continue;
+                }
                 tmem_ld32_issue(t0, r0);
                 tmem_ld_wait(r0);
 #pragma unroll
                 for (int c0 = 0; c0 < HALF_N; c0 += 64) {
                     tmem_ld32_issue(t0 + c0 + 32, r1);                        // in flight while r0 is processed
-                    epilogue_chunk<DUMP>(r0, st, item0 + c0, dump_row, valid);
+                    epilogue_chunk<DUMP>(r0, st, item0 + c0, dump_row, valid, invS);
                     tmem_ld_wait(r1);
                     if (c0 + 64 < HALF_N) tmem_ld32_issue(t0 + c0 + 64, r0);
-                    epilogue_chunk<DUMP>(r1, st, item0 + c0 + 32, dump_row, valid);
+                    epilogue_chunk<DUMP>(r1, st, item0 + c0 + 32, dump_row, valid, invS);
                     if (c0 + 64 < HALF_N) tmem_ld_wait(r0);
                 }
                 st.cnt = (int)((st.wp - st.list) >> 5);
@@ -773,7 +883,7 @@ __global__ void __launch_bounds__(128) rank_tc_finish_kernel(const FinishParams 
 struct Layout {
     int kp;
     int64_t n_it, chunk_rows, chunk_ut;
-    size_t off_vpack, off_scal, off_upack, off_unorm, off_lists, off_cnt, off_flag, off_over, off_slab, total;
+    size_t off_vpack, off_scal, off_upack, off_unorm, off_uabs, off_lists, off_cnt, off_flag, off_over, off_slab, total;
 };
 
 static Layout make_layout(int64_t n_q, int64_t n_items, int k)
@@ -790,6 +900,7 @@ static Layout make_layout(int64_t n_q, int64_t n_items, int k)
     L.off_scal = take(64);
     L.off_upack = take((size_t)L.chunk_ut * TM * L.kp * 2);
     L.off_unorm = take((size_t)L.chunk_rows * 4);
+    L.off_uabs = take((size_t)L.chunk_rows * 4);
     L.off_lists = take((size_t)L.chunk_ut * EPI_WARPS * CAP * 32 * 8);
     L.off_cnt = take((size_t)L.chunk_rows * 2 * 4);
     L.off_flag = take((size_t)L.chunk_rows * 2 * 4);
@@ -833,11 +944,24 @@ static int pack_items(const float* V, int64_t n_items, int k, const float* item_
     const int64_t n_pad = L.n_it * TN;
     B200_CUDA(cudaMemsetAsync(ws + L.off_scal, 0, 64, st));
     const int grid = sm_count() * 8;
-    pack_kernel<TN, true><<<grid, 256, 0, st>>>(V, nullptr, n_items, n_pad, k, L.kp, item_base, ws + L.off_vpack);
-    // one warp per row and a row is only 4k bytes: launch enough warps to cover the latency
-    const int64_t ngrid = (n_items + 7) / 8 < (1 << 20) ? (n_items + 7) / 8 : (1 << 20);
     unsigned int* scal = reinterpret_cast<unsigned int*>(ws + L.off_scal);
-    norm_kernel<<<(unsigned)(ngrid < grid ? grid : ngrid), 256, 0, st>>>(V, nullptr, n_items, k, nullptr, scal, item_base, scal + 1);
+    norm_kernel<<<grid, 256, 0, st>>>(V, nullptr, n_items, k, nullptr, nullptr, scal + SC_VNORM, scal + SC_VABS, item_base, scal + SC_BMAX);
+    scale_items_kernel<<<1, 1, 0, st>>>(scal);
+    pack_kernel<TN, true><<<grid, 256, 0, st>>>(V, nullptr, n_items, n_pad, k, L.kp, item_base, scal, nullptr, ws + L.off_vpack);
+    B200_CUDA(cudaGetLastError());
+    return B200_OK;
+}
+
+// per chunk of users: norms + element maximum, the chunk's scales, fp16 tile images
+static int pack_users(const float* Usrc, const int64_t* uidx, int64_t rows, int64_t n_ut, int k, const Layout& L, uint8_t* ws,
+                      cudaStream_t st)
+{
+    const int grid = sm_count() * 8;
+    unsigned int* scal = reinterpret_cast<unsigned int*>(ws + L.off_scal);
+    float* uabs = reinterpret_cast<float*>(ws + L.off_uabs);
+    norm_kernel<<<grid, 256, 0, st>>>(Usrc, uidx, rows, k, reinterpret_cast<float*>(ws + L.off_unorm), uabs, nullptr, nullptr,
+                                      nullptr, nullptr);
+    pack_kernel<TM, false><<<grid, 256, 0, st>>>(Usrc, uidx, rows, n_ut * TM, k, L.kp, nullptr, scal, uabs, ws + L.off_upack);
     B200_CUDA(cudaGetLastError());
     return B200_OK;
 }
@@ -854,18 +978,19 @@ int rank_tc(const float* U, const int64_t* user_idx, int64_t n_q, const float* V
     B200_CUDA(cudaFuncSetAttribute(rank_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int rc = pack_items(V, n_items, k, item_base, L, ws, st);
     if (rc) return rc;
-    const int grid_aux = sm_count() * 8;
     for (int64_t q0 = 0; q0 < n_q; q0 += L.chunk_rows) {
         const int64_t rows = (n_q - q0 < L.chunk_rows) ? n_q - q0 : L.chunk_rows;
         const int64_t n_ut = (rows + TM - 1) / TM;
         const int64_t* uidx = user_idx ? user_idx + q0 : nullptr;
         const float* Usrc = user_idx ? U : U + (size_t)q0 * k;
-        pack_kernel<TM, false><<<grid_aux, 256, 0, st>>>(Usrc, uidx, rows, n_ut * TM, k, L.kp, nullptr, ws + L.off_upack);
-        norm_kernel<<<grid_aux, 256, 0, st>>>(Usrc, uidx, rows, k, reinterpret_cast<float*>(ws + L.off_unorm), nullptr, nullptr, nullptr);
+        rc = pack_users(Usrc, uidx, rows, n_ut, k, L, ws, st);
+        if (rc) return rc;
         B200_CUDA(cudaMemsetAsync(ws + L.off_over, 0, 4, st));
         RankTcParams p;
         p.Upack = ws + L.off_upack; p.Vpack = ws + L.off_vpack;
         p.unorm = reinterpret_cast<const float*>(ws + L.off_unorm);
+        p.uabs = reinterpret_cast<const float*>(ws + L.off_uabs);
+    p.uabs = reinterpret_cast<const float*>(ws + L.off_uabs);
         p.scal = reinterpret_cast<const unsigned int*>(ws + L.off_scal);
         p.excl_indptr = excl_indptr ? excl_indptr + q0 : nullptr;
         p.excl_indices = excl_indices;
@@ -874,6 +999,7 @@ int rank_tc(const float* U, const int64_t* user_idx, int64_t n_q, const float* V
         p.row_cnt = reinterpret_cast<int*>(ws + L.off_cnt);
         p.row_flag = reinterpret_cast<int*>(ws + L.off_flag);
         p.dump = nullptr;
+        { const char* d = getenv("B200_RANK_DEBUG"); p.debug = d ? atoi(d) : 0; }
         const int grid = (int)(n_ut < sm_count() ? n_ut : sm_count());
         rank_tc_kernel<false><<<grid, THREADS, smem, st>>>(p);
         B200_CUDA(cudaGetLastError());
@@ -948,12 +1074,12 @@ extern "C" int b200_rank_tc_debug_scores(const float* U, int64_t n_q, const floa
     B200_CUDA(cudaFuncSetAttribute(rank_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int rc = pack_items(V, n_items, k, item_base, L, ws, st);
     if (rc) return rc;
-    const int grid_aux = sm_count() * 8;
-    pack_kernel<TM, false><<<grid_aux, 256, 0, st>>>(U, nullptr, n_q, n_ut * TM, k, L.kp, nullptr, ws + L.off_upack);
-    norm_kernel<<<grid_aux, 256, 0, st>>>(U, nullptr, n_q, k, reinterpret_cast<float*>(ws + L.off_unorm), nullptr, nullptr, nullptr);
+    rc = pack_users(U, nullptr, n_q, n_ut, k, L, ws, st);
+    if (rc) return rc;
     RankTcParams p;
     p.Upack = ws + L.off_upack; p.Vpack = ws + L.off_vpack;
     p.unorm = reinterpret_cast<const float*>(ws + L.off_unorm);
+    p.uabs = reinterpret_cast<const float*>(ws + L.off_uabs);
     p.scal = reinterpret_cast<const unsigned int*>(ws + L.off_scal);
     p.excl_indptr = nullptr; p.excl_indices = nullptr;
     p.n_rows = n_q; p.n_ut = (int)n_ut; p.n_it = (int)L.n_it; p.kp = L.kp; p.topk = 1;
@@ -961,6 +1087,7 @@ extern "C" int b200_rank_tc_debug_scores(const float* U, int64_t n_q, const floa
     p.row_cnt = reinterpret_cast<int*>(ws + L.off_cnt);
     p.row_flag = reinterpret_cast<int*>(ws + L.off_flag);
     p.dump = out;
+    p.debug = 0;
     const int grid = (int)(n_ut < sm_count() ? n_ut : sm_count());
     rank_tc_kernel<true><<<grid, THREADS, smem, st>>>(p);
     B200_CUDA(cudaGetLastError());

@@ -1,4 +1,4 @@
-"""Tensor-core (tcgen05) rank path: the approximate pass against a bf16 matmul, and the fused
+"""Tensor-core (tcgen05) rank path: the approximate pass against an fp16 matmul, and the fused
 b200_rank_topk against the oracle -- ids and scores bit-exact.  GPU only."""
 import os
 
@@ -40,8 +40,9 @@ def _rank_topk(U, V, base, uidx, uoff, excl, topk):
 
 
 @pytest.mark.parametrize("k,n_items,n_q", [(16, 1024, 128), (64, 1500, 100), (128, 3000, 260), (100, 2048, 37), (8, 1100, 5)])
-def test_tensor_pass_matches_bf16_matmul(k, n_items, n_q):
-    """UMMA descriptors / packing / TMEM read-back: dense approximate scores == bf16 x bf16 -> f32."""
+def test_tensor_pass_matches_fp16_matmul(k, n_items, n_q):
+    """UMMA descriptors / packing / power-of-two scaling / TMEM read-back: dense approximate scores ==
+    fp16 x fp16 -> f32 of the scaled operands, unscaled."""
     import torch
     from cornac_b200._lib import check, current_stream, load, ptr
     L = load()
@@ -59,14 +60,23 @@ def test_tensor_pass_matches_bf16_matmul(k, n_items, n_q):
                                       current_stream()), "b200_rank_tc_debug_scores")
     torch.cuda.synchronize()
     got = out.cpu().numpy()[:n_q]
-    Ub = dU.bfloat16().double().cpu().numpy()
-    Vb = dV.bfloat16().double().cpu().numpy()
+    def p2(m):                                              # the kernel's scales: m * s in [2^13, 2^14)
+        return 2.0 ** (14 - np.frexp(np.asarray(m, dtype=np.float32))[1])
+    sU, sV = p2(np.abs(U).max(axis=1, keepdims=True)), float(p2(np.abs(V).max()))     # one scale per user row
+    Ub = (dU * _dev(sU.astype(np.float32))).half().double().cpu().numpy() / sU
+    Vb = (dV * float(sV)).half().double().cpu().numpy() / sV
     want = Ub @ Vb.T + base[None, :].astype(np.float64)
     scale = np.abs(Ub) @ np.abs(Vb).T + np.abs(base)[None, :]
     err = np.abs(got[:, :n_items] - want)
-    # f32 accumulation of exact bf16 products + the item base carried as two bf16 (2^-16 relative)
-    assert np.all(err <= 2e-6 * scale + 2e-5 * np.abs(base)[None, :] + 1e-6), float((err / (scale + 1e-9)).max())
-    assert np.all(got[:, n_items:] < -1e38)                 # padding items carry a hugely negative base
+    # f32 accumulation of exact fp16 products + the item base carried as two fp16 (2^-22 relative)
+    assert np.all(err <= 2e-6 * scale + 1e-6 * np.abs(base)[None, :] + 1e-7), float((err / (scale + 1e-9)).max())
+    assert np.all(got[:, n_items:] < -1e38)                 # padding items score -inf
+    # the rigorous bound the candidate filter relies on (row_eps in rank_tc.cu), against the exact f64 scores
+    exact = U.astype(np.float64) @ V.astype(np.float64).T + base[None, :].astype(np.float64)
+    un = np.linalg.norm(U.astype(np.float64), axis=1)[:, None]
+    vmax, bmax = np.linalg.norm(V.astype(np.float64), axis=1).max(), np.abs(base).max()
+    eps = 0.00098 * un * vmax + 2e-6 * (un * vmax + bmax) + 4.8e-7 * bmax
+    assert np.all(np.abs(got[:, :n_items] - exact) <= eps)
 
 
 @pytest.mark.parametrize("k,n_items,n_q,topk", [(64, 20000, 300, 100), (128, 5000, 64, 100), (128, 100003, 130, 100),
@@ -113,6 +123,41 @@ def test_fused_rank_degenerate_rows_fall_back_to_exact():
         wi, ws, _ = O.topk(want[q], 100)
         assert np.array_equal(ids[q], wi), q
         assert np.array_equal(sc[q], ws)
+
+
+@pytest.mark.parametrize("case", ["tiny", "huge", "mixed_rows", "base_dominates", "base_negligible", "wide_elements",
+                                  "subnormal"])
+def test_fused_rank_dynamic_range(case):
+    """the fp16 tensor pass rescales both operands by powers of two: magnitudes far outside the fp16 range, rows of
+    very different size, a base that dwarfs (or vanishes next to) the dot products -- ids and scores stay exact"""
+    rng = np.random.RandomState(len(case))
+    n_q, n_items, k, topk = 150, 6000, 64, 50
+    U = rng.normal(0, 0.3, (n_q, k)).astype(np.float32)
+    V = rng.normal(0, 0.3, (n_items, k)).astype(np.float32)
+    base = rng.normal(0, 0.3, n_items).astype(np.float32)
+    if case == "tiny":
+        U *= np.float32(1e-9); V *= np.float32(1e-7); base *= np.float32(1e-16)
+    elif case == "huge":
+        U *= np.float32(3e6); V *= np.float32(1e7); base *= np.float32(1e13)
+    elif case == "mixed_rows":
+        U *= (10.0 ** rng.uniform(-6, 3, (n_q, 1))).astype(np.float32)
+        V *= (10.0 ** rng.uniform(-3, 2, (n_items, 1))).astype(np.float32)
+    elif case == "base_dominates":
+        base *= np.float32(1e9)
+    elif case == "base_negligible":
+        base *= np.float32(1e-12)
+    elif case == "wide_elements":
+        U *= (10.0 ** rng.uniform(-8, 0, (n_q, k))).astype(np.float32)
+        V *= (10.0 ** rng.uniform(-8, 0, (n_items, k))).astype(np.float32)
+    elif case == "subnormal":
+        U *= np.float32(1e-30); V *= np.float32(1e-12); base *= np.float32(1e-42)
+    excl = [np.unique(rng.randint(n_items, size=rng.randint(0, 80))) for _ in range(n_q)]
+    ids, sc = _rank_topk(U, V, base, None, None, excl, topk)
+    want = O.score_batch(U, V, base)
+    for q in range(n_q):
+        wi, ws, w = O.topk(want[q], topk, excl[q])
+        assert np.array_equal(ids[q], wi), (case, q, ids[q][:8], wi[:8])
+        assert np.array_equal(sc[q][:w], ws[:w])
 
 
 def test_tensor_path_and_exact_path_agree(monkeypatch):
