@@ -498,6 +498,17 @@ __device__ __forceinline__ void raise_threshold(RowState& st, int K, float eps2,
     st.checked = w;
 }
 
+// append the scores of one group of four that pass the filter to the calling lane's list
+__device__ __noinline__ unsigned long long* append4(unsigned long long* wp, float tau_f, float s0, float s1, float s2,
+                                                    float s3, int32_t id)
+{
+    if (s0 > tau_f) { *wp = ((unsigned long long)__float_as_uint(s0) << 32) | (uint32_t)id; wp += 32; }
+    if (s1 > tau_f) { *wp = ((unsigned long long)__float_as_uint(s1) << 32) | (uint32_t)(id + 1); wp += 32; }
+    if (s2 > tau_f) { *wp = ((unsigned long long)__float_as_uint(s2) << 32) | (uint32_t)(id + 2); wp += 32; }
+    if (s3 > tau_f) { *wp = ((unsigned long long)__float_as_uint(s3) << 32) | (uint32_t)(id + 3); wp += 32; }
+    return wp;
+}
+
 // one 32-column chunk of the accumulator (the item base is already in it: extra K slice of the MMA):
 // append every score above tau_f.  Scores are screened four at a time -- max of the four against the
 // row's filter, one warp vote -- and only when some lane of the warp has a hit (a few percent of the
@@ -521,19 +532,13 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t (&r)[32], RowState& st, 
                               fmaxf(__uint_as_float(r[j4 * 4 + 2]), __uint_as_float(r[j4 * 4 + 3])));
         hit[j4] = __any_sync(0xffffffffu, m > st.tau_f);          // warp-uniform
     }
-    // phase 2: predicated appends for the groups some lane of the warp has a hit in
+    // phase 2: predicated appends for the groups some lane of the warp has a hit in (out of line: thirty-two
+    // inlined copies of the append sequence made the hot loop overflow the instruction cache)
 #pragma unroll
     for (int j4 = 0; j4 < 8; ++j4) {
-        if (hit[j4]) {
-#pragma unroll
-            for (int x = 0; x < 4; ++x) {
-                const float sc = __uint_as_float(r[j4 * 4 + x]);
-                if (sc > st.tau_f) {
-                    *st.wp = ((unsigned long long)__float_as_uint(sc) << 32) | (uint32_t)(id0 + j4 * 4 + x);
-                    st.wp += 32;
-                }
-            }
-        }
+        if (hit[j4])
+            st.wp = append4(st.wp, st.tau_f, __uint_as_float(r[j4 * 4 + 0]), __uint_as_float(r[j4 * 4 + 1]),
+                            __uint_as_float(r[j4 * 4 + 2]), __uint_as_float(r[j4 * 4 + 3]), id0 + j4 * 4);
     }
     }
 }
@@ -728,6 +733,8 @@ struct FinishParams {
     int32_t* __restrict__ out_ids;             // offset to the chunk
     float* __restrict__ out_scores;
     int* __restrict__ overflow_rows;           // [0] = count, [1..] = global query indices
+    int* __restrict__ big_rows;                // [0] = count, [1..] = chunk rows whose lists exceed the warp kernel's capacity
+    const int* __restrict__ row_list;          // block kernel: null = every row, else [0] = count, [1..] = chunk rows
 };
 
 // STAGED: the candidates' item rows are gathered warp-cooperatively (one coalesced 16-byte cp.async per lane
@@ -749,7 +756,9 @@ __global__ void __launch_bounds__(128) rank_tc_finish_kernel(const FinishParams 
     const int tid = threadIdx.x;
     const bool vec4 = (p.k % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.V) & 15) == 0);
     const int stride = p.k * 4 + 16;
-    for (int64_t row = blockIdx.x; row < p.n_rows; row += gridDim.x) {
+    const int64_t n_iter = p.row_list ? (int64_t)p.row_list[0] : p.n_rows;
+    for (int64_t it = blockIdx.x; it < n_iter; it += gridDim.x) {
+        const int64_t row = p.row_list ? (int64_t)p.row_list[1 + it] : it;
         __syncthreads();
         if (p.row_flag[row * 2] | p.row_flag[row * 2 + 1]) {
             if (tid == 0) {
@@ -879,11 +888,132 @@ __global__ void __launch_bounds__(128) rank_tc_finish_kernel(const FinishParams 
     }
 }
 
+// One WARP per row (the common case: a few hundred candidates): no block barriers anywhere, ten rows in flight per
+// SM instead of two, so the dependent chain list -> exclusion search -> row gather -> f64 dot -> sort of one row
+// hides behind the other rows'.  Rows with more than FW_KEYS candidates go to the block kernel (big_rows).
+constexpr int FW_KEYS = 512;
+__host__ __device__ inline size_t finish_warp_smem(int k) { return (size_t)FW_KEYS * 8 + (size_t)MAX_KP * 8 + (size_t)32 * (k * 4 + 16); }
+
+__global__ void __launch_bounds__(32) rank_tc_finish_warp_kernel(const FinishParams p)
+{
+    extern __shared__ __align__(16) unsigned char fw_smem[];
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(fw_smem);               // [FW_KEYS]
+    double* su = reinterpret_cast<double*>(fw_smem + (size_t)FW_KEYS * 8);                   // [MAX_KP]
+    unsigned char* stage = fw_smem + (size_t)FW_KEYS * 8 + (size_t)MAX_KP * 8;               // [32][k*4 + 16]
+    const int lane = threadIdx.x;
+    const int stride = p.k * 4 + 16;
+    for (int64_t row = blockIdx.x; row < p.n_rows; row += gridDim.x) {
+        __syncwarp();
+        if (p.row_flag[row * 2] | p.row_flag[row * 2 + 1]) {
+            if (lane == 0) {
+                const int slot = atomicAdd(p.overflow_rows, 1);
+                p.overflow_rows[1 + slot] = (int)(p.q0 + row);
+            }
+            continue;
+        }
+        const int L0 = p.row_cnt[row * 2], L1 = p.row_cnt[row * 2 + 1], L = L0 + L1;
+        if (L > FW_KEYS) {
+            if (lane == 0) {
+                const int slot = atomicAdd(p.big_rows, 1);
+                p.big_rows[1 + slot] = (int)row;
+            }
+            continue;
+        }
+        const int64_t ut = row / TM;
+        const int r = (int)(row % TM);
+        const unsigned long long* list0 = p.lists + ((size_t)(ut * EPI_WARPS + (r >> 5)) * CAP) * 32 + (r & 31);
+        const unsigned long long* list1 = p.lists + ((size_t)(ut * EPI_WARPS + 4 + (r >> 5)) * CAP) * 32 + (r & 31);
+        const int64_t gq = p.q0 + row;
+        const int64_t urow = p.user_idx ? p.user_idx[row] : gq;
+        const float* u = p.U + (size_t)urow * p.k;
+        const float uo = p.user_off ? __ldg(p.user_off + gq) : 0.f;
+        const int32_t* ex = nullptr;
+        int n_ex = 0;
+        if (p.excl_indptr) {
+            const int64_t a = p.excl_indptr[row], b = p.excl_indptr[row + 1];
+            ex = p.excl_indices + a;
+            n_ex = (int)(b - a);
+        }
+        int sort_n = 32;                            // power of two >= L (padding keys are 0 = below every entry)
+        while (sort_n < L) sort_n <<= 1;
+        for (int f = lane; f < p.k; f += 32) su[f] = (double)__ldg(u + f);
+        __syncwarp();
+        for (int e = lane; e < sort_n; e += 32) {
+            unsigned long long key = 0ull;
+            int32_t id = -1;
+            if (e < L) {
+                const unsigned long long ent = e < L0 ? list0[(size_t)e * 32] : list1[(size_t)(e - L0) * 32];
+                id = (int32_t)(ent & 0xffffffffull);
+                if (n_ex) {                         // entries appended after the last merge are still unfiltered
+                    int lo = 0, hi = n_ex;
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if (__ldg(ex + mid) < id) lo = mid + 1; else hi = mid;
+                    }
+                    if (lo < n_ex && __ldg(ex + lo) == id) id = -1;
+                }
+            }
+            if (__any_sync(0xffffffffu, id >= 0)) {
+#pragma unroll 8
+                for (int c = 0; c < 32; ++c) {
+                    const int32_t idc = __shfl_sync(0xffffffffu, id, c);
+                    if (idc >= 0 && lane * 4 < p.k)
+                        cp_async16(stage + (size_t)c * stride + lane * 16, p.V + (size_t)idc * p.k + lane * 4);
+                }
+                cp_async_wait_all();
+                __syncwarp();
+                if (id >= 0) {
+                    const float4* rowp = reinterpret_cast<const float4*>(stage + (size_t)lane * stride);
+                    double acc = 0.0;              // f ascending, one f64 fma per factor: == score_batch_kernel
+                    for (int f = 0; f < p.k; f += 4) {
+                        const float4 x = rowp[f >> 2];
+                        acc = fma(su[f], (double)x.x, acc);
+                        acc = fma(su[f + 1], (double)x.y, acc);
+                        acc = fma(su[f + 2], (double)x.z, acc);
+                        acc = fma(su[f + 3], (double)x.w, acc);
+                    }
+                    const float base = p.item_base ? __ldg(p.item_base + id) : 0.f;
+                    const float sc = __fadd_rn(__fadd_rn(base, uo), __double2float_rn(acc));      // == score_batch_kernel
+                    key = ((unsigned long long)float_key(sc) << 32) | (unsigned)(0xffffffffu - (unsigned)id);
+                }
+                __syncwarp();                       // the stage is rewritten by the next batch
+            }
+            keys[e] = key;
+        }
+        __syncwarp();
+        for (int size = 2; size <= sort_n; size <<= 1) {
+            for (int st = size >> 1; st > 0; st >>= 1) {
+                for (int x = lane; x < sort_n / 2; x += 32) {
+                    const int lo = 2 * x - (x & (st - 1));
+                    const int hi = lo + st;
+                    const bool desc = ((lo & size) == 0);
+                    const unsigned long long a = keys[lo], b = keys[hi];
+                    if ((a < b) == desc) { keys[lo] = b; keys[hi] = a; }
+                }
+                __syncwarp();
+            }
+        }
+        for (int x = lane; x < p.topk; x += 32) {
+            int32_t id = -1;
+            float sc = -INFINITY;
+            const unsigned long long ent = x < sort_n ? keys[x] : 0ull;
+            if (ent != 0ull) {                              // excluded / padding keys are 0 and sort last
+                id = (int32_t)(0xffffffffu - (unsigned)(ent & 0xffffffffull));
+                const unsigned kb = (unsigned)(ent >> 32);           // invert float_key
+                const unsigned bits = (kb & 0x80000000u) ? (kb & 0x7fffffffu) : ~kb;
+                sc = __uint_as_float(bits);
+            }
+            p.out_ids[(size_t)row * p.topk + x] = id;
+            p.out_scores[(size_t)row * p.topk + x] = sc;
+        }
+    }
+}
+
 // ---------------------------------------------------------------- workspace layout
 struct Layout {
     int kp;
     int64_t n_it, chunk_rows, chunk_ut;
-    size_t off_vpack, off_scal, off_upack, off_unorm, off_uabs, off_lists, off_cnt, off_flag, off_over, off_slab, total;
+    size_t off_vpack, off_scal, off_upack, off_unorm, off_uabs, off_lists, off_cnt, off_flag, off_over, off_big, off_slab, total;
 };
 
 static Layout make_layout(int64_t n_q, int64_t n_items, int k)
@@ -905,6 +1035,7 @@ static Layout make_layout(int64_t n_q, int64_t n_items, int k)
     L.off_cnt = take((size_t)L.chunk_rows * 2 * 4);
     L.off_flag = take((size_t)L.chunk_rows * 2 * 4);
     L.off_over = take((size_t)(L.chunk_rows + 1) * 4);
+    L.off_big = take((size_t)(L.chunk_rows + 1) * 4);
     L.off_slab = take((size_t)n_items * 4);          // one exact score row for overflowed users
     L.total = o;
     return L;
@@ -1010,9 +1141,26 @@ int rank_tc(const float* U, const int64_t* user_idx, int64_t n_q, const float* V
         f.excl_indptr = p.excl_indptr; f.excl_indices = p.excl_indices;
         f.out_ids = out_ids + (size_t)q0 * topk; f.out_scores = out_scores + (size_t)q0 * topk;
         f.overflow_rows = reinterpret_cast<int*>(ws + L.off_over);
-        // latency-bound gathers: as many rows in flight per SM as the thread limit allows (16 x 128 threads)
-        const bool staged = (k % 4 == 0) && k <= 128 && ((reinterpret_cast<uintptr_t>(V) & 15) == 0) && !getenv("B200_RANK_FINISH_DIRECT");
-        if (staged) {
+        f.big_rows = reinterpret_cast<int*>(ws + L.off_big);
+        f.row_list = nullptr;
+        const bool staged = (k % 4 == 0) && k <= 128 && ((reinterpret_cast<uintptr_t>(V) & 15) == 0);
+        const char* fmode = getenv("B200_RANK_FINISH");        // dev knob: "block" = block-per-row kernel for every row
+        if (staged && !(fmode && fmode[0] == 'b')) {
+            // warp per row; the few rows with more than FW_KEYS candidates are redone by the block kernel
+            B200_CUDA(cudaMemsetAsync(f.big_rows, 0, 4, st));
+            const size_t wsmem = finish_warp_smem(k);
+            B200_CUDA(cudaFuncSetAttribute(rank_tc_finish_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+            int occ = 1;
+            B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rank_tc_finish_warp_kernel, 32, wsmem));
+            if (occ < 1) occ = 1;
+            const int64_t cap = (int64_t)sm_count() * occ;
+            rank_tc_finish_warp_kernel<<<(int)(rows < cap ? rows : cap), 32, wsmem, st>>>(f);
+            B200_CUDA(cudaGetLastError());
+            f.row_list = f.big_rows;
+            const size_t fsmem = (size_t)128 * (k * 4 + 16);
+            B200_CUDA(cudaFuncSetAttribute(rank_tc_finish_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+            rank_tc_finish_kernel<true><<<sm_count(), 128, fsmem, st>>>(f);
+        } else if (staged) {
             const size_t fsmem = (size_t)128 * (k * 4 + 16);
             B200_CUDA(cudaFuncSetAttribute(rank_tc_finish_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
             int occ = 1;
@@ -1021,6 +1169,7 @@ int rank_tc(const float* U, const int64_t* user_idx, int64_t n_q, const float* V
             const int64_t cap = (int64_t)sm_count() * occ;
             rank_tc_finish_kernel<true><<<(int)(rows < cap ? rows : cap), 128, fsmem, st>>>(f);
         } else {
+            // latency-bound gathers: as many rows in flight per SM as the thread limit allows (16 x 128 threads)
             const int fgrid = (int)(rows < (int64_t)sm_count() * 16 ? rows : (int64_t)sm_count() * 16);
             rank_tc_finish_kernel<false><<<fgrid, 128, 0, st>>>(f);
         }

@@ -80,7 +80,8 @@ def test_tensor_pass_matches_fp16_matmul(k, n_items, n_q):
 
 
 @pytest.mark.parametrize("k,n_items,n_q,topk", [(64, 20000, 300, 100), (128, 5000, 64, 100), (128, 100003, 130, 100),
-                                                (10, 1682, 40, 10), (100, 1024, 129, 256), (32, 4096, 1, 1)])
+                                                (10, 1682, 40, 10), (100, 1024, 129, 256), (32, 4096, 1, 1),
+                                                (64, 30000, 200, 256), (30, 5000, 70, 20)])
 def test_fused_rank_is_bit_exact(k, n_items, n_q, topk):
     rng = np.random.RandomState(k + n_q)
     U = rng.normal(0, 0.3, (1000, k)).astype(np.float32)
