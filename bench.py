@@ -158,6 +158,17 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def tensor_peak():
+    """dense 16-bit tensor TFLOP/s: the sustained figure of MEASURED_PEAKS.json (the kernel runs for many ms)."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        for key in ("bf16_tflops_sustained", "bf16_tflops"):
+            if key in d:
+                return float(d[key])
+    return 2250.0
+
+
 def algorithmic_bytes(k, updates, skipped, mean_deg):
     """3 rows read + 3 written (24k B) + 4 biases R/W (16 B) + indices/coo/indptr
     (16 B) + 4*ceil(log2(deg+1)) B binary search per update; a skipped sample costs only the
@@ -356,8 +367,13 @@ def main():
         rank_metric = run_rank(W, engine, data, U, V, B, dev)
 
     mf_metric = None
+    rank_c5 = None
     if not args.no_rank and rank == 0:
         mf_metric = run_mf(W, engine, data, dev)
+        if args.workload == "c2":
+            del data
+            torch.cuda.empty_cache()
+            rank_c5 = run_rank_c5(engine, dev)
 
     # ---- CPU baseline on rank 0, N = 1 only
     cpu_baseline = None
@@ -386,7 +402,7 @@ def main():
             "samples_per_s": round((nnz * args.steps * world) / (ms_total * 1e-3), 1),
             "skipped_frac": round(skipped_all / (nnz * args.steps * world), 5),
             "gpu_launches": args.steps * (1 + (2 * 2 if world > 1 else 0)),
-            "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "rank": rank_metric, "mf": mf_metric,
+            "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "rank": rank_metric, "rank_c5": rank_c5, "mf": mf_metric,
         }
         if args.scale != 1.0:
             out["INVALID"] = "scaled-down debug run (--scale %g)" % args.scale
@@ -488,6 +504,45 @@ def run_rank(W, engine, data, U, V, B, dev):
             "e2e": {"value": round(n_q / (ms_h * 1e-3), 1), "unit": "users/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(n_q * topk * 8), "ms": round(ms_h, 3),
                     "path": "engine.rank_topk_host: pinned user ids + exclusion CSR -> H2D -> b200_rank_topk -> D2H ids + scores"}}
+
+
+def run_rank_c5(engine, dev):
+    """ranked users/s on the item side of BASELINE.json configs[4] (1 M items, k = 128, top-100, 100 seen items
+    excluded per user): one call of b200_rank_topk for 75 776 users, random N(0, 0.1) factors and biases."""
+    import torch
+    from cornac_b200._lib import load
+    L = load()
+    n_items, k, n_q, topk, n_excl = 1_000_000, 128, 75776, 100, 100
+    g = torch.Generator(device=dev)
+    g.manual_seed(11)
+    U = torch.randn((n_q, k), generator=g, device=dev) * 0.1
+    V = torch.randn((n_items, k), generator=g, device=dev) * 0.1
+    B = torch.randn(n_items, generator=g, device=dev) * 0.1
+    ex = torch.randint(0, n_items, (n_q, n_excl), generator=g, device=dev, dtype=torch.int32)
+    ex_idx = torch.sort(ex, dim=1)[0].contiguous().view(-1)
+    ex_ptr = (torch.arange(n_q + 1, device=dev, dtype=torch.int64) * n_excl).contiguous()
+    nb = int(L.b200_rank_topk_workspace_bytes(n_q, n_items, k, topk))
+    ws = torch.empty(max(nb, 16), dtype=torch.uint8, device=dev)
+
+    def go():
+        return engine.rank_topk(U, V, topk, item_base=B, excl_indptr=ex_ptr, excl_indices=ex_idx, workspace=ws)
+    go()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        go()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    tf_peak = tensor_peak()
+    tfl = 2.0 * k * n_items * n_q / (ms * 1e-3) / 1e12
+    return {"metric": "ranked users/sec", "value": round(n_q / (ms * 1e-3), 1), "unit": "users/s",
+            "config": "%d users x %d items k=%d top-%d, %d excluded items per user (BASELINE.json configs[4] item side)"
+                      % (n_q, n_items, k, topk, n_excl), "ms": round(ms, 3),
+            "roofline": {"kernel": "rank_tc_kernel (tcgen05 fp16 -> f32) + finish", "bound": "tensor", "achieved": round(tfl, 1),
+                         "peak": tf_peak, "unit": "TFLOP/s", "frac": round(tfl / tf_peak, 4) if tf_peak else None,
+                         "note": "2*k*n_items flop per user over the whole call (pack + tensor pass + exact finish)"}}
 
 
 def run_mf(W, engine, data, dev):

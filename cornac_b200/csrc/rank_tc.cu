@@ -310,6 +310,7 @@ __global__ void norm_kernel(const float* __restrict__ src, const int64_t* __rest
     const int lane = threadIdx.x & 31;
     const int64_t wstride = (int64_t)gridDim.x * (blockDim.x >> 5) * 4;
     float m_norm = 0.f, m_abs = 0.f, m_base = 0.f;
+    const bool vec4 = (k % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
     for (int64_t row0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 4; row0 < n_rows; row0 += wstride) {
         float s[4] = {0.f, 0.f, 0.f, 0.f}, a[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -318,10 +319,18 @@ __global__ void norm_kernel(const float* __restrict__ src, const int64_t* __rest
             if (row < n_rows) {
                 const int64_t srow = row_idx ? row_idx[row] : row;
                 const float* p = src + (size_t)srow * k;
-                for (int f = lane; f < k; f += 32) {
-                    const float x = __ldg(p + f);
-                    s[r] = fmaf(x, x, s[r]);
-                    a[r] = fmaxf(a[r], fabsf(x));
+                if (vec4) {                     // one 16-byte load per lane covers a 128-wide row
+                    for (int f = lane * 4; f < k; f += 128) {
+                        const float4 x = __ldg(reinterpret_cast<const float4*>(p + f));
+                        s[r] = fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, fmaf(x.w, x.w, s[r]))));
+                        a[r] = fmaxf(fmaxf(a[r], fmaxf(fabsf(x.x), fabsf(x.y))), fmaxf(fabsf(x.z), fabsf(x.w)));
+                    }
+                } else {
+                    for (int f = lane; f < k; f += 32) {
+                        const float x = __ldg(p + f);
+                        s[r] = fmaf(x, x, s[r]);
+                        a[r] = fmaxf(a[r], fabsf(x));
+                    }
                 }
             }
         }
@@ -367,7 +376,7 @@ struct RankTcParams {
     int* __restrict__ row_cnt;             // [n_ut * TM][2 halves]
     int* __restrict__ row_flag;            // [n_ut * TM][2] 1 = list overflow -> exact path
     float* __restrict__ dump;              // debug: dense approximate scores [n_ut*TM][n_it*TN] or null
-    int debug;                             // B200_RANK_DEBUG: 1 = epilogue drains TMEM but skips the screening (timing only)
+    int debug;                             // B200_RANK_DEBUG (timing only): 1 = epilogue hands the accumulators straight back, 2 = tcgen05.ld only
 };
 
 __device__ __forceinline__ float ent_score(unsigned long long e) { return __uint_as_float((unsigned)(e >> 32)); }
@@ -498,6 +507,14 @@ __device__ __forceinline__ void raise_threshold(RowState& st, int K, float eps2,
     st.checked = w;
 }
 
+// three-input maximum (FMNMX3, sm_100+)
+__device__ __forceinline__ float fmax3(float a, float b, float c)
+{
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
 // append the scores of one group of four that pass the filter to the calling lane's list
 __device__ __noinline__ unsigned long long* append4(unsigned long long* wp, float tau_f, float s0, float s1, float s2,
                                                     float s3, int32_t id)
@@ -524,14 +541,19 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t (&r)[32], RowState& st, 
             for (int x = 0; x < 32; ++x) dump_row[id0 + x] = __uint_as_float(r[x]) * invS;
         }
     } else {
-    // phase 1: the eight group votes back to back (no branch between them, so their latencies overlap)
+    // phase 1: maxima of the eight groups of four (three-input max: 2 instructions per group) and of the whole
+    // chunk; ONE vote decides whether any of the warp's 32 x 32 scores passes the filter at all
+    float m[8];
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4)
+        m[j4] = fmaxf(fmax3(__uint_as_float(r[j4 * 4 + 0]), __uint_as_float(r[j4 * 4 + 1]), __uint_as_float(r[j4 * 4 + 2])),
+                      __uint_as_float(r[j4 * 4 + 3]));
+    const float mall = fmax3(fmax3(m[0], m[1], m[2]), fmax3(m[3], m[4], m[5]), fmaxf(m[6], m[7]));
+    if (!__any_sync(0xffffffffu, mall > st.tau_f)) return;
+    // the eight group votes back to back (no branch between them, so their latencies overlap)
     bool hit[8];
 #pragma unroll
-    for (int j4 = 0; j4 < 8; ++j4) {
-        const float m = fmaxf(fmaxf(__uint_as_float(r[j4 * 4 + 0]), __uint_as_float(r[j4 * 4 + 1])),
-                              fmaxf(__uint_as_float(r[j4 * 4 + 2]), __uint_as_float(r[j4 * 4 + 3])));
-        hit[j4] = __any_sync(0xffffffffu, m > st.tau_f);          // warp-uniform
-    }
+    for (int j4 = 0; j4 < 8; ++j4) hit[j4] = __any_sync(0xffffffffu, m[j4] > st.tau_f);          // warp-uniform
     // phase 2: predicated appends for the groups some lane of the warp has a hit in (out of line: thirty-two
     // inlined copies of the append sequence made the hot loop overflow the instruction cache)
 #pragma unroll
@@ -670,6 +692,20 @@ __global__ void __launch_bounds__(THREADS, 1) rank_tc_kernel(const RankTcParams 
                 uint32_t r0[32], r1[32];
                 st.wp = st.list + (size_t)st.cnt * 32;
                 if (p.debug & 1) {                 // timing experiment: MMA / TMA feed rate without the screening
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty + acc);
+                    continue;
+                }
+                if (p.debug & 2) {                 // timing experiment: TMEM drain rate (tcgen05.ld only, no screening)
+                    uint32_t acc_or = 0;
+#pragma unroll
+                    for (int c0 = 0; c0 < HALF_N; c0 += 32) {
+                        tmem_ld32_issue(t0 + c0, r0);
+                        tmem_ld_wait(r0);
+                        acc_or |= r0[0] ^ r0[31];
+                    }
+                    if (acc_or == 0x12345u) flag = 1;          // keep the loads alive
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(acc_empty + acc);
@@ -938,21 +974,43 @@ __global__ void __launch_bounds__(32) rank_tc_finish_warp_kernel(const FinishPar
         while (sort_n < L) sort_n <<= 1;
         for (int f = lane; f < p.k; f += 32) su[f] = (double)__ldg(u + f);
         __syncwarp();
-        for (int e = lane; e < sort_n; e += 32) {
-            unsigned long long key = 0ull;
-            int32_t id = -1;
-            if (e < L) {
-                const unsigned long long ent = e < L0 ? list0[(size_t)e * 32] : list1[(size_t)(e - L0) * 32];
-                id = (int32_t)(ent & 0xffffffffull);
-                if (n_ex) {                         // entries appended after the last merge are still unfiltered
-                    int lo = 0, hi = n_ex;
-                    while (lo < hi) {
-                        const int mid = (lo + hi) >> 1;
-                        if (__ldg(ex + mid) < id) lo = mid + 1; else hi = mid;
-                    }
-                    if (lo < n_ex && __ldg(ex + lo) == id) id = -1;
+        // resolve every candidate first (list entry -> id, membership in the sorted exclusion list by a
+        // branch-free lower bound): four independent chains per lane are in flight per pass
+        int pow2 = 1;
+        while (pow2 < n_ex) pow2 <<= 1;
+        for (int e0 = lane; e0 < sort_n; e0 += 128) {
+            int32_t cid[4];
+            int lo[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int e = e0 + 32 * j;
+                cid[j] = -1;
+                lo[j] = 0;
+                if (e < L) {
+                    const unsigned long long ent = e < L0 ? list0[(size_t)e * 32] : list1[(size_t)(e - L0) * 32];
+                    cid[j] = (int32_t)(ent & 0xffffffffull);
                 }
             }
+            if (n_ex) {                             // entries appended after the last merge are still unfiltered
+                for (int half = pow2; half > 0; half >>= 1) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int mid = lo[j] + half;
+                        if (mid <= n_ex && __ldg(ex + mid - 1) < cid[j]) lo[j] = mid;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (cid[j] >= 0 && lo[j] < n_ex && __ldg(ex + lo[j]) == cid[j]) cid[j] = -1;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (e0 + 32 * j < sort_n) keys[e0 + 32 * j] = (unsigned long long)(uint32_t)cid[j];
+        }
+        __syncwarp();
+        for (int e = lane; e < sort_n; e += 32) {
+            unsigned long long key = 0ull;
+            const int32_t id = (int32_t)(uint32_t)keys[e];
             if (__any_sync(0xffffffffu, id >= 0)) {
 #pragma unroll 8
                 for (int c = 0; c < 32; ++c) {
