@@ -173,10 +173,11 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N)
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// V-tile ring depth that fits next to the U tile in 220 KB of shared memory (2..4)
+// V-tile ring depth that fits next to the U tile in 200 KB of shared memory (2..4); the rest holds barriers,
+// thresholds and the pair-exchange area
 __host__ __device__ __forceinline__ int num_stages(int kp)
 {
-    const int budget = 220 * 1024 - TM * kp * 2;
+    const int budget = 200 * 1024 - TM * kp * 2;
     int ns = budget / (TN * kp * 2);
     return ns > 4 ? 4 : (ns < 2 ? 2 : ns);
 }
@@ -413,13 +414,27 @@ __device__ __forceinline__ void scan_list(const unsigned long long* list, int L,
     for (; e < L; ++e) f(list[(size_t)e * 32]);
 }
 
-// Raise the threshold of one list: tau = (approximately) the K-th largest listed score, never above
+// 64-thread named barrier of the two epilogue warps that own the two column halves of the same 32 user rows
+__device__ __forceinline__ void pair_sync(int bar_id)
+{
+    __syncwarp();
+    asm volatile("bar.sync %0, 64;" :: "r"(bar_id) : "memory");
+}
+
+// Raise the threshold of a row: tau = (approximately) the K-th largest listed score, never above
 // it.  All 32 lanes run this together, each on its own list (the lanes' entries are interleaved in
 // memory, so the lock-step scans are coalesced).  Steps: (1) merge the new tail of the list against
 // the user's exclusion list and drop excluded items; (2) two rounds of 16-way bisection on the score
 // range for the largest t with #(score >= t) >= K; (3) drop entries below tau - 2 eps.
+// JOINT (the scheduled raises, which both column halves of a row reach at the same stage): the two
+// threads of a row add up their bin counts through shared memory, so the K-th best is taken over the
+// UNION of the row's two lists -- together they keep ~K candidates instead of ~K each.  The control flow
+// between the pair barriers is the same for every thread (rows that cannot be raised count nothing).
+// Solo (a list hit TRIGGER between two scheduled raises): the list's own K-th best, a valid lower bound.
+template <bool JOINT>
 __device__ __forceinline__ void raise_threshold(RowState& st, int K, float eps2, uint32_t tile,
-                                                unsigned long long* my_tau, const unsigned long long* sibling_tau)
+                                                unsigned long long* my_tau, const unsigned long long* sibling_tau,
+                                                int* pair_mine, const int* pair_theirs, int bar_id)
 {
     unsigned long long* __restrict__ list = st.list;
     // The other column half of this row publishes its own lower bound of the row's k-th best score; any
@@ -463,10 +478,10 @@ __device__ __forceinline__ void raise_threshold(RowState& st, int K, float eps2,
     }
     st.checked = st.cnt;
     const int L = st.cnt;
-    if (L < K) return;
     // ---- (2) score range, then two rounds of 16-way bisection (resolution (hi - lo) / 256)
     float lo = st.tau_f, hi = st.hi;
-    if (!(hi > -INFINITY) || !(lo > -1.0e37f)) {  // this list's score range is not known yet
+    if (L == 0) { lo = INFINITY; hi = -INFINITY; }
+    else if (!(hi > -INFINITY) || !(lo > -1.0e37f)) {  // this list's score range is not known yet
         lo = INFINITY; hi = -INFINITY;
         scan_list(list, L, [&](unsigned long long ent) {
             const float sc = ent_score(ent);
@@ -475,26 +490,52 @@ __device__ __forceinline__ void raise_threshold(RowState& st, int K, float eps2,
         });
     }
     float a = lo, b = hi;                       // invariant: #(score >= a) >= K  (every entry is >= lo)
+    bool act = L >= K;
+    if (JOINT) {
+        pair_mine[0] = L; pair_mine[1] = __float_as_int(lo); pair_mine[2] = __float_as_int(hi);
+        pair_sync(bar_id);
+        const int Lo = pair_theirs[0];
+        a = fminf(lo, __int_as_float(pair_theirs[1]));
+        b = fmaxf(hi, __int_as_float(pair_theirs[2]));
+        act = L + Lo >= K;                      // the same decision in both threads of the row
+        pair_sync(bar_id);
+    } else if (!act) {
+        return;
+    }
     float new_hi = -INFINITY;
     for (int round = 0; round < 2; ++round) {
         const float step = (b - a) * 0.0625f;
-        if (!(step > 0.f) || !isfinite(step)) break;
+        const bool ok = act && (step > 0.f) && isfinite(step);
+        if (!JOINT && !ok) break;
         int c[15];
 #pragma unroll
         for (int j = 0; j < 15; ++j) c[j] = 0;
-        scan_list(list, L, [&](unsigned long long ent) {
-            const float sc = ent_score(ent);
-            new_hi = fmaxf(new_hi, sc);
+        if (ok) {
+            scan_list(list, L, [&](unsigned long long ent) {
+                const float sc = ent_score(ent);
+                new_hi = fmaxf(new_hi, sc);
 #pragma unroll
-            for (int j = 0; j < 15; ++j) c[j] += (sc >= a + (float)(j + 1) * step);
-        });
-        float na = a, nb = a + step;
+                for (int j = 0; j < 15; ++j) c[j] += (sc >= a + (float)(j + 1) * step);
+            });
+        }
+        if (JOINT) {
 #pragma unroll
-        for (int j = 0; j < 15; ++j)
-            if (c[j] >= K) { na = a + (float)(j + 1) * step; nb = (j < 14) ? a + (float)(j + 2) * step : b; }
-        a = na; b = nb;
+            for (int j = 0; j < 15; ++j) pair_mine[j] = c[j];
+            pair_sync(bar_id);
+#pragma unroll
+            for (int j = 0; j < 15; ++j) c[j] += pair_theirs[j];
+            pair_sync(bar_id);
+        }
+        if (ok) {
+            float na = a, nb = a + step;
+#pragma unroll
+            for (int j = 0; j < 15; ++j)
+                if (c[j] >= K) { na = a + (float)(j + 1) * step; nb = (j < 14) ? a + (float)(j + 2) * step : b; }
+            a = na; b = nb;
+        }
     }
-    st.hi = fmaxf(hi, new_hi);                  // scores above the old range only make the top bin fuller
+    if (L > 0) st.hi = fmaxf(hi, new_hi);       // scores above the old range only make the top bin fuller
+    if (!act) return;
     if (a > st.tau) st.tau = a;
     st.tau_f = st.tau - eps2;
     *reinterpret_cast<volatile unsigned long long*>(my_tau) = ((unsigned long long)tile << 32) | __float_as_uint(st.tau);
@@ -584,6 +625,8 @@ __global__ void __launch_bounds__(THREADS, 1) rank_tc_kernel(const RankTcParams 
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 22);
     // [2 halves][TM rows] last published row threshold, tagged with the tile it belongs to: (tile << 32) | f32 bits
     unsigned long long* tau_share = reinterpret_cast<unsigned long long*>(bars + 24);
+    // [2 halves][TM rows][16] bin counts / list length and score range exchanged by the two threads of a row
+    int* pair_share = reinterpret_cast<int*>(bars + 24 + 2 * TM);
     // The V ring is released by the tensor pipe alone, so the TMA producer runs NS tiles ahead of the
     // MMAs whatever the epilogue does; the epilogue only hands the TMEM accumulators back.
 
@@ -735,11 +778,15 @@ __global__ void __launch_bounds__(THREADS, 1) rank_tc_kernel(const RankTcParams 
                     // stage: keep cnt <= CAP - HALF_N.
                     const int done = it + 1;
                     const bool scheduled = done >= 2 && (done & (done - 1)) == 0;
-                    if (scheduled || __any_sync(0xffffffffu, st.cnt >= TRIGGER)) {
-                        raise_threshold(st, p.topk, eps2, (uint32_t)ut, tau_share + half * TM + q * 32 + lane,
-                                        tau_share + (1 - half) * TM + q * 32 + lane);
-                        if (st.cnt > CAP - HALF_N) { flag = 1; st.cnt = 0; st.checked = 0; st.tau_f = INFINITY; }
-                    }
+                    int* pm = pair_share + ((half * TM + q * 32 + lane) << 4);
+                    const int* pt = pair_share + (((1 - half) * TM + q * 32 + lane) << 4);
+                    if (scheduled)
+                        raise_threshold<true>(st, p.topk, eps2, (uint32_t)ut, tau_share + half * TM + q * 32 + lane,
+                                              tau_share + (1 - half) * TM + q * 32 + lane, pm, pt, 1 + q);
+                    else if (__any_sync(0xffffffffu, st.cnt >= TRIGGER))
+                        raise_threshold<false>(st, p.topk, eps2, (uint32_t)ut, tau_share + half * TM + q * 32 + lane,
+                                               tau_share + (1 - half) * TM + q * 32 + lane, pm, pt, 1 + q);
+                    if (st.cnt > CAP - HALF_N) { flag = 1; st.cnt = 0; st.checked = 0; st.tau_f = INFINITY; }
                 }
             }
             if (valid && !DUMP) { p.row_cnt[row * 2 + half] = st.cnt; p.row_flag[row * 2 + half] = flag; }
@@ -1102,7 +1149,7 @@ static Layout make_layout(int64_t n_q, int64_t n_items, int k)
 static size_t smem_bytes_for(int kp)
 {
     const int NS = num_stages(kp);
-    return (size_t)TM * kp * 2 + (size_t)NS * (TN * kp * 2) + 32 * 8 + 2 * TM * 8 + 1024;
+    return (size_t)TM * kp * 2 + (size_t)NS * (TN * kp * 2) + 32 * 8 + 2 * TM * 8 + 2 * TM * 16 * 4 + 1024;
 }
 
 }  // namespace tc
