@@ -362,18 +362,28 @@ def main():
         e2e = run_e2e(args, W, engine, indptr, indices, dev, world, rank)
 
     # ---- secondary metric: ranked users/s (score + exclusion + top-k) on the trained model
+    # (users shard across the GPUs with the item side replicated and no collective: every rank ranks its own users,
+    # the time is the max over ranks)
+    def over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     rank_metric = None
-    if not args.no_rank and rank == 0:
-        rank_metric = run_rank(W, engine, data, U, V, B, dev)
+    if not args.no_rank:
+        rank_metric = run_rank(W, engine, data, U, V, B, dev, world, over_ranks)
 
     mf_metric = None
     rank_c5 = None
-    if not args.no_rank and rank == 0:
-        mf_metric = run_mf(W, engine, data, dev)
+    if not args.no_rank:
+        if rank == 0:
+            mf_metric = run_mf(W, engine, data, dev)
         if args.workload == "c2":
             del data
             torch.cuda.empty_cache()
-            rank_c5 = run_rank_c5(engine, dev)
+            rank_c5 = run_rank_c5(engine, dev, world, over_ranks)
 
     # ---- CPU baseline on rank 0, N = 1 only
     cpu_baseline = None
@@ -456,7 +466,7 @@ def run_e2e(args, W, engine, indptr, indices, dev, world, rank):
                     + (" -> item-delta all-reduce" if world > 1 else "") + " -> D2H U/V/B + stats"}
 
 
-def run_rank(W, engine, data, U, V, B, dev):
+def run_rank(W, engine, data, U, V, B, dev, world=1, over_ranks=lambda ms: ms):
     """ranked users/s: score + exclusion of train positives + top-100 for a batch of users (tensor-core fused
     kernel), device-resident request (`value`) and through the host-buffer entry (`e2e`)."""
     import torch
@@ -480,7 +490,9 @@ def run_rank(W, engine, data, U, V, B, dev):
         go()
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 3
+    if world > 1:
+        dist_barrier()
+    ms = over_ranks(e0.elapsed_time(e1) / 3)
     # end to end: pinned host request (user ids + exclusion CSR) -> H2D -> kernels -> D2H ids + scores
     h_u = uidx.cpu().pin_memory()
     h_p, h_i = ex_ptr.cpu().pin_memory(), ex_idx.cpu().pin_memory()
@@ -496,17 +508,24 @@ def run_rank(W, engine, data, U, V, B, dev):
     for _ in range(3):
         go_host()
     torch.cuda.synchronize()
-    ms_h = (time.perf_counter() - t0) / 3 * 1e3
+    ms_h = over_ranks((time.perf_counter() - t0) / 3 * 1e3)
     h2d = h_u.numel() * 8 + h_p.numel() * 8 + h_i.numel() * 4
-    return {"metric": "ranked users/sec", "value": round(n_q / (ms * 1e-3), 1), "unit": "users/s",
-            "config": "%d users x %d items k=%d top-%d, train positives excluded (the bench's BPR model)" % (n_q, W["n_items"], k, topk),
-            "ms": round(ms, 3), "tflops": round(2.0 * k * W["n_items"] * n_q / (ms * 1e-3) / 1e12, 2),
-            "e2e": {"value": round(n_q / (ms_h * 1e-3), 1), "unit": "users/s", "h2d_bytes_per_step": int(h2d),
+    return {"metric": "ranked users/sec", "value": round(world * n_q / (ms * 1e-3), 1), "unit": "users/s", "n_gpus": world,
+            "config": "%d users per GPU x %d items k=%d top-%d, train positives excluded (the bench's BPR model)" % (n_q, W["n_items"], k, topk),
+            "ms": round(ms, 3), "tflops": round(world * 2.0 * k * W["n_items"] * n_q / (ms * 1e-3) / 1e12, 2),
+            "e2e": {"value": round(world * n_q / (ms_h * 1e-3), 1), "unit": "users/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(n_q * topk * 8), "ms": round(ms_h, 3),
                     "path": "engine.rank_topk_host: pinned user ids + exclusion CSR -> H2D -> b200_rank_topk -> D2H ids + scores"}}
 
 
-def run_rank_c5(engine, dev):
+def dist_barrier():
+    import torch
+    import torch.distributed as dist
+    dist.barrier()
+    torch.cuda.synchronize()
+
+
+def run_rank_c5(engine, dev, world=1, over_ranks=lambda ms: ms):
     """ranked users/s on the item side of BASELINE.json configs[4] (1 M items, k = 128, top-100, 100 seen items
     excluded per user): one call of b200_rank_topk for 75 776 users, random N(0, 0.1) factors and biases."""
     import torch
@@ -534,11 +553,13 @@ def run_rank_c5(engine, dev):
         go()
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 3
-    tf_peak = tensor_peak()
-    tfl = 2.0 * k * n_items * n_q / (ms * 1e-3) / 1e12
-    return {"metric": "ranked users/sec", "value": round(n_q / (ms * 1e-3), 1), "unit": "users/s",
-            "config": "%d users x %d items k=%d top-%d, %d excluded items per user (BASELINE.json configs[4] item side)"
+    if world > 1:
+        dist_barrier()
+    ms = over_ranks(e0.elapsed_time(e1) / 3)
+    tf_peak = tensor_peak() * world
+    tfl = world * 2.0 * k * n_items * n_q / (ms * 1e-3) / 1e12
+    return {"metric": "ranked users/sec", "value": round(world * n_q / (ms * 1e-3), 1), "unit": "users/s", "n_gpus": world,
+            "config": "%d users per GPU x %d items k=%d top-%d, %d excluded items per user (BASELINE.json configs[4] item side)"
                       % (n_q, n_items, k, topk, n_excl), "ms": round(ms, 3),
             "roofline": {"kernel": "rank_tc_kernel (tcgen05 fp16 -> f32) + finish", "bound": "tensor", "achieved": round(tfl, 1),
                          "peak": tf_peak, "unit": "TFLOP/s", "frac": round(tfl / tf_peak, 4) if tf_peak else None,
