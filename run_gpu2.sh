@@ -16,5 +16,5 @@ echo "bench n2 exit $?" >> gpurun_out/bench_n2.err
 timeout -s KILL 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --steps 2 --warmup 1 --impl reference > gpurun_out/bench_n2_ref.json 2> gpurun_out/bench_n2_ref.err
 timeout -s KILL 900 python -m pytest tests -m gpu -q --timeout 300 > gpurun_out/pytest.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest.log
-timeout -s KILL 300 python tools/tune_rank.py > gpurun_out/tune_rank.log 2>&1
-cat gpurun_out/warm.log; tail -4 gpurun_out/mgpu_check.log; cat gpurun_out/bench_n2.json | cut -c1-2500; tail -3 gpurun_out/bench_n2.err; cat gpurun_out/bench_n2_ref.json | cut -c1-600; tail -6 gpurun_out/pytest.log; cat gpurun_out/tune_rank.log
+timeout -s KILL 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
+cat gpurun_out/warm.log; tail -4 gpurun_out/mgpu_check.log; cat gpurun_out/bench_n2.json | cut -c1-2500; tail -3 gpurun_out/bench_n2.err; cat gpurun_out/bench_n2_ref.json | cut -c1-600; tail -6 gpurun_out/pytest.log; tail -3 gpurun_out/smoke.log
