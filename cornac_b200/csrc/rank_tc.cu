@@ -377,7 +377,8 @@ struct RankTcParams {
     int* __restrict__ row_cnt;             // [n_ut * TM][2 halves]
     int* __restrict__ row_flag;            // [n_ut * TM][2] 1 = list overflow -> exact path
     float* __restrict__ dump;              // debug: dense approximate scores [n_ut*TM][n_it*TN] or null
-    int debug;                             // B200_RANK_DEBUG (timing only): 1 = epilogue hands the accumulators straight back, 2 = tcgen05.ld only
+    int debug;                             // B200_RANK_DEBUG: timing only: 1 = epilogue hands the accumulators straight back, 2 = tcgen05.ld only;
+                                           // 4 = raise schedule with ratio 1.41 instead of 2 (results stay exact)
 };
 
 __device__ __forceinline__ float ent_score(unsigned long long e) { return __uint_as_float((unsigned)(e >> 32)); }
@@ -726,6 +727,7 @@ __global__ void __launch_bounds__(THREADS, 1) rank_tc_kernel(const RankTcParams 
             st.tau_f = valid ? -1.0e38f : INFINITY;       // padding items score -inf: never above the filter
             int flag = 0;
             float* dump_row = DUMP ? p.dump + (size_t)(valid ? row : 0) * ((size_t)p.n_it * TN) : nullptr;
+            int next_sched = 2;
             for (int it = 0; it < p.n_it; ++it, ++it_global) {
                 const int acc = it_global & 1;
                 mbar_wait(acc_full + acc, (it_global >> 1) & 1);
@@ -777,7 +779,11 @@ __global__ void __launch_bounds__(THREADS, 1) rank_tc_kernel(const RankTcParams 
                     // ~K ln 2 entries, so the lists stay short.  A list grows by at most HALF_N entries per
                     // stage: keep cnt <= CAP - HALF_N.
                     const int done = it + 1;
-                    const bool scheduled = done >= 2 && (done & (done - 1)) == 0;
+                    const bool scheduled = done == next_sched;
+                    if (scheduled) {               // geometric schedule, ratio 2 (or ~1.41 with debug bit 4)
+                        const int grown = (p.debug & 4) ? (done * 181) >> 7 : done * 2;
+                        next_sched = grown > done ? grown : done + 1;
+                    }
                     int* pm = pair_share + ((half * TM + q * 32 + lane) << 4);
                     const int* pt = pair_share + (((1 - half) * TM + q * 32 + lane) << 4);
                     if (scheduled)
