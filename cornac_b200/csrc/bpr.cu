@@ -664,13 +664,15 @@ static int launch_hogwild(const BprParams& p, cudaStream_t st)
     const HogwildTune tune = read_tune();
     if constexpr (E <= 8) {
         // measured on B200 (profiles/r01_bpr_scatter_experiments.txt): 16-lane groups run best two row-gathers
-        // ahead at 3 blocks/SM (4.14 vs 3.90 G samples/s on C2); 32-lane groups gain nothing from the second slot
+        // ahead at 3 blocks/SM (4.14 vs 3.90 G samples/s on C2); 32-lane groups (k = 128: 512-byte rows, V beyond
+        // the L2 at 1 M items) gain nothing from the second slot but 15 % from a fourth resident block
+        // (60 registers; 1.55 vs 1.35 G updates/s on the configs[2] shard shape)
         if (tune.S == 0) {
-            if (G >= 32) return launch_hogwild_chunk<G, NPL, VEC, ATOMIC, 3, 1>(p, st, tune);
+            if (G >= 32) return launch_hogwild_chunk<G, NPL, VEC, ATOMIC, 4, 1>(p, st, tune);
             return launch_hogwild_chunk<G, NPL, VEC, ATOMIC, 3, 2>(p, st, tune);
         }
-        if (tune.S == 32) {              // the other combination, for A/B runs
-            if (G >= 32) return launch_hogwild_chunk<G, NPL, VEC, ATOMIC, 3, 2>(p, st, tune);
+        if (tune.S == 32) {              // the other combinations, for A/B runs
+            if (G >= 32) return launch_hogwild_chunk<G, NPL, VEC, ATOMIC, 3, 1>(p, st, tune);
             return launch_hogwild_chunk<G, NPL, VEC, ATOMIC, 4, 1>(p, st, tune);
         }
     }
