@@ -850,8 +850,14 @@ struct FinishParams {
 // candidate e of a row whose strip lists hold Ls[0..strips) entries (lists interleaved [warp][entry][lane])
 __device__ __forceinline__ unsigned long long finish_entry(const FinishParams& p, int64_t ut, int r, const int* Ls, int e)
 {
-    int s = 0;
-    while (e >= Ls[s]) { e -= Ls[s]; ++s; }
+    int s = 0;                                  // constant indices only: Ls stays in registers
+    if (e >= Ls[0]) {
+        e -= Ls[0]; s = 1;
+        if (e >= Ls[1]) {
+            e -= Ls[1]; s = 2;
+            if (e >= Ls[2]) { e -= Ls[2]; s = 3; }
+        }
+    }
     const unsigned long long* list = p.lists + ((size_t)(ut * (4 * p.strips) + s * 4 + (r >> 5)) * p.cap) * 32 + (r & 31);
     return list[(size_t)e * 32];
 }
@@ -881,10 +887,13 @@ __global__ void __launch_bounds__(128) rank_tc_finish_kernel(const FinishParams 
         __syncthreads();
         int Ls[MAX_ST] = {0, 0, 0, 0};
         int L = 0, any_flag = 0;
-        for (int x = 0; x < p.strips; ++x) {
-            Ls[x] = p.row_cnt[row * MAX_ST + x];
-            L += Ls[x];
-            any_flag |= p.row_flag[row * MAX_ST + x];
+#pragma unroll
+        for (int x = 0; x < MAX_ST; ++x) {
+            if (x < p.strips) {
+                Ls[x] = p.row_cnt[row * MAX_ST + x];
+                L += Ls[x];
+                any_flag |= p.row_flag[row * MAX_ST + x];
+            }
         }
         if (any_flag) {
             if (tid == 0) {
@@ -1029,10 +1038,13 @@ __global__ void __launch_bounds__(32) rank_tc_finish_warp_kernel(const FinishPar
         __syncwarp();
         int Ls[MAX_ST] = {0, 0, 0, 0};
         int L = 0, any_flag = 0;
-        for (int x = 0; x < p.strips; ++x) {
-            Ls[x] = p.row_cnt[row * MAX_ST + x];
-            L += Ls[x];
-            any_flag |= p.row_flag[row * MAX_ST + x];
+#pragma unroll
+        for (int x = 0; x < MAX_ST; ++x) {
+            if (x < p.strips) {
+                Ls[x] = p.row_cnt[row * MAX_ST + x];
+                L += Ls[x];
+                any_flag |= p.row_flag[row * MAX_ST + x];
+            }
         }
         if (any_flag) {
             if (lane == 0) {
