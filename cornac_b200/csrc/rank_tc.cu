@@ -1209,14 +1209,16 @@ static size_t smem_bytes_for(int kp, int st)
 }
 
 // column strips per row (epilogue warps = 4 x strips): B200_RANK_STRIPS = 2 | 4
-static int rank_strips(int topk)
+static int rank_strips(int k, int topk)
 {
     if (topk > 128) return 2;                   // 4-strip lists hold 512 entries: too close to 2 x topk
     if (const char* e = getenv("B200_RANK_STRIPS")) {
         if (e[0] == '4') return 4;
         if (e[0] == '2') return 2;
     }
-    return 4;                                   // measured: 16 epilogue warps beat 8 by 3 % (1 M items, k=128) to 11 % (100 K items, k=64)
+    // measured (profiles/r01_rank_tc_c5.md): 16 epilogue warps beat 8 by 11 % at k=64 / 100 K items; at k=128 / 1 M items
+    // they are +3 % on random factors but -7 % on a trained model (more list traffic per strip), so 8 stay there
+    return k <= 64 ? 4 : 2;
 }
 
 }  // namespace tc
@@ -1277,7 +1279,7 @@ int rank_tc(const float* U, const int64_t* user_idx, int64_t n_q, const float* V
     B200_REQUIRE((int64_t)L.total <= workspace_bytes, "rank_tc: workspace too small");
     B200_REQUIRE((((uintptr_t)workspace) & 127) == 0, "rank_tc: workspace must be 128-byte aligned");
     uint8_t* ws = static_cast<uint8_t*>(workspace);
-    const int strips = rank_strips(topk);
+    const int strips = rank_strips(k, topk);
     const size_t smem = smem_bytes_for(L.kp, strips);
     if (strips == 4) B200_CUDA(cudaFuncSetAttribute(rank_tc_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     else B200_CUDA(cudaFuncSetAttribute(rank_tc_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
