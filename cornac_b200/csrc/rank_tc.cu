@@ -184,7 +184,7 @@ __host__ __device__ __forceinline__ int num_stages(int kp, int st)
     return ns > 4 ? 4 : (ns < 2 ? 2 : ns);
 }
 
-// byte offset of element (row r, column c) inside a packed tile of `kp` bf16 columns
+// byte offset of element (row r, column c) inside a packed tile of `kp` fp16 columns
 __host__ __device__ __forceinline__ size_t packed_offset(int r, int c, int kp)
 {
     return ((size_t)(r >> 3) * (kp >> 3) + (c >> 3)) * 128 + (size_t)(r & 7) * 16 + (size_t)(c & 7) * 2;
@@ -366,8 +366,8 @@ __global__ void norm_kernel(const float* __restrict__ src, const int64_t* __rest
 
 // ---------------------------------------------------------------- main kernel
 struct RankTcParams {
-    const uint8_t* __restrict__ Upack;     // [n_ut][TM x kp bf16 tile image]
-    const uint8_t* __restrict__ Vpack;     // [n_it][TN x kp bf16 tile image]
+    const uint8_t* __restrict__ Upack;     // [n_ut][TM x kp fp16 tile image]
+    const uint8_t* __restrict__ Vpack;     // [n_it][TN x kp fp16 tile image]
     const float* __restrict__ unorm;       // [n_ut * TM] |u| per chunk row
     const float* __restrict__ uabs;        // [n_ut * TM] max |element| per chunk row (-> the row's scales)
     const unsigned int* __restrict__ scal; // [0] = max |v| bits, [1] = max |base| bits
@@ -1297,7 +1297,6 @@ int rank_tc(const float* U, const int64_t* user_idx, int64_t n_q, const float* V
         p.Upack = ws + L.off_upack; p.Vpack = ws + L.off_vpack;
         p.unorm = reinterpret_cast<const float*>(ws + L.off_unorm);
         p.uabs = reinterpret_cast<const float*>(ws + L.off_uabs);
-    p.uabs = reinterpret_cast<const float*>(ws + L.off_uabs);
         p.scal = reinterpret_cast<const unsigned int*>(ws + L.off_scal);
         p.excl_indptr = excl_indptr ? excl_indptr + q0 : nullptr;
         p.excl_indices = excl_indices;
@@ -1382,8 +1381,8 @@ int rank_tc(const float* U, const int64_t* user_idx, int64_t n_q, const float* V
 using namespace b200;
 using namespace b200::tc;
 
-// Debug / validation entry: dense APPROXIMATE scores of the tensor-core pass (bf16 operands, f32
-// accumulation, + item base), out[n_q_pad128, n_items_pad256] row-major.  Not part of the rank path.
+// Debug / validation entry: dense APPROXIMATE scores of the tensor-core pass (scaled fp16 operands, f32
+// accumulation, + item base, unscaled again), out[n_q_pad128, n_items_pad256] row-major.  Not part of the rank path.
 extern "C" int b200_rank_tc_debug_scores(const float* U, int64_t n_q, const float* V, int64_t n_items, int k,
                                          const float* item_base, float* out, int64_t out_elems,
                                          void* workspace, int64_t workspace_bytes, void* stream)

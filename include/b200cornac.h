@@ -163,8 +163,9 @@ B200_API int b200_rank_topk(const float* U, const int64_t* user_idx, int64_t n_q
                             int topk, int32_t* out_ids, float* out_scores,
                             void* workspace, int64_t workspace_bytes, void* stream);
 
-/* Validation hook of the tensor-core pass: dense APPROXIMATE scores (bf16 operands, f32
- * accumulation, + item_base) as the candidate pass of b200_rank_topk sees them.
+/* Validation hook of the tensor-core pass: dense APPROXIMATE scores (operands scaled by powers of
+ * two and rounded to fp16, f32 accumulation, + item_base, scaled back) as the candidate pass of
+ * b200_rank_topk sees them; padding items (>= n_items) read -inf.
  *   out device f32[ceil(n_q/128)*128, ceil(n_items/256)*256] row-major; workspace as above. */
 B200_API int b200_rank_tc_debug_scores(const float* U, int64_t n_q, const float* V, int64_t n_items, int k,
                                        const float* item_base, float* out, int64_t out_elems,
