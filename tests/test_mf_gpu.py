@@ -140,3 +140,24 @@ def test_windowed_ordered_epoch_is_bit_identical_to_serial(hot, monkeypatch):
     for _ in range(2):
         l_ref = O.mf_epoch(rid, cid, val, Ur, Vr, Bur, Bir, 0.01, 0.02, 3.0, True)
     assert rel_err(outs[1][0], Ur) < 1e-5 and abs(0.5 * outs[1][4] - l_ref) < 1e-4 * l_ref
+
+
+def test_mf_fit_sharded_single_process_trains_like_plain_epochs():
+    """parallel.mf_fit_sharded with no process group (world 1): the whole rating list is this rank's shard; the
+    result must be in the same regime as the oracle's sequential epochs and be written back into the host arrays."""
+    from cornac_b200 import parallel
+    rng = np.random.RandomState(8)
+    n_users, n_items, k, n = 3000, 1000, 16, 120000
+    P, Q = rng.normal(0, 0.5, (n_users, 4)), rng.normal(0, 0.5, (n_items, 4))
+    rid = rng.randint(n_users, size=n).astype(np.int64)
+    cid = rng.randint(n_items, size=n).astype(np.int64)
+    val = (3.0 + np.einsum("nk,nk->n", P[rid], Q[cid]) + rng.normal(0, 0.1, n)).astype(np.float32)
+    U0, V0, Bu0, Bi0 = O.mf_init(2, n_users, n_items, k)
+    Uc, Vc, Buc, Bic = U0.copy(), V0.copy(), Bu0.copy(), Bi0.copy()
+    mu = float(val.mean())
+    cpu = [O.mf_epoch(rid, cid, val, Uc, Vc, Buc, Bic, 0.02, 0.01, mu, True) for _ in range(10)]
+    U, V, Bu, Bi = U0.copy(), V0.copy(), Bu0.copy(), Bi0.copy()
+    bounds, losses = parallel.mf_fit_sharded(rid, cid, val, U, V, Bu, Bi, 0.02, 0.01, mu, True, max_iter=10)
+    assert bounds.tolist() == [0, n_users] and len(losses) == 10
+    assert losses[-1] < 0.5 * losses[0] and abs(losses[-1] - cpu[-1]) < 0.25 * cpu[-1]
+    assert np.abs(U - U0).max() > 1e-3 and np.abs(V - V0).max() > 1e-3 and np.abs(Bi - Bi0).max() > 1e-3

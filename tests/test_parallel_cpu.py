@@ -8,7 +8,8 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from conftest import synth_csr
-from cornac_b200.parallel import ItemReplicaSync, shard_csr, shard_users_by_nnz
+from cornac_b200.parallel import (ItemReplicaSync, mf_fit_sharded, shard_csr, shard_ratings, shard_ratings_by_user,
+                                  shard_users_by_nnz)
 
 
 def test_shard_users_balanced_and_complete():
@@ -73,4 +74,95 @@ def test_item_replica_exchange_gloo_world2():
     mgr = mp.Manager()
     out = mgr.dict()
     mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    assert out[0] and out[1]
+
+
+# ---------------------------------------------------------------------------------------------
+# MF sharded by user: the host logic of parallel.mf_fit_sharded over gloo, world size 2, with the
+# oracle's sequential epoch as the stand-in for b200_mf_epoch and torch-CPU stand-ins for the delta kernels.
+class _OracleMf:
+    ops = _CpuOps
+
+    def ids(self, a):
+        return np.ascontiguousarray(a, dtype=np.int64)
+
+    def f32(self, a):
+        return torch.from_numpy(np.array(a, dtype=np.float32, copy=True))
+
+    def zeros1(self):
+        return torch.zeros(1)
+
+    def epoch(self, rid, cid, val, U, V, Bu, Bi, lr, reg, mu, use_bias, loss, atomic):
+        from oracle import oracle as O
+        half = O.mf_epoch(rid, cid, val.numpy(), U.numpy(), V.numpy(), Bu.numpy(), Bi.numpy(), lr, reg, mu, use_bias)
+        loss[0] = 2.0 * half                           # the device kernel reports sum(err^2)
+
+    def to_host(self, host, dev):
+        host[...] = dev.numpy()
+
+
+def _mf_problem():
+    rng = np.random.RandomState(3)
+    n_users, n_items, n, k = 120, 40, 3000, 8
+    rid = rng.randint(n_users, size=n).astype(np.int64)
+    cid = rng.randint(n_items, size=n).astype(np.int64)
+    val = rng.randint(1, 6, size=n).astype(np.float32)
+    U = rng.normal(0, 0.01, (n_users, k)).astype(np.float32)
+    V = rng.normal(0, 0.01, (n_items, k)).astype(np.float32)
+    return rid, cid, val, U, V, np.zeros(n_users, np.float32), np.zeros(n_items, np.float32)
+
+
+def test_shard_ratings_by_user_partitions_the_rating_list():
+    rid, cid, val, U, *_ = _mf_problem()
+    for world in (1, 2, 3):
+        b = shard_ratings_by_user(rid, U.shape[0], world)
+        parts = [shard_ratings(rid, cid, val, b, r) for r in range(world)]
+        assert sum(len(p[2]) for p in parts) == len(val)
+        sizes = [len(p[2]) for p in parts]
+        assert max(sizes) - min(sizes) <= 2 * np.bincount(rid).max()
+        for r, (rr, cc, vv) in enumerate(parts):
+            keep = (rid >= b[r]) & (rid < b[r + 1])
+            assert np.array_equal(rr + b[r], rid[keep]) and np.array_equal(cc, cid[keep]) and np.array_equal(vv, val[keep])
+
+
+def _mf_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle as O
+    rid, cid, val, U, V, Bu, Bi = _mf_problem()
+    U0, V0, Bu0, Bi0 = U.copy(), V.copy(), Bu.copy(), Bi.copy()
+    bounds, losses = mf_fit_sharded(rid, cid, val, U, V, Bu, Bi, 0.01, 0.02, 3.0, True, max_iter=1, _device=_OracleMf())
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    # expectation for one epoch: every shard trained from the SAME start; V, Bi = start + sum of the shards' changes
+    dV, dBi, tot = np.zeros_like(V0), np.zeros_like(Bi0), 0.0
+    for r in range(world):
+        rr, cc, vv = shard_ratings(rid, cid, val, bounds, r)
+        a, b = int(bounds[r]), int(bounds[r + 1])
+        Ur, Vr, Bur, Bir = U0[a:b].copy(), V0.copy(), Bu0[a:b].copy(), Bi0.copy()
+        tot += O.mf_epoch(rr, cc, vv, Ur, Vr, Bur, Bir, 0.01, 0.02, 3.0, True)
+        dV += Vr - V0
+        dBi += Bir - Bi0
+        if r == rank:
+            mine = (Ur, Bur)
+    ok = (np.allclose(V, V0 + dV, atol=1e-6) and np.allclose(Bi, Bi0 + dBi, atol=1e-6)
+          and np.array_equal(U[lo:hi], mine[0]) and np.array_equal(Bu[lo:hi], mine[1])
+          and np.array_equal(np.delete(U, np.s_[lo:hi], axis=0), np.delete(U0, np.s_[lo:hi], axis=0))
+          and abs(losses[0] - tot) <= 1e-3 * tot)
+    # several epochs + early stop: same decision and same replicas everywhere
+    _, l2 = mf_fit_sharded(rid, cid, val, U, V, Bu, Bi, 0.01, 0.02, 3.0, True, max_iter=4, early_stop=True, _device=_OracleMf())
+    g = [torch.empty(V.shape) for _ in range(world)]
+    dist.all_gather(g, torch.from_numpy(V.copy()))
+    n_ep = torch.tensor([len(l2)])
+    dist.all_reduce(n_ep, op=dist.ReduceOp.MAX)
+    out[rank] = bool(ok and all(torch.equal(g[0], t) for t in g) and int(n_ep.item()) == len(l2) and l2[-1] < losses[0])
+    dist.destroy_process_group()
+
+
+def test_mf_fit_sharded_gloo_world2():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_mf_worker, args=(2, port, out), nprocs=2, join=True)
     assert out[0] and out[1]

@@ -13,6 +13,31 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from cornac_b200 import parallel  # noqa: E402
 
 
+def mf_check(rank, world):
+    """parallel.mf_fit_sharded: replicas of V / Bi identical on every rank, only the rank's own users trained, loss falls."""
+    rng = np.random.RandomState(9)                      # same data on every rank
+    n_users, n_items, k, n = 20000, 3000, 32, 600000
+    P, Q = rng.normal(0, 0.5, (n_users, 4)), rng.normal(0, 0.5, (n_items, 4))
+    rid = rng.randint(n_users, size=n).astype(np.int64)
+    cid = rng.randint(n_items, size=n).astype(np.int64)
+    val = (3.0 + np.einsum("nk,nk->n", P[rid], Q[cid]) + rng.normal(0, 0.1, n)).astype(np.float32)
+    U = rng.normal(0, 0.01, (n_users, k)).astype(np.float32)
+    V = rng.normal(0, 0.01, (n_items, k)).astype(np.float32)
+    Bu, Bi = np.zeros(n_users, np.float32), np.zeros(n_items, np.float32)
+    U0 = U.copy()
+    bounds, losses = parallel.mf_fit_sharded(rid, cid, val, U, V, Bu, Bi, 0.02, 0.01, float(val.mean()), True, max_iter=10)
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    Vd = torch.from_numpy(np.concatenate([V.ravel(), Bi])).cuda()
+    gathered = [torch.empty_like(Vd) for _ in range(world)]
+    dist.all_gather(gathered, Vd)
+    same = all(torch.equal(gathered[0], g) for g in gathered)
+    untouched = np.array_equal(np.delete(U, np.s_[lo:hi], axis=0), np.delete(U0, np.s_[lo:hi], axis=0))
+    ok = same and untouched and losses[-1] < 0.5 * losses[0]
+    print("rank %d/%d MF users [%d,%d): replicas_equal=%s untouched=%s loss %.1f -> %.1f -> %s"
+          % (rank, world, lo, hi, same, untouched, losses[0], losses[-1], "OK" if ok else "FAIL"), flush=True)
+    return ok
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -49,6 +74,7 @@ def main():
     ok = same and untouched and moved and acc > 0.9 and auc_like > 1.0
     print("rank %d/%d users [%d,%d): replicas_equal=%s untouched=%s moved=%s acc=%.3f sep=%.2f -> %s"
           % (rank, world, lo, hi, same, untouched, moved, acc, auc_like, "OK" if ok else "FAIL"), flush=True)
+    ok = mf_check(rank, world) and ok
     flag = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(flag)
     dist.destroy_process_group()
