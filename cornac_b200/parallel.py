@@ -116,7 +116,7 @@ def shard_ratings(rid, cid, val, bounds, rank):
 
 class _DeviceMf:
     """The device operations mf_fit_sharded needs (the test seam: tests/test_parallel_cpu.py drives the same
-    function over gloo with a CPU stand-in built on the oracle)."""
+    function over gloo with a CPU stand-in)."""
 
     def __init__(self):
         import torch
