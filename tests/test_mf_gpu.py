@@ -159,5 +159,6 @@ def test_mf_fit_sharded_single_process_trains_like_plain_epochs():
     U, V, Bu, Bi = U0.copy(), V0.copy(), Bu0.copy(), Bi0.copy()
     bounds, losses = parallel.mf_fit_sharded(rid, cid, val, U, V, Bu, Bi, 0.02, 0.01, mu, True, max_iter=10)
     assert bounds.tolist() == [0, n_users] and len(losses) == 10
-    assert losses[-1] < 0.5 * losses[0] and abs(losses[-1] - cpu[-1]) < 0.25 * cpu[-1]
-    assert np.abs(U - U0).max() > 1e-3 and np.abs(V - V0).max() > 1e-3 and np.abs(Bi - Bi0).max() > 1e-3
+    # (measured on B200: 15932.0 -> 15645.7 against the sequential 15931.2 -> 15645.5)
+    assert losses[-1] < losses[0] and abs(losses[0] - cpu[0]) < 0.02 * cpu[0] and abs(losses[-1] - cpu[-1]) < 0.02 * cpu[-1]
+    assert np.abs(U - U0).max() > 1e-4 and np.abs(V - V0).max() > 1e-4 and np.abs(Bi - Bi0).max() > 1e-3
