@@ -127,3 +127,53 @@ def test_mmmf_fit_matches_compiled_reference():
     r = O.bpr_fit(g["indptr"], g["indices"], int(g["num_items"]), int(g["total_users"]), int(g["total_items"]), int(g["k"]),
                   int(g["max_iter"]), float(g["lr"]), float(g["reg"]), True, int(g["seed"]), mmmf=True)
     assert rel_err(r["U"], g["U"]) < TOL and rel_err(r["V"], g["V"]) < TOL and rel_err(r["B"], g["B"]) < TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# WMF -- the reference's TensorFlow graph cannot run here: PARITY UNPINNED.  The restatement in
+# oracle/wmf_oracle.py is only checked for internal consistency.
+def test_wmf_restatement_is_self_consistent():
+    import scipy.sparse as sp
+    from oracle import wmf_oracle as W
+    rng = np.random.RandomState(0)
+    n_users, n_items, k = 30, 20, 4
+    R = sp.random(n_users, n_items, density=0.2, random_state=rng, format="csc", dtype=np.float32)
+    R.data[:] = rng.randint(1, 6, size=R.nnz)
+    U = W.xavier_uniform((n_users, k), rng)
+    V = W.xavier_uniform((n_items, k), rng)
+    assert U.dtype == np.float32 and np.abs(U).max() <= np.sqrt(6.0 / (n_users + k)) + 1e-6
+    ids = np.array([3, 7, 11, 0])
+    R_b, C_b = W.batch_inputs(R, ids, a=1.0, b=0.01)
+    assert set(np.unique(C_b)) <= {np.float32(0.01), np.float32(1.0)} and np.all((C_b == 1.0) == (R_b != 0))
+    # analytic gradients == finite differences of the restated loss (in f64 to make the difference quotient meaningful)
+    U64, Vb64 = U.astype(np.float64), V[ids].astype(np.float64)
+
+    def loss64(Ux, Vx):
+        E = R_b - Ux @ Vx.T
+        return np.sum(C_b * E * E) + 0.01 * np.sum(Ux * Ux) / 2 + 0.02 * np.sum(Vx * Vx) / 2
+    _, gU, gVb = W.loss_and_grads(U, V[ids], R_b, C_b, 0.01, 0.02)
+    h = 1e-6
+    for (r, c) in [(0, 0), (5, 2), (29, 3)]:
+        d = np.zeros_like(U64); d[r, c] = h
+        assert abs((loss64(U64 + d, Vb64) - loss64(U64 - d, Vb64)) / (2 * h) - gU[r, c]) < 1e-3 * max(1.0, abs(gU[r, c]))
+    for (r, c) in [(0, 0), (2, 1), (3, 3)]:
+        d = np.zeros_like(Vb64); d[r, c] = h
+        assert abs((loss64(U64, Vb64 + d) - loss64(U64, Vb64 - d)) / (2 * h) - gVb[r, c]) < 1e-3 * max(1.0, abs(gVb[r, c]))
+    # first Adam step: m = (1-b1) g, v = (1-b2) g^2, lr_1 = lr sqrt(1-b2)/(1-b1)  =>  step = lr * g / (|g| + eps sqrt(1-b2)...)
+    opt, st = W.Adam(0.001), W.AdamState((2, 2))
+    var = np.zeros((2, 2), np.float32)
+    g = np.array([[1.0, -2.0], [0.5, 0.0]], np.float32)
+    opt.apply_dense(var, st, g)
+    want = -0.001 * np.sqrt(1 - 0.999) / (1 - 0.9) * (0.1 * g) / (np.sqrt(0.001 * g * g) + 1e-8)
+    assert np.allclose(var, want, rtol=1e-5, atol=1e-9)
+    # sparse (gathered) variable: untouched rows do not move on the first step (their m is 0) but do decay afterwards
+    opt, stv = W.Adam(0.001), W.AdamState((4, 2))
+    var = np.ones((4, 2), np.float32)
+    opt.apply_sparse(var, stv, np.array([1, 3]), np.ones((2, 2), np.float32))
+    opt.finish()
+    assert np.all(var[[0, 2]] == 1.0) and np.all(var[[1, 3]] < 1.0)
+    opt.apply_sparse(var, stv, np.array([0]), np.ones((1, 2), np.float32))
+    assert np.all(var[2] == 1.0) and np.all(var[1] < 0.9995)                     # row 1 keeps moving on its decayed m
+    # toy fit: the batch loss falls
+    hist = W.fit(R, U, V, lambda: [np.arange(0, 10), np.arange(10, 20)], lr=0.01, max_iter=30)
+    assert hist[-1] < 0.7 * hist[0]
