@@ -466,6 +466,33 @@ def run_e2e(args, W, engine, indptr, indices, dev, world, rank):
                     + (" -> item-delta all-reduce" if world > 1 else "") + " -> D2H U/V/B + stats"}
 
 
+def reference_rank_users_per_s(U_host, V_host, B_host, topk, budget_s=8.0):
+    """ranked users/s of the UNMODIFIED reference on the host cores: cornac.models.BPR.rank(user, k=topk) -- score() =
+    copy(B) + fast_dot(U[u], V) (recom_bpr.pyx:272-297, OpenMP over the items) + argpartition top-k
+    (recommender.py:476-530) -- called once per user like ranking_eval does, for a bounded number of users.
+    Returns (users/s, users timed, seconds) or None when the compiled reference is not importable."""
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.isdir(os.path.join(ref, "cornac")):
+        return None
+    if ref not in sys.path:
+        sys.path.insert(0, ref)
+    from cornac.models import BPR as RefBPR
+    m = RefBPR(k=U_host.shape[1])
+    m.num_users, m.num_items = U_host.shape[0], V_host.shape[0]
+    m.u_factors = np.ascontiguousarray(U_host, dtype=np.float32)
+    m.i_factors = np.ascontiguousarray(V_host, dtype=np.float32)
+    m.i_biases = np.ascontiguousarray(B_host, dtype=np.float32)
+    m.rank(0, k=topk)                                     # warm-up (thread pool, page faults)
+    n, t0 = 0, time.perf_counter()
+    while n < U_host.shape[0]:
+        m.rank(n, k=topk)
+        n += 1
+        if (n & 15) == 0 and time.perf_counter() - t0 > budget_s:
+            break
+    secs = time.perf_counter() - t0
+    return n / secs, n, secs
+
+
 def run_rank(W, engine, data, U, V, B, dev, world=1, over_ranks=lambda ms: ms):
     """ranked users/s: score + exclusion of train positives + top-100 for a batch of users (tensor-core fused
     kernel), device-resident request (`value`) and through the host-buffer entry (`e2e`)."""
@@ -510,7 +537,17 @@ def run_rank(W, engine, data, U, V, B, dev, world=1, over_ranks=lambda ms: ms):
     torch.cuda.synchronize()
     ms_h = over_ranks((time.perf_counter() - t0) / 3 * 1e3)
     h2d = h_u.numel() * 8 + h_p.numel() * 8 + h_i.numel() * 4
-    return {"metric": "ranked users/sec", "value": round(world * n_q / (ms * 1e-3), 1), "unit": "users/s", "n_gpus": world,
+    cpu = None
+    if world == 1:
+        try:                                                # a reported baseline, never a reason for the bench line to fail
+            r = reference_rank_users_per_s(U[:4096].cpu().numpy(), V.cpu().numpy(), B.cpu().numpy(), topk)
+            if r is not None:
+                cpu = {"value": round(r[0], 1), "unit": "users/s", "cores": os.cpu_count(), "kind": "reference",
+                       "sample": "cornac.models.BPR.rank(u, k=%d) of the compiled reference for %d users of the same model "
+                                 "(%d items, k=%d) in %.1fs, no exclusion list" % (topk, r[1], W["n_items"], k, r[2])}
+        except Exception as exc:                            # noqa: BLE001
+            cpu = {"unavailable": "%s: %s" % (type(exc).__name__, exc)}
+    return {"metric": "ranked users/sec", "cpu_baseline": cpu, "value": round(world * n_q / (ms * 1e-3), 1), "unit": "users/s", "n_gpus": world,
             "config": "%d users per GPU x %d items k=%d top-%d, train positives excluded (the bench's BPR model)" % (n_q, W["n_items"], k, topk),
             "ms": round(ms, 3), "tflops": round(world * 2.0 * k * W["n_items"] * n_q / (ms * 1e-3) / 1e12, 2),
             "e2e": {"value": round(world * n_q / (ms_h * 1e-3), 1), "unit": "users/s", "h2d_bytes_per_step": int(h2d),
