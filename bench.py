@@ -603,6 +603,33 @@ def run_rank_c5(engine, dev, world=1, over_ranks=lambda ms: ms):
                          "note": "2*k*n_items flop per user over the whole call (pack + tensor pass + exact finish)"}}
 
 
+def reference_mf_ratings_per_s(rid, cid, val, n_users, n_items, k, budget_s=8.0):
+    """ratings/s of the UNMODIFIED reference kernel backend_cpu.fit_sgd (cornac/models/mf/backend_cpu.pyx:35-97) with all
+    host threads on a bounded rating sample.  Returns (ratings/s, threads, epochs, seconds) or None."""
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.isdir(os.path.join(ref, "cornac")):
+        return None
+    if ref not in sys.path:
+        sys.path.insert(0, ref)
+    import multiprocessing
+    from cornac.models.mf import backend_cpu
+    rng = np.random.RandomState(5)
+    n_u = int(rid.max()) + 1 if len(rid) else 1
+    U = rng.normal(0, 0.01, (n_u, k)).astype(np.float32)
+    V = rng.normal(0, 0.01, (n_items, k)).astype(np.float32)
+    Bu, Bi = np.zeros(n_u, np.float32), np.zeros(n_items, np.float32)
+    rid64, cid64 = np.ascontiguousarray(rid, dtype=np.int64), np.ascontiguousarray(cid, dtype=np.int64)
+    val32 = np.ascontiguousarray(val, dtype=np.float32)
+    threads = multiprocessing.cpu_count()
+    backend_cpu.fit_sgd(rid64[:100000], cid64[:100000], val32[:100000], U, V, Bu, Bi, 0.01, 0.02, 3.0, 1, threads, True, False, False)
+    epochs, t0 = 0, time.perf_counter()
+    while epochs < 1 or time.perf_counter() - t0 < budget_s / 2:
+        backend_cpu.fit_sgd(rid64, cid64, val32, U, V, Bu, Bi, 0.01, 0.02, 3.0, 1, threads, True, False, False)
+        epochs += 1
+    secs = time.perf_counter() - t0
+    return epochs * len(val32) / secs, threads, epochs, secs
+
+
 def run_mf(W, engine, data, dev):
     """secondary metric: MF ratings/s (b200_mf_epoch, Hogwild + atomic scatter) on the same interaction matrix
     with synthetic ratings in {1..5}, stored by user (CSR order), k = 128 as in BASELINE.json configs[3]."""
@@ -630,7 +657,18 @@ def run_mf(W, engine, data, dev):
     ms = e0.elapsed_time(e1) / 3
     peak, _ = measured_peaks()
     gbs = n * (16 * k + 28) / (ms * 1e-3) / 1e9
-    return {"metric": "MF ratings/sec", "value": round(n / (ms * 1e-3), 1), "unit": "ratings/s",
+    cpu = None
+    try:                                                    # a reported baseline, never a reason for the bench line to fail
+        n_s = min(n, 10_000_000)                            # bounded sample: the first 10 M ratings (users in CSR order)
+        r = reference_mf_ratings_per_s(rid[:n_s].cpu().numpy(), cid[:n_s].cpu().numpy(), val[:n_s].cpu().numpy(),
+                                       W["n_users"], W["n_items"], k)
+        if r is not None:
+            cpu = {"value": round(r[0], 1), "unit": "ratings/s", "cores": r[1], "kind": "reference",
+                   "sample": "backend_cpu.fit_sgd of the compiled reference, %d epoch(s) over the first %d ratings of the same "
+                             "list (%d items, k=%d) in %.1fs" % (r[2], n_s, W["n_items"], k, r[3])}
+    except Exception as exc:                                # noqa: BLE001
+        cpu = {"unavailable": "%s: %s" % (type(exc).__name__, exc)}
+    return {"metric": "MF ratings/sec", "cpu_baseline": cpu, "value": round(n / (ms * 1e-3), 1), "unit": "ratings/s",
             "config": "%d users x %d items x %d ratings, k=%d, use_bias, Hogwild + red.global.add" % (W["n_users"], W["n_items"], n, k),
             "ms_per_epoch": round(ms, 3),
             "roofline": {"bound": "hbm", "achieved": round(gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(gbs / peak, 4),
