@@ -99,6 +99,33 @@ class DeviceScoringMixin:
         return engine.rank_topk(d["U"], d["V"], int(k), user_idx=uidx, item_base=d["item_base"], user_off=uoff,
                                 excl_indptr=ep, excl_indices=ei, n_items=d["n_items"])
 
+    # ---- batched Recommender.recommend ---------------------------------------------
+    def recommend_batch(self, batch_users, k=-1, remove_seen=False, train_set=None):
+        """Top-k recommendations for many users in one fused kernel call, in ORIGINAL ids: the batched form of
+        `Recommender.recommend` (cornac/models/recommender.py:532-580), with the signature of the reference's only batched
+        precedent (`ANNMixin.recommend_batch`, cornac/models/ann/recom_ann_base.py:182-235).  Seen items are removed
+        BEFORE the top-k (every list has k items, unlike the ANN post-filter).  Returns a list of lists of item ids."""
+        user_idx = [self.uid_map.get(uid, -1) for uid in batch_users]
+        if any(i == -1 for i in user_idx):
+            raise ValueError(f"{batch_users} is unknown to the model.")
+        if k < -1 or k > self.total_items:
+            raise ValueError(f"k={k} is invalid, there are {self.total_users} users in total.")
+        if remove_seen and train_set is None:
+            raise ValueError("train_set must be provided to remove seen items.")
+        if k == -1 or k > 4096 or any(not self.knows_user(u) for u in user_idx):
+            # full rankings / unknown users: not the batched path
+            return [self.recommend(uid, k=k, remove_seen=remove_seen, train_set=train_set) for uid in batch_users]
+        exclude = None
+        if remove_seen:
+            exclude = train_set.csr_matrix
+            n_rows = max(user_idx) + 1
+            if exclude.shape[0] < n_rows:                 # users without a training row have nothing to remove
+                import scipy.sparse as sp
+                exclude = sp.vstack([exclude, sp.csr_matrix((n_rows - exclude.shape[0], exclude.shape[1]), dtype=exclude.dtype)]).tocsr()
+        ids, _ = self.rank_batch(np.asarray(user_idx, dtype=np.int64), int(k), exclude=exclude)
+        item_ids = self.item_ids
+        return [[item_ids[i] for i in row if i >= 0] for row in ids]
+
     # ---- Recommender.rank ------------------------------------------------------------
     def _b200_rank(self, all_scores_dev, item_indices, k):
         """Reference semantics of Recommender.rank (recommender.py:513-530) given the

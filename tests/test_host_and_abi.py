@@ -87,3 +87,42 @@ def test_kernels_fail_loudly_without_gpu():
     from cornac_b200._lib import B200Error
     with pytest.raises(B200Error):
         engine.require_cuda()
+
+
+def test_recommend_batch_host_logic_with_a_stubbed_device():
+    """id mapping, argument errors and seen-item plumbing of DeviceScoringMixin.recommend_batch (the kernel call itself is
+    stubbed: rank_batch is covered on the GPU)."""
+    import scipy.sparse as sp
+    from conftest import have_cornac
+    if not have_cornac():
+        pytest.skip("needs the cornac package")
+    from cornac.models.recommender import Recommender
+    from cornac_b200._scoring import DeviceScoringMixin
+
+    class Stub(DeviceScoringMixin, Recommender):
+        def __init__(self):
+            Recommender.__init__(self, name="stub")
+            self.calls = []
+
+        def rank_batch(self, user_indices, k, exclude=None):
+            self.calls.append((np.asarray(user_indices).tolist(), k, None if exclude is None else exclude.shape))
+            n = len(user_indices)
+            ids = np.tile(np.arange(k, dtype=np.int32), (n, 1))
+            ids[:, -1] = -1                                   # a padded (short) list
+            return ids, np.zeros((n, k), np.float32)
+
+    m = Stub()
+    m.uid_map = {"a": 0, "b": 1, "c": 2}
+    m.iid_map = {"i%d" % j: j for j in range(6)}
+    m.num_users, m.num_items = 3, 6
+    out = m.recommend_batch(["c", "a"], k=3)
+    assert out == [["i0", "i1"], ["i0", "i1"]] and m.calls[-1] == ([2, 0], 3, None)
+    train = type("T", (), {"csr_matrix": sp.csr_matrix(np.eye(2, 6, dtype=np.float32))})()
+    m.recommend_batch(["c"], k=2, remove_seen=True, train_set=train)
+    assert m.calls[-1] == ([2], 2, (3, 6))                   # exclusion matrix padded to cover user 2
+    with pytest.raises(ValueError):
+        m.recommend_batch(["zz"], k=2)
+    with pytest.raises(ValueError):
+        m.recommend_batch(["a"], k=7)
+    with pytest.raises(ValueError):
+        m.recommend_batch(["a"], k=2, remove_seen=True)
