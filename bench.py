@@ -252,7 +252,9 @@ def main():
     ap.add_argument("--no-rank", action="store_true")
     args = ap.parse_args()
 
-    os.environ["NCCL_DEBUG"] = os.environ.get("B200_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+    # keep stdout to the one JSON line: NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION and above (WARN
+    # included).  An explicit value that names no level silences it whatever the box's environment or nccl.conf say.
+    os.environ["NCCL_DEBUG"] = os.environ.get("B200_NCCL_DEBUG", "NONE")
     import torch
     import torch.distributed as dist
 
