@@ -2,7 +2,7 @@
 # TEST INFRASTRUCTURE (not product code).
 #
 # Builds the UNMODIFIED reference (PreferredAI/cornac, mounted read-only at
-# /root/reference) into oracle/_ref/ so that
+# /root/reference) into baseline/_ref/ so that
 #   * tests can validate the C/numpy restatement in oracle/ against the real
 #     Cython/OpenMP kernels (cornac/models/bpr/recom_bpr.pyx:208-269,
 #     cornac/models/mf/backend_cpu.pyx:35-97, cornac/utils/fast_dot.pyx:40-43),
@@ -10,7 +10,7 @@
 #   * bench.py --impl reference can time the reference's own CPU path,
 #   * the drop-in models can be exercised through an unchanged cornac.Experiment.
 #
-# Nothing from the reference is copied into tracked files: oracle/_ref/ is
+# Nothing from the reference is copied into tracked files: baseline/_ref/ is
 # git-ignored (it still travels to the GPU box with gpurun, like our own .so).
 # The reference is a Python/Cython package, so "compiling its few source
 # files" means cythonising + g++ on its own setup.py extension list; we build a

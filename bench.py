@@ -1,22 +1,28 @@
 #!/usr/bin/env python
-"""bench.py -- BPR triplet-updates/s (and ranked users/s) on B200 vs the reference CPU path.
+"""bench.py -- BPR triplet-updates/s and ranked-users/s on 1/2/4/8 B200 vs the reference CPU path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c3|c2]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1]): synthetic 1M users x 100K items x 100M interactions,
-BPR k=64, one B200.  A "step" is one BPR epoch = nnz sampled triplets (what one call of the
-reference's BPR._fit_sgd does, cornac/models/bpr/recom_bpr.pyx:208-269).  For N > 1 every
-rank holds its own 1M-user / 100M-interaction shard (weak scaling), the 100K-item matrix is
-replicated and the item deltas are all-reduced once per epoch inside the timed region.
+Workload (default, BASELINE.json configs[2] -- the north_star target): ONE synthetic model of 10 M users x
+1 M items x 1 B interactions, BPR k = 128.  The matrix is generated as 8 fixed user blocks (1.25 M users /
+125 M interactions each, block b seeded 1234 + b, one shared item-popularity law), so it is THE SAME model
+for every N; `--gpus N` shards it by interaction count: rank r owns blocks [8 r / N, 8 (r + 1) / N)
+(STRONG scaling: total work fixed).  The 1 M-item matrix V (512 MB) and the biases are replicated and the
+item deltas are all-reduced once per epoch inside the timed region (NCCL over NVLink).  N = 1 holds the
+whole model on one GPU (about 35 GB of the 180 GB).
 
-value  = non-skipped triplet updates per second, inputs resident in HBM (CUDA events, max
-         over ranks);
-e2e    = the same through the host-buffer entry the plug-in's fit() uses
-         (engine.bpr_train_host): pinned-host CSR + factors -> H2D -> one epoch -> D2H;
-roofline / cpu_baseline / rank (ranked users/s) are reported alongside.
---impl reference times the reference's own Cython/OpenMP kernel (oracle/_ref) on the host
-cores, on a bounded sample of the same workload.
+A "step" is one BPR epoch over the whole model = 1 B sampled triplets in total (what one call of the
+reference's BPR._fit_sgd does, cornac/models/bpr/recom_bpr.pyx:208-269), i.e. nnz / N per rank.
+
+value  = non-skipped triplet updates per second over all ranks, inputs resident in HBM (CUDA events on
+         the launching stream, max over ranks);
+e2e    = the same through the host-buffer entry the plug-in's fit() uses (engine.bpr_train_host):
+         pinned-host CSR + factors -> H2D -> prepare -> one epoch -> D2H, per rank on its shard;
+roofline / cpu_baseline / per_rank / rank (configs[4]: all 10 M users of the trained model ranked against
+the 1 M items, top-100) / mf (configs[3]: MF k = 128 on the same 10 M x 1 M x 1 B rating list) ride along.
+--impl reference times the reference's own Cython/OpenMP kernel (baseline/_ref) on the host cores the
+process actually owns, on a bounded sample of the same workload.
 """
 import argparse
 import json
@@ -32,11 +38,19 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = dict(n_users=1_000_000, n_items=100_000, nnz=100_000_000, k=64, lr=0.05, reg=0.01, use_bias=True)
-# one GPU's share of BASELINE.json configs[2] (10M users x 1M items x 1B interactions, k=128, over 8 GPUs); `--workload c3shard`
-WORKLOAD_C3_SHARD = dict(n_users=1_250_000, n_items=1_000_000, nnz=125_000_000, k=128, lr=0.05, reg=0.01, use_bias=True)
-RANK_WORKLOAD = dict(n_q=75776, topk=100)          # secondary metric: ranked users/s on the same model
-CPU_SAMPLE = dict(n_users=100_000, nnz_target=10_000_000)   # bounded sample for the CPU legs (same k, same items)
+N_BLOCKS = 8
+WORKLOADS = {
+    # BASELINE.json configs[2]
+    "c3": dict(label="BASELINE.json configs[2]", n_users=10_000_000, n_items=1_000_000, nnz=1_000_000_000, k=128,
+               lr=0.05, reg=0.01, use_bias=True),
+    # BASELINE.json configs[1] (round-1 headline; kept for A/B runs)
+    "c2": dict(label="BASELINE.json configs[1]", n_users=1_000_000, n_items=100_000, nnz=100_000_000, k=64,
+               lr=0.05, reg=0.01, use_bias=True),
+}
+RANK_TOPK = 100
+RANK_E2E_BATCH = 1_000_000                          # users per host request of the rank e2e leg
+CPU_SAMPLE = dict(n_users=100_000)                  # bounded sample for the CPU legs: the first users of block 0
+ITEM_SEED = 4321                                    # the item-popularity law is one property of the model, shared by all blocks
 
 
 def log(*a):
@@ -45,16 +59,22 @@ def log(*a):
 
 # --------------------------------------------------------------------------------------
 # synthetic data (torch on the GPU is used as a fast array library here; not product code)
-def synth_interactions(n_users, n_items, nnz, seed, device):
+def synth_interactions(n_users, n_items, nnz, seed, device, item_seed=None):
     """Unique (u, i) pairs: user activity ~ log-normal (mean degree nnz/n_users), item
-    popularity ~ Zipf(1.0); returns CSR (indptr int32, indices int32) on `device`."""
+    popularity ~ Zipf(1.0); returns CSR (indptr int32, indices int32) on `device`.
+    item_seed: seed of the popular-item permutation (None: drawn from `seed`)."""
     import torch
     g = torch.Generator(device=device)
     g.manual_seed(seed)
     w_u = torch.exp(torch.randn(n_users, generator=g, device=device, dtype=torch.float64))
     cdf_u = torch.cumsum(w_u / w_u.sum(), 0)
     w_i = 1.0 / torch.arange(1, n_items + 1, device=device, dtype=torch.float64)
-    perm = torch.randperm(n_items, generator=g, device=device)          # popular ids spread over the id range
+    if item_seed is None:
+        perm = torch.randperm(n_items, generator=g, device=device)      # popular ids spread over the id range
+    else:
+        gi = torch.Generator(device=device)
+        gi.manual_seed(item_seed)
+        perm = torch.randperm(n_items, generator=gi, device=device)
     cdf_i = torch.cumsum(w_i / w_i.sum(), 0)
     keys = torch.empty(0, dtype=torch.int64, device=device)
     need = nnz
@@ -78,15 +98,52 @@ def synth_interactions(n_users, n_items, nnz, seed, device):
     return indptr.to(torch.int32), indices.contiguous()
 
 
-def init_factors(n_users, n_items, k, seed, device):
-    """(U[0,1) - 0.5) / k like BPR._init (recom_bpr.pyx:145-152)."""
+def block_shape(W):
+    """(users, interactions) of one of the N_BLOCKS user blocks the model is generated in."""
+    return W["n_users"] // N_BLOCKS, W["nnz"] // N_BLOCKS
+
+
+def rank_blocks(rank, world):
+    per = N_BLOCKS // world
+    return list(range(rank * per, (rank + 1) * per))
+
+
+def synth_shard(W, blocks, device):
+    """CSR of the user blocks `blocks` (consecutive), user ids local to the shard."""
+    import torch
+    ub, nb = block_shape(W)
+    ptrs, idxs, base = [], [], 0
+    for b in blocks:
+        ip, ix = synth_interactions(ub, W["n_items"], nb, seed=1234 + b, device=device, item_seed=ITEM_SEED)
+        ptrs.append(ip[:-1].to(torch.int64) + base)
+        base += int(ix.numel())
+        idxs.append(ix)
+        del ip, ix
+    ptrs.append(torch.tensor([base], dtype=torch.int64, device=device))
+    indptr = torch.cat(ptrs).to(torch.int32)
+    indices = torch.cat(idxs) if len(idxs) > 1 else idxs[0]
+    return indptr.contiguous(), indices.contiguous()
+
+
+def init_user_factors(W, blocks, device):
+    """(U[0,1) - 0.5) / k like BPR._init (recom_bpr.pyx:145-152), block b seeded 500 + b."""
+    import torch
+    ub, _ = block_shape(W)
+    U = torch.empty((ub * len(blocks), W["k"]), dtype=torch.float32, device=device)
+    for n, b in enumerate(blocks):
+        g = torch.Generator(device=device)
+        g.manual_seed(500 + b)
+        U[n * ub:(n + 1) * ub] = (torch.rand((ub, W["k"]), generator=g, device=device) - 0.5) / W["k"]
+    return U
+
+
+def init_item_factors(W, device, seed=99):
     import torch
     g = torch.Generator(device=device)
     g.manual_seed(seed)
-    U = (torch.rand((n_users, k), generator=g, device=device) - 0.5) / k
-    V = (torch.rand((n_items, k), generator=g, device=device) - 0.5) / k
-    B = torch.zeros(n_items, device=device)
-    return U, V, B
+    V = (torch.rand((W["n_items"], W["k"]), generator=g, device=device) - 0.5) / W["k"]
+    B = torch.zeros(W["n_items"], device=device)
+    return V, B
 
 
 # --------------------------------------------------------------------------------------
@@ -165,8 +222,8 @@ def tensor_peak():
         d = json.load(open(p))
         for key in ("bf16_tflops_sustained", "bf16_tflops"):
             if key in d:
-                return float(d[key])
-    return 2250.0
+                return float(d[key]), "measured sustained (MEASURED_PEAKS.json)"
+    return 1400.0, "fallback sustained (B200_PROFILING.md)"
 
 
 def algorithmic_bytes(k, updates, skipped, mean_deg):
@@ -177,12 +234,61 @@ def algorithmic_bytes(k, updates, skipped, mean_deg):
     return updates * (24 * k + 16 + 16 + search) + skipped * (16 + search)
 
 
+def host_cores():
+    """The host cores this process may actually use: the scheduler affinity mask capped by the cgroup CPU quota
+    (a 1-GPU lease of a 128-core box does not own 128 cores; 128 OpenMP threads on a 16-core quota run SLOWER
+    than 16).  The reference's own rule is multiprocessing.cpu_count() (recom_bpr.pyx:134-137), which ignores both."""
+    try:
+        aff = len(os.sched_getaffinity(0))
+    except Exception:
+        aff = os.cpu_count() or 1
+    quota = None
+    try:
+        f = open("/sys/fs/cgroup/cpu.max").read().split()                 # cgroup v2: "<quota> <period>" or "max <period>"
+        if f[0] != "max":
+            quota = float(f[0]) / float(f[1])
+    except Exception:
+        try:                                                                 # cgroup v1
+            q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            p = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / p
+        except Exception:
+            quota = None
+    use = aff if quota is None else max(1, min(aff, int(quota + 0.5)))
+    try:
+        load1 = os.getloadavg()[0]
+    except Exception:
+        load1 = None
+    return {"os_cpu_count": os.cpu_count(), "sched_affinity": aff, "cgroup_cpu_quota": quota, "threads_used": use,
+            "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS"), "loadavg_1m": load1}
+
+
+def measured_traffic(workload, kernel_name, samples_per_launch):
+    """DRAM bytes per launch of the timed kernel from the committed `ncu --set full` capture of THIS kernel on THIS
+    workload shape (profiles/bpr_hogwild_dram_bytes.json: per-sample bytes, kernel name, commit, capture file);
+    None when no capture of this kernel / shape exists."""
+    p = os.path.join(ROOT, "profiles", "bpr_hogwild_dram_bytes.json")
+    try:
+        rec = json.load(open(p)).get("captures", {}).get(workload)
+        if rec and rec.get("kernel") == kernel_name:
+            return {"bytes_per_launch": rec["dram_bytes_per_sample"] * samples_per_launch,
+                    "dram_bytes_per_sample": rec["dram_bytes_per_sample"], "capture": rec.get("capture"), "commit": rec.get("commit")}
+    except Exception:
+        pass
+    return None
+
+
 # --------------------------------------------------------------------------------------
+def ref_path():
+    return os.path.join(ROOT, "baseline", "_ref")
+
+
 def reference_fit_sgd_runner(indptr, indices, n_items, k, lr, reg, n_threads):
     """Returns (run_epoch() -> (correct, skipped), kind, cores).  Uses the UNMODIFIED compiled
-    reference (oracle/_ref: cornac.models.bpr.recom_bpr.BPR._fit_sgd + RNGVector) when it is
+    reference (baseline/_ref: cornac.models.bpr.recom_bpr.BPR._fit_sgd + RNGVector) when it is
     importable, else the oracle's OpenMP port."""
-    ref = os.path.join(ROOT, "oracle", "_ref")
+    ref = ref_path()
     n_users = len(indptr) - 1
     rng = np.random.RandomState(1)
     U = ((rng.uniform(0, 1, (n_users, k)).astype(np.float32) - 0.5) / k)
@@ -192,9 +298,8 @@ def reference_fit_sgd_runner(indptr, indices, n_items, k, lr, reg, n_threads):
     try:
         if ref not in sys.path:
             sys.path.insert(0, ref)
-        import multiprocessing
         from cornac.models.bpr.recom_bpr import BPR as RefBPR, RNGVector
-        n_threads = n_threads or multiprocessing.cpu_count()
+        n_threads = n_threads or host_cores()["threads_used"]
         m = RefBPR(k=k, learning_rate=lr, lambda_reg=reg, use_bias=True)
         rp = RNGVector(n_threads, len(user_ids) - 1, 11)
         rn = RNGVector(n_threads, n_items - 1, 12)
@@ -206,7 +311,7 @@ def reference_fit_sgd_runner(indptr, indices, n_items, k, lr, reg, n_threads):
     except Exception as e:   # reference install absent: the oracle port, all threads
         log("[bench] reference install not importable (%s); using the oracle OpenMP port" % (e,))
         from oracle import oracle as O
-        n_threads = n_threads or O.n_threads()
+        n_threads = n_threads or host_cores()["threads_used"]
         state = {"e": 0}
 
         def run():
@@ -217,7 +322,7 @@ def reference_fit_sgd_runner(indptr, indices, n_items, k, lr, reg, n_threads):
 
 def cpu_sample_csr(indptr_host, indices_host):
     """Bounded sample of the workload for the CPU legs: the first users of the same synthetic
-    matrix (same k, same 100K items, ~1/10 of the interactions)."""
+    matrix (same k, same item catalogue, ~1 % of the interactions)."""
     n_u = CPU_SAMPLE["n_users"]
     n_u = min(n_u, len(indptr_host) - 1)
     end = int(indptr_host[n_u])
@@ -237,40 +342,54 @@ def time_cpu_epochs(run, nnz, min_seconds=8.0, max_epochs=6):
 
 
 # --------------------------------------------------------------------------------------
+def workload_text(W, world):
+    return ("%s: ONE model of %d users x %d items x %d interactions, BPR k=%d, lr=%g reg=%g use_bias; user activity "
+            "log-normal, item popularity Zipf(1.0), unique pairs; generated as %d user blocks, rank r owns blocks "
+            "[%d r, %d (r+1))" % (W["label"], W["n_users"], W["n_items"], W["nnz"], W["k"], W["lr"], W["reg"], N_BLOCKS,
+                                  N_BLOCKS // world, N_BLOCKS // world))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debug only; result then INVALID)")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3shard"],
-                    help="c2 = BASELINE configs[1] per GPU (default, the quoted metric); c3shard = one GPU's share of configs[2]")
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink users and interactions (debug only; result then INVALID)")
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS),
+                    help="c3 = BASELINE configs[2] (default, the north_star target); c2 = configs[1]")
     ap.add_argument("--atomic", type=int, default=1, help="1: red.global.add scatter (default), 0: plain racy stores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-rank", action="store_true")
+    ap.add_argument("--no-mf", action="store_true")
     args = ap.parse_args()
 
-    # keep stdout to the one JSON line: NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION and above (WARN
-    # included).  An explicit value that names no level silences it whatever the box's environment or nccl.conf say.
-    os.environ["NCCL_DEBUG"] = os.environ.get("B200_NCCL_DEBUG", "NONE")
+    # stdout carries exactly ONE line, the JSON record: everything else any library prints to fd 1 (NCCL's INFO log goes
+    # to stdout by default) is sent to stderr, where the NCCL init lines ("... nranks N ...") stay visible.
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    os.environ.setdefault("NCCL_DEBUG", "INFO")
+    os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+
     import torch
     import torch.distributed as dist
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    W = dict(WORKLOAD if args.workload == "c2" else WORKLOAD_C3_SHARD)
+    W = dict(WORKLOADS[args.workload])
     if args.scale != 1.0:
-        W["n_users"] = max(1000, int(W["n_users"] * args.scale))
-        W["nnz"] = max(10000, int(W["nnz"] * args.scale))
+        W["n_users"] = max(8000, int(W["n_users"] * args.scale) // N_BLOCKS * N_BLOCKS)
+        W["nnz"] = max(80000, int(W["nnz"] * args.scale) // N_BLOCKS * N_BLOCKS)
     k = W["k"]
+    if world not in (1, 2, 4, 8):
+        raise SystemExit("bench.py shards %d user blocks: --gpus must be 1, 2, 4 or 8" % N_BLOCKS)
 
     if args.impl == "reference":
         if rank != 0:
             return 0
-        return run_reference_arm(args, W)
+        return run_reference_arm(args, W, world, real_stdout)
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
     torch.cuda.set_device(local_rank)
@@ -278,28 +397,33 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     from cornac_b200 import engine
+    from cornac_b200._lib import load
     from cornac_b200.parallel import ItemReplicaSync
+    L = load()
 
-    # ---- data: every rank builds its own user shard (weak scaling), items are shared
+    # ---- data: this rank's user blocks of the ONE model; items shared
     t0 = time.time()
-    indptr, indices = synth_interactions(W["n_users"], W["n_items"], W["nnz"], seed=1234 + rank, device=dev)
-    U, V, B = init_factors(W["n_users"], W["n_items"], k, seed=99, device=dev)     # V/B identical on all ranks
+    blocks = rank_blocks(rank, world)
+    indptr, indices = synth_shard(W, blocks, dev)
+    U = init_user_factors(W, blocks, dev)
+    V, B = init_item_factors(W, dev)
     if world > 1:
         dist.broadcast(V, 0); dist.broadcast(B, 0)
     data = engine.BprData(indptr, indices)
     nnz = data.nnz
-    mean_deg = nnz / W["n_users"]
+    n_local = data.n_users
+    mean_deg = W["nnz"] / W["n_users"]
+    data.prepare()
     torch.cuda.synchronize()
-    log("[bench] rank %d data ready in %.1fs: %d users x %d items x %d nnz" % (rank, time.time() - t0, W["n_users"], W["n_items"], nnz))
+    log("[bench] rank %d/%d data ready in %.1fs: blocks %s = %d users x %d items x %d nnz (%.1f GB allocated)"
+        % (rank, world, time.time() - t0, blocks, n_local, W["n_items"], nnz, torch.cuda.memory_allocated() / 1e9))
     sync = ItemReplicaSync([V, B]) if world > 1 else None
     stats = torch.zeros(2, dtype=torch.int64, device=dev)
     key = 0xB200
 
-    def step(epoch):
-        engine.bpr_epoch(data, W["n_items"], U, V, B, W["lr"], W["reg"], W["use_bias"], key + rank, epoch, stats,
+    def epoch(e):
+        engine.bpr_epoch(data, W["n_items"], U, V, B, W["lr"], W["reg"], W["use_bias"], key + rank, e, stats,
                          atomic=bool(args.atomic))
-        if sync is not None:
-            sync.exchange()
 
     def barrier():
         if world > 1:
@@ -307,65 +431,79 @@ def main():
         torch.cuda.synchronize()
 
     for e in range(args.warmup):
-        step(e)
+        epoch(e)
+        if sync is not None:
+            sync.exchange()
     barrier()
     stats.zero_()
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kern_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    ev0, ev1 = ev(), ev()
+    step_ev = [(ev(), ev(), ev()) for _ in range(args.steps)]
     barrier()
+    launches0 = int(L.b200_kernel_launches())
     clocks.window_begin()
     ev0.record()
     for e in range(args.steps):
-        kern_ev[e][0].record()
-        engine.bpr_epoch(data, W["n_items"], U, V, B, W["lr"], W["reg"], W["use_bias"], key + rank, args.warmup + e,
-                         stats, atomic=bool(args.atomic))
-        kern_ev[e][1].record()
+        a, b, c = step_ev[e]
+        a.record()
+        epoch(args.warmup + e)
+        b.record()
         if sync is not None:
             sync.exchange()
+        c.record()
     ev1.record()
     barrier()
     clocks.window_end()
+    launches = int(L.b200_kernel_launches()) - launches0
     clk = clocks.stop() if rank == 0 else None
     ms_total = ev0.elapsed_time(ev1)
-    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kern_ev]))
+    kern_list = [a.elapsed_time(b) for a, b, _ in step_ev]
+    xchg_list = [b.elapsed_time(c) for _, b, c in step_ev]
+    kern_ms, xchg_ms = float(np.mean(kern_list)), float(np.mean(xchg_list))
     correct, skipped = stats.cpu().tolist()
-    t = torch.tensor([ms_total, float(nnz * args.steps - skipped), float(skipped), kern_ms], dtype=torch.float64, device=dev)
+    mine = torch.tensor([ms_total, float(nnz * args.steps - skipped), float(skipped), kern_ms, xchg_ms, float(launches),
+                         float(np.min(kern_list)), float(np.max(kern_list))], dtype=torch.float64, device=dev)
     if world > 1:
-        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms_total, updates, skipped_all, kern_ms = tmax[0].item(), tsum[1].item(), tsum[2].item(), tmax[3].item()
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        allr = torch.stack(allr).cpu().numpy()
     else:
-        updates, skipped_all = t[1].item(), t[2].item()
+        allr = mine.cpu().numpy()[None, :]
+    ms_total = float(allr[:, 0].max())
+    updates, skipped_all = float(allr[:, 1].sum()), float(allr[:, 2].sum())
     value = updates / (ms_total * 1e-3)
 
-    # ---- roofline of the dominant kernel (bpr_hogwild_kernel), this rank's launches
+    # ---- roofline of the dominant kernel, per rank (every rank launches the same kernel on nnz / N samples)
     peak, peak_src = measured_peaks()
-    upd_per_launch = (nnz * args.steps - skipped) / args.steps
-    alg_bytes = algorithmic_bytes(k, upd_per_launch, skipped / args.steps, mean_deg)
-    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
-    traffic = None
-    prof = os.path.join(ROOT, "profiles", "bpr_hogwild_dram_bytes.json")
-    if os.path.exists(prof) and args.workload == "c2" and args.scale == 1.0:      # the capture is of this workload
-        try:
-            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
-    roofline = {"kernel": "bpr_hogwild_chunk_kernel<G=%d,NPL=1,VEC,%s>" % (min(32, max(4, k // 4)), "ATOMIC" if args.atomic else "PLAIN"), "bound": "hbm", "achieved": round(achieved, 1),
-                "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
-                "peak_source": peak_src, "algorithmic_bytes_per_update": 24 * k + 32 + 4 * math.ceil(math.log2(mean_deg + 1)),
-                "kernel_ms": round(kern_ms, 3)}
+    g_lanes = min(32, max(4, k // 4))
+    kernel_name = "bpr_hogwild_chunk_kernel<G=%d,NPL=1,VEC,%s>" % (g_lanes, "ATOMIC" if args.atomic else "PLAIN")
+    fracs = []
+    for r in range(world):
+        upd_r, skp_r = allr[r, 1] / args.steps, allr[r, 2] / args.steps
+        fracs.append(algorithmic_bytes(k, upd_r, skp_r, mean_deg) / (allr[r, 3] * 1e-3) / 1e9)
+    slow = int(np.argmax(allr[:, 3]))
+    roofline = {"kernel": kernel_name, "bound": "hbm", "achieved": round(fracs[slow], 1), "peak": peak, "unit": "GB/s",
+                "frac": round(fracs[slow] / peak, 4), "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_update": 24 * k + 32 + 4 * math.ceil(math.log2(mean_deg + 1)),
+                "kernel_ms": round(float(allr[slow, 3]), 3), "rank": slow,
+                "note": "slowest rank's launches; achieved = algorithmic bytes of one launch / its mean CUDA-event duration",
+                "frac_per_rank": [round(f / peak, 4) for f in fracs]}
+    tr = measured_traffic(args.workload if args.scale == 1.0 else "scaled", kernel_name, nnz)
+    if tr is not None:
+        roofline["traffic"] = tr["bytes_per_launch"]
+        roofline["traffic_source"] = tr
+    per_rank = {"kernel_ms_mean": [round(float(x), 3) for x in allr[:, 3]],
+                "kernel_ms_min": [round(float(x), 3) for x in allr[:, 6]],
+                "kernel_ms_max": [round(float(x), 3) for x in allr[:, 7]],
+                "exchange_ms_mean": [round(float(x), 3) for x in allr[:, 4]],
+                "kernel_ms_min_med_max_over_ranks": [round(float(np.min(allr[:, 3])), 3), round(float(np.median(allr[:, 3])), 3),
+                                                     round(float(np.max(allr[:, 3])), 3)],
+                "exchange": ("delta_make -> NCCL all-reduce(%d MB) -> delta_apply" % ((W["n_items"] * (k + 1) * 4) // 1000000))
+                            if world > 1 else "none (single GPU)"}
 
-    # ---- e2e: host buffers through the plug-in's training entry, copies inside the timed region
-    e2e = None
-    if not args.no_e2e:
-        e2e = run_e2e(args, W, engine, indptr, indices, dev, world, rank)
-
-    # ---- secondary metric: ranked users/s (score + exclusion + top-k) on the trained model
-    # (users shard across the GPUs with the item side replicated and no collective: every rank ranks its own users,
-    # the time is the max over ranks)
     def over_ranks(ms):
         if world == 1:
             return ms
@@ -373,19 +511,27 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    # the pair store / membership table are only needed by the epochs
+    data.pairs = data.table = None
+    sync = None
+    torch.cuda.empty_cache()
+
+    # ---- e2e: host buffers through the plug-in's training entry, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, W, engine, indptr, indices, blocks, dev, world, rank)
+
+    # ---- configs[4]: every user of the trained model ranked against the item catalogue (users stay sharded, no collective)
     rank_metric = None
     if not args.no_rank:
-        rank_metric = run_rank(W, engine, data, U, V, B, dev, world, over_ranks)
+        rank_metric = run_rank(W, engine, L, data, U, V, B, dev, world, over_ranks)
+    del U
+    torch.cuda.empty_cache()
 
+    # ---- configs[3]: MF on the same rating list, all ranks
     mf_metric = None
-    rank_c5 = None
-    if not args.no_rank:
-        if rank == 0:
-            mf_metric = run_mf(W, engine, data, dev)
-        if args.workload == "c2":
-            del data
-            torch.cuda.empty_cache()
-            rank_c5 = run_rank_c5(engine, dev, world, over_ranks)
+    if not args.no_mf:
+        mf_metric = run_mf(W, engine, data, dev, world, over_ranks)
 
     # ---- CPU baseline on rank 0, N = 1 only
     cpu_baseline = None
@@ -395,43 +541,46 @@ def main():
         v, secs, eps = time_cpu_epochs(run, len(ix))
         cpu_baseline = {"value": round(v, 1), "unit": "triplet-updates/s", "cores": cores, "kind": kind,
                         "sample": "first %d users of the same matrix: %d interactions, %d items, k=%d, %d epoch(s) in %.1fs"
-                                  % (len(ip) - 1, len(ix), W["n_items"], k, eps, secs)}
+                                  % (len(ip) - 1, len(ix), W["n_items"], k, eps, secs),
+                        "host": host_cores()}
 
     if rank == 0:
         out = {
             "metric": "BPR triplet-updates/sec", "value": round(value, 1), "unit": "updates/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 3),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": ("BASELINE.json configs[1]" if args.workload == "c2" else "1/8 of BASELINE.json configs[2]")
-                                   + ": %d users x %d items x %d interactions per GPU, BPR k=%d, "
-                                   "lr=%g reg=%g use_bias; user activity log-normal, item popularity Zipf(1.0), unique pairs"
-                                   % (W["n_users"], W["n_items"], nnz, k, W["lr"], W["reg"]),
-                       "step": "one epoch = nnz sampled triplets (Hogwild, on-device Philox sampling)",
-                       "l2": "working set (U %d MB + pair store %d MB + membership table per GPU) exceeds the 126 MB L2; no flush needed"
-                             % (W["n_users"] * k * 4 // 1000000, nnz * 8 // 1000000),
-                       "parallelism": "users sharded x%d, items replicated, 1 all-reduce of item deltas per epoch" % world,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_text(W, world),
+                       "step": "one epoch over the whole model = %d sampled triplets (%d per rank; Hogwild, on-device Philox sampling)"
+                               % (W["nnz"], nnz),
+                       "l2": "working set per rank (U %d MB + V %d MB + pair store %d MB + membership table) exceeds the 126 MB L2; no flush needed"
+                             % (n_local * k * 4 // 1000000, W["n_items"] * k * 4 // 1000000, nnz * 8 // 1000000),
+                       "parallelism": "users sharded x%d by interaction count, items replicated, 1 all-reduce of item deltas per epoch" % world,
                        "scatter": "red.global.add.v4.f32" if args.atomic else "st.global.cg.v4.f32 (Hogwild)"},
-            "samples_per_s": round((nnz * args.steps * world) / (ms_total * 1e-3), 1),
-            "skipped_frac": round(skipped_all / (nnz * args.steps * world), 5),
-            "gpu_launches": args.steps * (1 + (2 * 2 if world > 1 else 0)),
-            "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "rank": rank_metric, "rank_c5": rank_c5, "mf": mf_metric,
+            "samples_per_s": round((W["nnz"] * args.steps) / (ms_total * 1e-3), 1),
+            "skipped_frac": round(skipped_all / (W["nnz"] * args.steps), 5),
+            "timed_region_s": round(ms_total * 1e-3, 3),
+            "gpu_launches": int(allr[:, 5].sum()),
+            "gpu_launches_note": "b200_kernel_launches() delta over the timed region, summed over ranks (NCCL's own kernels not counted)",
+            "clocks": clk, "roofline": roofline, "per_rank": per_rank, "cpu_baseline": cpu_baseline, "e2e": e2e,
+            "rank": rank_metric, "mf": mf_metric, "host": host_cores(),
         }
         if args.scale != 1.0:
             out["INVALID"] = "scaled-down debug run (--scale %g)" % args.scale
-        print(json.dumps(out), flush=True)
+        real_stdout.write(json.dumps(out) + "\n")
+        real_stdout.flush()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
 
 
-def run_e2e(args, W, engine, indptr, indices, dev, world, rank):
+def run_e2e(args, W, engine, indptr, indices, blocks, dev, world, rank):
     import torch
     import torch.distributed as dist
-    k = W["k"]
     pin = lambda t: t.cpu().pin_memory()
     h_indptr, h_indices = pin(indptr), pin(indices)
-    U, V, B = init_factors(W["n_users"], W["n_items"], k, seed=7, device=dev)
+    U = init_user_factors(W, blocks, dev)
+    V, B = init_item_factors(W, dev, seed=7)
     hU, hV, hB = pin(U), pin(V), pin(B)
     del U, V, B
     torch.cuda.empty_cache()
@@ -457,15 +606,16 @@ def run_e2e(args, W, engine, indptr, indices, dev, world, rank):
         upd += nnz - s
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    t = torch.tensor([dt, float(upd)], dtype=torch.float64, device=dev)
+    t = torch.tensor([dt, float(upd), float(h2d), float(d2h)], dtype=torch.float64, device=dev)
     if world > 1:
         tm = t.clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         ts = t.clone(); dist.all_reduce(ts, op=dist.ReduceOp.SUM)
-        dt, upd = tm[0].item(), ts[1].item()
+        dt, upd, h2d, d2h = tm[0].item(), ts[1].item(), ts[2].item(), ts[3].item()
     return {"value": round(upd / dt, 1), "unit": "updates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "steps": steps, "ms_per_step": round(dt / steps * 1e3, 2),
-            "path": "engine.bpr_train_host (the call BPR.fit makes): pinned host CSR + U/V/B -> H2D -> prepare -> 1 epoch"
-                    + (" -> item-delta all-reduce" if world > 1 else "") + " -> D2H U/V/B + stats"}
+            "path": "engine.bpr_train_host (the call BPR.fit makes) on every rank's shard: pinned host CSR + U/V/B -> H2D -> "
+                    "prepare (pair store + membership table) -> 1 epoch" + (" -> item-delta all-reduce" if world > 1 else "")
+                    + " -> D2H U/V/B + stats; bytes are summed over ranks"}
 
 
 def reference_rank_users_per_s(U_host, V_host, B_host, topk, budget_s=8.0):
@@ -473,7 +623,7 @@ def reference_rank_users_per_s(U_host, V_host, B_host, topk, budget_s=8.0):
     copy(B) + fast_dot(U[u], V) (recom_bpr.pyx:272-297, OpenMP over the items) + argpartition top-k
     (recommender.py:476-530) -- called once per user like ranking_eval does, for a bounded number of users.
     Returns (users/s, users timed, seconds) or None when the compiled reference is not importable."""
-    ref = os.path.join(ROOT, "oracle", "_ref")
+    ref = ref_path()
     if not os.path.isdir(os.path.join(ref, "cornac")):
         return None
     if ref not in sys.path:
@@ -495,125 +645,94 @@ def reference_rank_users_per_s(U_host, V_host, B_host, topk, budget_s=8.0):
     return n / secs, n, secs
 
 
-def run_rank(W, engine, data, U, V, B, dev, world=1, over_ranks=lambda ms: ms):
-    """ranked users/s: score + exclusion of train positives + top-100 for a batch of users (tensor-core fused
-    kernel), device-resident request (`value`) and through the host-buffer entry (`e2e`)."""
+def run_rank(W, engine, L, data, U, V, B, dev, world=1, over_ranks=lambda ms: ms):
+    """BASELINE.json configs[4] on the model the bench just trained: EVERY user of this rank's shard (10 M / N) is
+    scored against all items (U x V^T + B on the tensor cores), the user's train positives are excluded, top-100 kept.
+    `value` = device-resident request; `e2e` = host request -> H2D -> kernels -> D2H ids + scores."""
     import torch
-    from cornac_b200._lib import load
-    L = load()
-    n_q, topk, k = RANK_WORKLOAD["n_q"], RANK_WORKLOAD["topk"], W["k"]
-    n_q = min(n_q, W["n_users"])
-    uidx = torch.arange(n_q, device=dev, dtype=torch.int64)
-    ex_ptr = data.indptr[: n_q + 1].to(torch.int64).contiguous()
-    ex_idx = data.indices[: int(ex_ptr[-1].item())].contiguous()
-    nb = int(L.b200_rank_topk_workspace_bytes(n_q, W["n_items"], k, topk))
+    import torch.distributed as dist
+    topk, k, n_items = RANK_TOPK, W["k"], W["n_items"]
+    n_q = data.n_users
+    ex_ptr = data.indptr.to(torch.int64).contiguous()
+    ex_idx = data.indices
+    nb = int(L.b200_rank_topk_workspace_bytes(n_q, n_items, k, topk))
     ws = torch.empty(max(nb, 16), dtype=torch.uint8, device=dev)
-
-    def go():
-        return engine.rank_topk(U, V, topk, user_idx=uidx, item_base=B, excl_indptr=ex_ptr, excl_indices=ex_idx, workspace=ws)
-    go()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(3):
-        go()
-    e1.record()
+    n_warm = min(n_q, 75776)
+    engine.rank_topk(U[:n_warm], V, topk, item_base=B, excl_indptr=ex_ptr[: n_warm + 1].contiguous(), excl_indices=ex_idx, workspace=ws)
     torch.cuda.synchronize()
     if world > 1:
-        dist_barrier()
-    ms = over_ranks(e0.elapsed_time(e1) / 3)
-    # end to end: pinned host request (user ids + exclusion CSR) -> H2D -> kernels -> D2H ids + scores
-    h_u = uidx.cpu().pin_memory()
-    h_p, h_i = ex_ptr.cpu().pin_memory(), ex_idx.cpu().pin_memory()
-    o_i = torch.empty((n_q, topk), dtype=torch.int32).pin_memory()
-    o_s = torch.empty((n_q, topk), dtype=torch.float32).pin_memory()
+        dist.barrier()
+    launches0 = int(L.b200_kernel_launches())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    ids, sc = engine.rank_topk(U, V, topk, item_base=B, excl_indptr=ex_ptr, excl_indices=ex_idx, workspace=ws)
+    e1.record()
+    torch.cuda.synchronize()
+    launches = int(L.b200_kernel_launches()) - launches0
+    ms = over_ranks(e0.elapsed_time(e1))
+    filled = float((ids[: min(n_q, 100000)] >= 0).float().mean().item())
+    del ids, sc
+    torch.cuda.empty_cache()
+    # end to end: pinned host request (user ids + their exclusion CSR) -> H2D -> kernels -> D2H ids + scores
+    nb_e = min(n_q, RANK_E2E_BATCH)
+    n_batches = 2 if n_q >= 2 * nb_e else 1
+    reqs = []
+    for b in range(n_batches):
+        lo = b * nb_e
+        p = ex_ptr[lo: lo + nb_e + 1]
+        base = int(p[0].item())
+        reqs.append((torch.arange(lo, lo + nb_e, dtype=torch.int64).pin_memory(), (p - base).cpu().pin_memory(),
+                     ex_idx[base: int(p[-1].item())].cpu().pin_memory()))
+    o_i = torch.empty((nb_e, topk), dtype=torch.int32).pin_memory()
+    o_s = torch.empty((nb_e, topk), dtype=torch.float32).pin_memory()
 
-    def go_host():
-        engine.rank_topk_host(U, V, topk, h_u.numpy(), item_base=B, excl_indptr=h_p.numpy(), excl_indices=h_i.numpy(),
+    def go_host(r):
+        engine.rank_topk_host(U, V, topk, r[0].numpy(), item_base=B, excl_indptr=r[1].numpy(), excl_indices=r[2].numpy(),
                               out_ids=o_i.numpy(), out_scores=o_s.numpy(), workspace=ws)
-    go_host()
+    go_host(reqs[0])
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(3):
-        go_host()
+    for r in reqs:
+        go_host(r)
     torch.cuda.synchronize()
-    ms_h = over_ranks((time.perf_counter() - t0) / 3 * 1e3)
-    h2d = h_u.numel() * 8 + h_p.numel() * 8 + h_i.numel() * 4
+    ms_h = over_ranks((time.perf_counter() - t0) * 1e3)
+    h2d = sum(r[0].numel() * 8 + r[1].numel() * 8 + r[2].numel() * 4 for r in reqs) / len(reqs)
     cpu = None
     if world == 1:
         try:                                                # a reported baseline, never a reason for the bench line to fail
             r = reference_rank_users_per_s(U[:4096].cpu().numpy(), V.cpu().numpy(), B.cpu().numpy(), topk)
             if r is not None:
-                cpu = {"value": round(r[0], 1), "unit": "users/s", "cores": os.cpu_count(), "kind": "reference",
+                cpu = {"value": round(r[0], 1), "unit": "users/s", "cores": host_cores()["threads_used"], "kind": "reference",
                        "sample": "cornac.models.BPR.rank(u, k=%d) of the compiled reference for %d users of the same model "
-                                 "(%d items, k=%d) in %.1fs, no exclusion list" % (topk, r[1], W["n_items"], k, r[2])}
+                                 "(%d items, k=%d) in %.1fs, no exclusion list (OpenMP default thread count)" % (topk, r[1], n_items, k, r[2])}
         except Exception as exc:                            # noqa: BLE001
             cpu = {"unavailable": "%s: %s" % (type(exc).__name__, exc)}
-    return {"metric": "ranked users/sec", "cpu_baseline": cpu, "value": round(world * n_q / (ms * 1e-3), 1), "unit": "users/s", "n_gpus": world,
-            "config": "%d users per GPU x %d items k=%d top-%d, train positives excluded (the bench's BPR model)" % (n_q, W["n_items"], k, topk),
-            "ms": round(ms, 3), "tflops": round(world * 2.0 * k * W["n_items"] * n_q / (ms * 1e-3) / 1e12, 2),
-            "e2e": {"value": round(world * n_q / (ms_h * 1e-3), 1), "unit": "users/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(n_q * topk * 8), "ms": round(ms_h, 3),
-                    "path": "engine.rank_topk_host: pinned user ids + exclusion CSR -> H2D -> b200_rank_topk -> D2H ids + scores"}}
-
-
-def dist_barrier():
-    import torch
-    import torch.distributed as dist
-    dist.barrier()
-    torch.cuda.synchronize()
-
-
-def run_rank_c5(engine, dev, world=1, over_ranks=lambda ms: ms):
-    """ranked users/s on the item side of BASELINE.json configs[4] (1 M items, k = 128, top-100, 100 seen items
-    excluded per user): one call of b200_rank_topk for 75 776 users, random N(0, 0.1) factors and biases."""
-    import torch
-    from cornac_b200._lib import load
-    L = load()
-    n_items, k, n_q, topk, n_excl = 1_000_000, 128, 75776, 100, 100
-    g = torch.Generator(device=dev)
-    g.manual_seed(11)
-    U = torch.randn((n_q, k), generator=g, device=dev) * 0.1
-    V = torch.randn((n_items, k), generator=g, device=dev) * 0.1
-    B = torch.randn(n_items, generator=g, device=dev) * 0.1
-    ex = torch.randint(0, n_items, (n_q, n_excl), generator=g, device=dev, dtype=torch.int32)
-    ex_idx = torch.sort(ex, dim=1)[0].contiguous().view(-1)
-    ex_ptr = (torch.arange(n_q + 1, device=dev, dtype=torch.int64) * n_excl).contiguous()
-    nb = int(L.b200_rank_topk_workspace_bytes(n_q, n_items, k, topk))
-    ws = torch.empty(max(nb, 16), dtype=torch.uint8, device=dev)
-
-    def go():
-        return engine.rank_topk(U, V, topk, item_base=B, excl_indptr=ex_ptr, excl_indices=ex_idx, workspace=ws)
-    go()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(3):
-        go()
-    e1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist_barrier()
-    ms = over_ranks(e0.elapsed_time(e1) / 3)
-    tf_peak = tensor_peak() * world
-    tfl = world * 2.0 * k * n_items * n_q / (ms * 1e-3) / 1e12
-    return {"metric": "ranked users/sec", "value": round(world * n_q / (ms * 1e-3), 1), "unit": "users/s", "n_gpus": world,
-            "config": "%d users per GPU x %d items k=%d top-%d, %d excluded items per user (BASELINE.json configs[4] item side)"
-                      % (n_q, n_items, k, topk, n_excl), "ms": round(ms, 3),
-            "roofline": {"kernel": "rank_tc_kernel (tcgen05 fp16 -> f32) + finish", "bound": "tensor", "achieved": round(tfl, 1),
-                         "peak": tf_peak, "unit": "TFLOP/s", "frac": round(tfl / tf_peak, 4) if tf_peak else None,
-                         "note": "2*k*n_items flop per user over the whole call (pack + tensor pass + exact finish)"}}
+    tf_peak, tf_src = tensor_peak()
+    users_all = n_q * world
+    tfl = 2.0 * k * n_items * users_all / (ms * 1e-3) / 1e12
+    return {"metric": "ranked users/sec", "value": round(users_all / (ms * 1e-3), 1), "unit": "users/s", "n_gpus": world,
+            "config": "BASELINE.json configs[4] on the trained bench model: all %d users (%d per rank) x %d items, k=%d, top-%d, "
+                      "each user's train positives excluded" % (users_all, n_q, n_items, k, topk),
+            "ms": round(ms, 3), "filled_frac_of_lists": round(filled, 4), "gpu_launches": launches,
+            "roofline": {"kernel": "rank_tc_kernel (tcgen05 fp16 -> f32) + finish + packs", "bound": "tensor", "achieved": round(tfl, 1),
+                         "peak": tf_peak * world, "unit": "TFLOP/s", "frac": round(tfl / (tf_peak * world), 4), "peak_source": tf_src,
+                         "note": "2*k*n_items flop per user over the WHOLE call (pack + tensor pass + exact finish), all ranks"},
+            "cpu_baseline": cpu,
+            "e2e": {"value": round(world * nb_e * len(reqs) / (ms_h * 1e-3), 1), "unit": "users/s",
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(nb_e * topk * 8), "ms_per_step": round(ms_h / len(reqs), 3),
+                    "steps": len(reqs),
+                    "path": "engine.rank_topk_host per rank, %d users per request: pinned user ids + exclusion CSR -> H2D -> "
+                            "b200_rank_topk -> D2H ids + scores" % nb_e}}
 
 
 def reference_mf_ratings_per_s(rid, cid, val, n_users, n_items, k, budget_s=8.0):
-    """ratings/s of the UNMODIFIED reference kernel backend_cpu.fit_sgd (cornac/models/mf/backend_cpu.pyx:35-97) with all
-    host threads on a bounded rating sample.  Returns (ratings/s, threads, epochs, seconds) or None."""
-    ref = os.path.join(ROOT, "oracle", "_ref")
+    """ratings/s of the UNMODIFIED reference kernel backend_cpu.fit_sgd (cornac/models/mf/backend_cpu.pyx:35-97) with the
+    host threads this process owns on a bounded rating sample.  Returns (ratings/s, threads, epochs, seconds) or None."""
+    ref = ref_path()
     if not os.path.isdir(os.path.join(ref, "cornac")):
         return None
     if ref not in sys.path:
         sys.path.insert(0, ref)
-    import multiprocessing
     from cornac.models.mf import backend_cpu
     rng = np.random.RandomState(5)
     n_u = int(rid.max()) + 1 if len(rid) else 1
@@ -622,7 +741,7 @@ def reference_mf_ratings_per_s(rid, cid, val, n_users, n_items, k, budget_s=8.0)
     Bu, Bi = np.zeros(n_u, np.float32), np.zeros(n_items, np.float32)
     rid64, cid64 = np.ascontiguousarray(rid, dtype=np.int64), np.ascontiguousarray(cid, dtype=np.int64)
     val32 = np.ascontiguousarray(val, dtype=np.float32)
-    threads = multiprocessing.cpu_count()
+    threads = host_cores()["threads_used"]
     backend_cpu.fit_sgd(rid64[:100000], cid64[:100000], val32[:100000], U, V, Bu, Bi, 0.01, 0.02, 3.0, 1, threads, True, False, False)
     epochs, t0 = 0, time.perf_counter()
     while epochs < 1 or time.perf_counter() - t0 < budget_s / 2:
@@ -632,10 +751,13 @@ def reference_mf_ratings_per_s(rid, cid, val, n_users, n_items, k, budget_s=8.0)
     return epochs * len(val32) / secs, threads, epochs, secs
 
 
-def run_mf(W, engine, data, dev):
-    """secondary metric: MF ratings/s (b200_mf_epoch, Hogwild + atomic scatter) on the same interaction matrix
-    with synthetic ratings in {1..5}, stored by user (CSR order), k = 128 as in BASELINE.json configs[3]."""
+def run_mf(W, engine, data, dev, world=1, over_ranks=lambda ms: ms):
+    """BASELINE.json configs[3]: MF ratings/s (b200_mf_epoch, Hogwild + atomic scatter), k = 128, on the rating list made
+    of the model's interactions with synthetic ratings in {1..5}, stored by user (CSR order); every rank trains its
+    shard, V / Bi are replicated and all-reduced once per epoch like BPR's."""
     import torch
+    import torch.distributed as dist
+    from cornac_b200.parallel import ItemReplicaSync
     k = 128
     g = torch.Generator(device=dev)
     g.manual_seed(5)
@@ -643,51 +765,73 @@ def run_mf(W, engine, data, dev):
     rid = data.coo_row
     cid = data.indices
     val = torch.randint(1, 6, (n,), generator=g, device=dev).float()
-    U = torch.randn((W["n_users"], k), generator=g, device=dev) * 0.01
-    V = torch.randn((W["n_items"], k), generator=g, device=dev) * 0.01
-    Bu, Bi = torch.zeros(W["n_users"], device=dev), torch.zeros(W["n_items"], device=dev)
+    U = torch.randn((data.n_users, k), generator=g, device=dev) * 0.01
+    gv = torch.Generator(device=dev)
+    gv.manual_seed(6)
+    V = torch.randn((W["n_items"], k), generator=gv, device=dev) * 0.01
+    Bu, Bi = torch.zeros(data.n_users, device=dev), torch.zeros(W["n_items"], device=dev)
     loss = torch.zeros(1, device=dev)
-    for _ in range(2):
+    sync = ItemReplicaSync([V, Bi]) if world > 1 else None
+
+    def step():
         engine.mf_epoch(rid, cid, val, U, V, Bu, Bi, 0.01, 0.02, 3.0, True, loss)
+
+    for _ in range(2):
+        step()
+        if sync is not None:
+            sync.exchange()
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    steps = 3
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(3):
-        engine.mf_epoch(rid, cid, val, U, V, Bu, Bi, 0.01, 0.02, 3.0, True, loss)
+    for a, b in ev:
+        a.record()
+        step()
+        b.record()
+        if sync is not None:
+            sync.exchange()
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 3
+    ms = over_ranks(e0.elapsed_time(e1) / steps)
+    kms = over_ranks(float(np.mean([a.elapsed_time(b) for a, b in ev])))
     peak, _ = measured_peaks()
-    gbs = n * (16 * k + 28) / (ms * 1e-3) / 1e9
+    gbs = n * (16 * k + 28) / (kms * 1e-3) / 1e9
     cpu = None
-    try:                                                    # a reported baseline, never a reason for the bench line to fail
-        n_s = min(n, 10_000_000)                            # bounded sample: the first 10 M ratings (users in CSR order)
-        r = reference_mf_ratings_per_s(rid[:n_s].cpu().numpy(), cid[:n_s].cpu().numpy(), val[:n_s].cpu().numpy(),
-                                       W["n_users"], W["n_items"], k)
-        if r is not None:
-            cpu = {"value": round(r[0], 1), "unit": "ratings/s", "cores": r[1], "kind": "reference",
-                   "sample": "backend_cpu.fit_sgd of the compiled reference, %d epoch(s) over the first %d ratings of the same "
-                             "list (%d items, k=%d) in %.1fs" % (r[2], n_s, W["n_items"], k, r[3])}
-    except Exception as exc:                                # noqa: BLE001
-        cpu = {"unavailable": "%s: %s" % (type(exc).__name__, exc)}
-    return {"metric": "MF ratings/sec", "cpu_baseline": cpu, "value": round(n / (ms * 1e-3), 1), "unit": "ratings/s",
-            "config": "%d users x %d items x %d ratings, k=%d, use_bias, Hogwild + red.global.add" % (W["n_users"], W["n_items"], n, k),
-            "ms_per_epoch": round(ms, 3),
-            "roofline": {"bound": "hbm", "achieved": round(gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(gbs / peak, 4),
-                         "algorithmic_bytes_per_rating": 16 * k + 28}}
+    if world == 1:
+        try:                                                # a reported baseline, never a reason for the bench line to fail
+            n_s = min(n, 10_000_000)                        # bounded sample: the first 10 M ratings (users in CSR order)
+            r = reference_mf_ratings_per_s(rid[:n_s].cpu().numpy(), cid[:n_s].cpu().numpy(), val[:n_s].cpu().numpy(),
+                                           data.n_users, W["n_items"], k)
+            if r is not None:
+                cpu = {"value": round(r[0], 1), "unit": "ratings/s", "cores": r[1], "kind": "reference",
+                       "sample": "backend_cpu.fit_sgd of the compiled reference, %d epoch(s) over the first %d ratings of the same "
+                                 "list (%d items, k=%d) in %.1fs" % (r[2], n_s, W["n_items"], k, r[3])}
+        except Exception as exc:                            # noqa: BLE001
+            cpu = {"unavailable": "%s: %s" % (type(exc).__name__, exc)}
+    return {"metric": "MF ratings/sec", "cpu_baseline": cpu, "value": round(world * n / (ms * 1e-3), 1), "unit": "ratings/s", "n_gpus": world,
+            "config": "BASELINE.json configs[3]: %d users x %d items x %d ratings (%d per rank), k=%d, use_bias, Hogwild + red.global.add, "
+                      "item replicas all-reduced once per epoch" % (W["n_users"], W["n_items"], W["nnz"], n, k),
+            "ms_per_epoch": round(ms, 3), "steps": steps,
+            "roofline": {"kernel": "mf_hogwild_kernel", "bound": "hbm", "achieved": round(gbs, 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(gbs / peak, 4), "kernel_ms": round(kms, 3), "algorithmic_bytes_per_rating": 16 * k + 28,
+                         "note": "slowest rank's kernel launches"}}
 
 
-def run_reference_arm(args, W):
+def run_reference_arm(args, W, world, out_stream):
     """--impl reference: the reference's own CPU kernel on a bounded sample of the workload."""
     import torch
     k = W["k"]
+    ub, nb = block_shape(W)
     if torch.cuda.is_available():
-        indptr, indices = synth_interactions(W["n_users"], W["n_items"], W["nnz"], seed=1234, device=torch.device("cuda", 0))
+        indptr, indices = synth_interactions(ub, W["n_items"], nb, seed=1234, device=torch.device("cuda", 0), item_seed=ITEM_SEED)
         ip, ix = cpu_sample_csr(indptr.cpu().numpy(), indices.cpu().numpy())
         del indptr, indices
     else:   # no GPU: generate the sample directly at sample size
-        frac = CPU_SAMPLE["n_users"] / W["n_users"]
-        ipt, ixt = synth_interactions(CPU_SAMPLE["n_users"], W["n_items"], int(W["nnz"] * frac), seed=1234, device=torch.device("cpu"))
+        n_u = min(CPU_SAMPLE["n_users"], ub)
+        ipt, ixt = synth_interactions(n_u, W["n_items"], int(nb * (n_u / ub)), seed=1234, device=torch.device("cpu"), item_seed=ITEM_SEED)
         ip, ix = ipt.numpy(), ixt.numpy()
     run, kind, cores = reference_fit_sgd_runner(ip, ix, W["n_items"], k, W["lr"], W["reg"], 0)
     nnz = len(ix)
@@ -701,16 +845,18 @@ def run_reference_arm(args, W):
         upd += nnz - s
     dt = time.perf_counter() - t0
     v = upd / dt
-    sample = "first %d users of the configs[1] matrix: %d interactions, %d items, k=%d" % (len(ip) - 1, nnz, W["n_items"], k)
+    sample = "first %d users of block 0 of the matrix: %d interactions, %d items, k=%d" % (len(ip) - 1, nnz, W["n_items"], k)
     out = {"impl": "reference", "metric": "BPR triplet-updates/sec", "value": round(v, 1), "unit": "updates/s",
            "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": round(dt / steps * 1e3, 2),
-           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "BASELINE.json configs[1] (1M x 100K x 100M, BPR k=64), each step = one _fit_sgd epoch "
-                                  "over a bounded sample: " + sample},
-           "cpu_baseline": {"value": round(v, 1), "unit": "updates/s", "cores": cores, "kind": kind, "sample": sample},
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": workload_text(W, world) + "; each step = one _fit_sgd epoch over a bounded sample: " + sample},
+           "cpu_baseline": {"value": round(v, 1), "unit": "updates/s", "cores": cores, "kind": kind, "sample": sample, "host": host_cores()},
            "e2e": {"value": round(v, 1), "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out), flush=True)
+    if args.scale != 1.0:
+        out["INVALID"] = "scaled-down debug run (--scale %g)" % args.scale
+    out_stream.write(json.dumps(out) + "\n")
+    out_stream.flush()
     return 0
 
 

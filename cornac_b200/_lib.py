@@ -23,6 +23,7 @@ _vp, _i64, _i32, _u64, _u32, _f32, _int = (_c.c_void_p, _c.c_int64, _c.c_int32, 
 SIGNATURES = {
     "b200_last_error": (_c.c_char_p, []),
     "b200_abi_version": (_int, []),
+    "b200_kernel_launches": (_i64, []),
     "b200_device_info": (_int, [_vp, _vp, _vp]),
     "b200_bpr_table_slots": (_i64, [_i64]),
     "b200_bpr_prepare": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _i64, _vp]),

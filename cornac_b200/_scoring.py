@@ -47,10 +47,21 @@ class DeviceScoringMixin:
         self._b200_dev = dict(U=U, V=V, item_base=item_base, user_off=user_off, n_items=int(n_items))
 
     # ---- scores --------------------------------------------------------------------
+    @staticmethod
+    def _b200_check_users(user_indices, n_rows):
+        """The kernels gather U rows without a bounds check: an index outside [0, n_rows) raises here, like the
+        reference's numpy indexing does (IndexError), instead of reading foreign device memory."""
+        user_indices = np.asarray(user_indices, dtype=np.int64)
+        if user_indices.size and (int(user_indices.min()) < 0 or int(user_indices.max()) >= int(n_rows)):
+            bad = user_indices[(user_indices < 0) | (user_indices >= n_rows)]
+            raise IndexError("user index %d is out of bounds for the %d user rows of the model" % (int(bad[0]), int(n_rows)))
+        return user_indices
+
     def _b200_scores_dev(self, user_indices):
         """[n_q, n_items] device scores for known users."""
         d = self._b200_device()
-        uidx = torch.as_tensor(np.asarray(user_indices, dtype=np.int64)).cuda()
+        user_indices = self._b200_check_users(user_indices, d["U"].shape[0])
+        uidx = torch.as_tensor(user_indices).cuda()
         uoff = None if d["user_off"] is None else d["user_off"][uidx].contiguous()
         return engine.score_batch(d["U"], d["V"], user_idx=uidx, item_base=d["item_base"], user_off=uoff,
                                   n_items=d["n_items"])
@@ -66,7 +77,7 @@ class DeviceScoringMixin:
         ordered by (score desc, item id asc).
         """
         d = self._b200_device()
-        user_indices = np.asarray(user_indices, dtype=np.int64)
+        user_indices = self._b200_check_users(user_indices, d["U"].shape[0])
         ex_ptr, ex_idx = self._b200_exclusion_rows(user_indices, exclude)
         if d["user_off"] is None:
             return engine.rank_topk_host(d["U"], d["V"][: d["n_items"]], int(k), user_indices, item_base=d["item_base"],
@@ -85,19 +96,21 @@ class DeviceScoringMixin:
         sub.sort_indices()
         return sub.indptr.astype(np.int64), sub.indices.astype(np.int32)
 
-    def rank_batch_device(self, user_indices, k, exclude=None, _rows=None):
+    def rank_batch_device(self, user_indices, k, exclude=None, _rows=None, n_items=None):
         """`rank_batch` leaving the result on the GPU: (ids int32 [n_q, k], scores f32 [n_q, k]) CUDA tensors
-        (what the device-side metric reduction of cornac_b200.evaluation consumes)."""
+        (what the device-side metric reduction of cornac_b200.evaluation consumes).  `n_items` restricts the candidates
+        to the first n_items item rows (ranking_eval with exclude_unknowns: only the train items, base_method.py:200-202)."""
         d = self._b200_device()
-        user_indices = np.asarray(user_indices, dtype=np.int64)
+        user_indices = self._b200_check_users(user_indices, d["U"].shape[0])
         ex_ptr, ex_idx = _rows if _rows is not None else self._b200_exclusion_rows(user_indices, exclude)
         uidx = engine.to_device(user_indices, torch.int64)
         uoff = None if d["user_off"] is None else d["user_off"][uidx].contiguous()
         ep = None if ex_ptr is None else engine.to_device(ex_ptr, torch.int64)
         ei = None if ex_ptr is None else (engine.to_device(ex_idx, torch.int32) if len(ex_idx) else
                                           torch.zeros(1, dtype=torch.int32, device="cuda"))
+        n_rank = d["n_items"] if n_items is None else min(int(n_items), d["n_items"])
         return engine.rank_topk(d["U"], d["V"], int(k), user_idx=uidx, item_base=d["item_base"], user_off=uoff,
-                                excl_indptr=ep, excl_indices=ei, n_items=d["n_items"])
+                                excl_indptr=ep, excl_indices=ei, n_items=n_rank)
 
     # ---- batched Recommender.recommend ---------------------------------------------
     def recommend_batch(self, batch_users, k=-1, remove_seen=False, train_set=None):

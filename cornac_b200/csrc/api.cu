@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -22,6 +24,9 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line)
     set_error("CUDA error %d (%s) at %s:%d in `%s`", (int)e, cudaGetErrorString(e), base ? base + 1 : file, line, what);
     return B200_ERR_CUDA;
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int sm_count()
 {
@@ -70,7 +75,8 @@ __global__ void delta_apply_kernel(float4* __restrict__ x, float4* __restrict__ 
 using namespace b200;
 
 extern "C" const char* b200_last_error(void) { return g_err; }
-extern "C" int b200_abi_version(void) { return 1; }
+extern "C" int b200_abi_version(void) { return 2; }
+extern "C" int64_t b200_kernel_launches(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int b200_device_info(int* sms, int* cc_major, int* cc_minor)
 {
@@ -96,7 +102,7 @@ extern "C" int b200_delta_make(const float* x, const float* snapshot, float* del
     const int64_t n4 = aligned16(x, snapshot, delta) ? n / 4 : 0;
     const int grid = sm_count() * 8;
     delta_make_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)x, (const float4*)snapshot, (float4*)delta, n4,
-                                                              x, snapshot, delta, n);
+                                                              x, snapshot, delta, n); ::b200::count_launch();
     B200_CUDA(cudaGetLastError());
     return B200_OK;
 }
@@ -108,7 +114,7 @@ extern "C" int b200_delta_apply(float* x, float* snapshot, const float* delta, i
     const int64_t n4 = aligned16(x, snapshot, delta) ? n / 4 : 0;
     const int grid = sm_count() * 8;
     delta_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((float4*)x, (float4*)snapshot, (const float4*)delta, n4,
-                                                               x, snapshot, delta, n);
+                                                               x, snapshot, delta, n); ::b200::count_launch();
     B200_CUDA(cudaGetLastError());
     return B200_OK;
 }

@@ -629,7 +629,7 @@ static int launch_hogwild_s(const BprParams& p, cudaStream_t st, const HogwildTu
     const int64_t cap = (p.max_groups + groups_per_block * S - 1) / (groups_per_block * S);
     if (cap < grid) grid = cap;
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, threads, 0, st>>>(p);
+    kern<<<(unsigned)grid, threads, 0, st>>>(p); ::b200::count_launch();
     B200_CUDA(cudaGetLastError());
     return B200_OK;
 }
@@ -651,7 +651,7 @@ static int launch_hogwild_chunk(const BprParams& p, cudaStream_t st, const Hogwi
     const int64_t cap = (p.max_groups + groups_per_block - 1) / groups_per_block;     // staleness bound
     if (cap < grid) grid = cap;
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, threads, 0, st>>>(p);
+    kern<<<(unsigned)grid, threads, 0, st>>>(p); ::b200::count_launch();
     B200_CUDA(cudaGetLastError());
     return B200_OK;
 }
@@ -708,7 +708,7 @@ extern "C" int b200_bpr_prepare(const int32_t* indptr, const int32_t* indices, i
     if (grid > (int64_t)sm_count() * 32) grid = (int64_t)sm_count() * 32;
     if (grid < 1) grid = 1;
     bpr_prepare_kernel<<<(unsigned)grid, 256, 0, st>>>(indptr, indices, n_users, nnz, reinterpret_cast<int2*>(pairs),
-                                                       reinterpret_cast<unsigned long long*>(table), mask);
+                                                       reinterpret_cast<unsigned long long*>(table), mask); ::b200::count_launch();
     B200_CUDA(cudaGetLastError());
     return B200_OK;
 }
@@ -744,10 +744,10 @@ extern "C" int b200_bpr_epoch(const int32_t* pairs, const uint64_t* table, int64
     }
     p.neg_weighted = (flags & B200_BPR_NEG_WEIGHTED) ? 1 : 0;
     p.hinge = (flags & B200_BPR_LOSS_HINGE) ? 1 : 0;
-    if (p.hinge) p.use_bias = 1;
     p.debug_skip = 0;
     if (const char* e = getenv("B200_BPR_DEBUG_SKIP")) p.debug_skip = atoi(e);
     p.U = U; p.V = V; p.B = B; p.k = k; p.lr = lr; p.reg = reg; p.use_bias = use_bias;
+    if (p.hinge) p.use_bias = 1;          // MMMF always trains the item biases (recom_mmmf.pyx:149-152)
     p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32);
     p.epoch_lo = (uint32_t)epoch; p.epoch_hi = (uint32_t)(epoch >> 32);
     p.sample_base = sample_base;
@@ -784,6 +784,7 @@ extern "C" int b200_bpr_epoch_replay(const int64_t* i_index, const int32_t* j_id
     if (p.hinge) p.use_bias = 1;
     p.stats = reinterpret_cast<unsigned long long*>(stats);
     const char* serial = getenv("B200_REPLAY_SERIAL");
+    ::b200::count_launch();
     if (serial && serial[0] == '1') bpr_replay_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(p);
     else bpr_replay_window_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(p);
     B200_CUDA(cudaGetLastError());

@@ -29,6 +29,7 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
     } while (0)
 
 int sm_count();   // cached multiProcessorCount of the current device
+void count_launch(int n = 1);   // one tick per kernel this library launches (b200_kernel_launches)
 
 // ---------------------------------------------------------------------------
 // Philox4x32-10 counter-based RNG (Salmon et al., SC'11).  Stateless: the

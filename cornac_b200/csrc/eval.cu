@@ -116,7 +116,7 @@ extern "C" int b200_topk_metrics(const int32_t* ids, int64_t n_q, int topk, int6
     if (blocks > cap) blocks = cap;
     topk_metrics_kernel<<<(unsigned)blocks, EV_THREADS, smem, (cudaStream_t)stream>>>(
         ids, (long long)n_q, topk, (long long)ids_stride, (const long long*)user_idx,
-        (const long long*)pos_indptr, pos_indices, metric_kind, metric_k, n_metrics, out);
+        (const long long*)pos_indptr, pos_indices, metric_kind, metric_k, n_metrics, out); ::b200::count_launch();
     B200_CUDA(cudaGetLastError());
     return 0;
 }

@@ -239,7 +239,7 @@ static int launch_mf(const MfParams<IdT>& p, cudaStream_t st)
     const int64_t cap = (p.max_groups + groups_per_block * S - 1) / (groups_per_block * S);
     if (cap < grid) grid = cap;
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, threads, 0, st>>>(p);
+    kern<<<(unsigned)grid, threads, 0, st>>>(p); ::b200::count_launch();
     B200_CUDA(cudaGetLastError());
     return B200_OK;
 }
@@ -263,6 +263,7 @@ static int mf_epoch_impl(const IdT* rid, const IdT* cid, const float* val, int64
     if (n == 0) return B200_OK;
     if (ordered) {
         const char* serial = getenv("B200_REPLAY_SERIAL");
+        ::b200::count_launch();
         if (serial && serial[0] == '1') mf_replay_kernel<IdT><<<1, 32, 0, st>>>(p);
         else mf_replay_window_kernel<IdT><<<1, 1024, 0, st>>>(p);
         B200_CUDA(cudaGetLastError());

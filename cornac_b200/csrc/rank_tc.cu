@@ -1250,9 +1250,9 @@ static int pack_items(const float* V, int64_t n_items, int k, const float* item_
     B200_CUDA(cudaMemsetAsync(ws + L.off_scal, 0, 64, st));
     const int grid = sm_count() * 8;
     unsigned int* scal = reinterpret_cast<unsigned int*>(ws + L.off_scal);
-    norm_kernel<<<grid, 256, 0, st>>>(V, nullptr, n_items, k, nullptr, nullptr, scal + SC_VNORM, scal + SC_VABS, item_base, scal + SC_BMAX);
-    scale_items_kernel<<<1, 1, 0, st>>>(scal);
-    pack_kernel<TN, true><<<grid, 256, 0, st>>>(V, nullptr, n_items, n_pad, k, L.kp, item_base, scal, nullptr, ws + L.off_vpack);
+    norm_kernel<<<grid, 256, 0, st>>>(V, nullptr, n_items, k, nullptr, nullptr, scal + SC_VNORM, scal + SC_VABS, item_base, scal + SC_BMAX); ::b200::count_launch();
+    scale_items_kernel<<<1, 1, 0, st>>>(scal); ::b200::count_launch();
+    pack_kernel<TN, true><<<grid, 256, 0, st>>>(V, nullptr, n_items, n_pad, k, L.kp, item_base, scal, nullptr, ws + L.off_vpack); ::b200::count_launch();
     B200_CUDA(cudaGetLastError());
     return B200_OK;
 }
@@ -1265,8 +1265,8 @@ static int pack_users(const float* Usrc, const int64_t* uidx, int64_t rows, int6
     unsigned int* scal = reinterpret_cast<unsigned int*>(ws + L.off_scal);
     float* uabs = reinterpret_cast<float*>(ws + L.off_uabs);
     norm_kernel<<<grid, 256, 0, st>>>(Usrc, uidx, rows, k, reinterpret_cast<float*>(ws + L.off_unorm), uabs, nullptr, nullptr,
-                                      nullptr, nullptr);
-    pack_kernel<TM, false><<<grid, 256, 0, st>>>(Usrc, uidx, rows, n_ut * TM, k, L.kp, nullptr, scal, uabs, ws + L.off_upack);
+                                      nullptr, nullptr); ::b200::count_launch();
+    pack_kernel<TM, false><<<grid, 256, 0, st>>>(Usrc, uidx, rows, n_ut * TM, k, L.kp, nullptr, scal, uabs, ws + L.off_upack); ::b200::count_launch();
     B200_CUDA(cudaGetLastError());
     return B200_OK;
 }
@@ -1307,6 +1307,7 @@ int rank_tc(const float* U, const int64_t* user_idx, int64_t n_q, const float* V
         p.dump = nullptr;
         { const char* d = getenv("B200_RANK_DEBUG"); p.debug = d ? atoi(d) : 0; }
         const int grid = (int)(n_ut < sm_count() ? n_ut : sm_count());
+        ::b200::count_launch();
         if (strips == 4) rank_tc_kernel<false, 4><<<grid, threads_for(4), smem, st>>>(p);
         else rank_tc_kernel<false, 2><<<grid, threads_for(2), smem, st>>>(p);
         B200_CUDA(cudaGetLastError());
@@ -1331,12 +1332,12 @@ int rank_tc(const float* U, const int64_t* user_idx, int64_t n_q, const float* V
             B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rank_tc_finish_warp_kernel, 32, wsmem));
             if (occ < 1) occ = 1;
             const int64_t cap = (int64_t)sm_count() * occ;
-            rank_tc_finish_warp_kernel<<<(int)(rows < cap ? rows : cap), 32, wsmem, st>>>(f);
+            rank_tc_finish_warp_kernel<<<(int)(rows < cap ? rows : cap), 32, wsmem, st>>>(f); ::b200::count_launch();
             B200_CUDA(cudaGetLastError());
             f.row_list = f.big_rows;
             const size_t fsmem = (size_t)128 * (k * 4 + 16);
             B200_CUDA(cudaFuncSetAttribute(rank_tc_finish_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-            rank_tc_finish_kernel<true><<<sm_count(), 128, fsmem, st>>>(f);
+            rank_tc_finish_kernel<true><<<sm_count(), 128, fsmem, st>>>(f); ::b200::count_launch();
         } else if (staged) {
             const size_t fsmem = (size_t)128 * (k * 4 + 16);
             B200_CUDA(cudaFuncSetAttribute(rank_tc_finish_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
@@ -1344,11 +1345,11 @@ int rank_tc(const float* U, const int64_t* user_idx, int64_t n_q, const float* V
             B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rank_tc_finish_kernel<true>, 128, fsmem));
             if (occ < 1) occ = 1;
             const int64_t cap = (int64_t)sm_count() * occ;
-            rank_tc_finish_kernel<true><<<(int)(rows < cap ? rows : cap), 128, fsmem, st>>>(f);
+            rank_tc_finish_kernel<true><<<(int)(rows < cap ? rows : cap), 128, fsmem, st>>>(f); ::b200::count_launch();
         } else {
             // latency-bound gathers: as many rows in flight per SM as the thread limit allows (16 x 128 threads)
             const int fgrid = (int)(rows < (int64_t)sm_count() * 16 ? rows : (int64_t)sm_count() * 16);
-            rank_tc_finish_kernel<false><<<fgrid, 128, 0, st>>>(f);
+            rank_tc_finish_kernel<false><<<fgrid, 128, 0, st>>>(f); ::b200::count_launch();
         }
         B200_CUDA(cudaGetLastError());
         // rows whose candidate list overflowed: exact path, one row at a time (rare; needs the count on the host)
@@ -1415,7 +1416,7 @@ extern "C" int b200_rank_tc_debug_scores(const float* U, int64_t n_q, const floa
     p.dump = out;
     p.debug = 0;
     const int grid = (int)(n_ut < sm_count() ? n_ut : sm_count());
-    rank_tc_kernel<true, 2><<<grid, threads_for(2), smem, st>>>(p);
+    rank_tc_kernel<true, 2><<<grid, threads_for(2), smem, st>>>(p); ::b200::count_launch();
     B200_CUDA(cudaGetLastError());
     return B200_OK;
 }

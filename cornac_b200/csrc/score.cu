@@ -280,7 +280,7 @@ extern "C" int b200_score_batch(const float* U, const int64_t* user_idx, int64_t
     const int64_t n_it = (n_items + SC_ITEMS - 1) / SC_ITEMS;
     const int64_t n_qt = (n_q + SC_Q - 1) / SC_Q;
     dim3 grid((unsigned)n_it, (unsigned)(n_qt < 65535 ? n_qt : 65535));
-    score_batch_kernel<<<grid, SC_THREADS, 0, (cudaStream_t)stream>>>(U, user_idx, n_q, V, n_items, k, item_base, user_off, out);
+    score_batch_kernel<<<grid, SC_THREADS, 0, (cudaStream_t)stream>>>(U, user_idx, n_q, V, n_items, k, item_base, user_off, out); ::b200::count_launch();
     B200_CUDA(cudaGetLastError());
     return B200_OK;
 }
@@ -301,7 +301,7 @@ extern "C" int b200_topk_rows(const float* scores, int64_t n_q, int64_t n_items,
     int64_t grid = (int64_t)sm_count() * 2;
     if (n_q < grid) grid = n_q;
     topk_rows_kernel<<<(unsigned)grid, TK_THREADS, smem, (cudaStream_t)stream>>>(
-        scores, n_q, n_items, excl_indptr, excl_indptr ? excl_indices : nullptr, topk, sort_n, out_ids, out_scores);
+        scores, n_q, n_items, excl_indptr, excl_indptr ? excl_indices : nullptr, topk, sort_n, out_ids, out_scores); ::b200::count_launch();
     B200_CUDA(cudaGetLastError());
     return B200_OK;
 }

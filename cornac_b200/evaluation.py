@@ -51,7 +51,7 @@ def ranking_eval(model, metrics, train_set, test_set, val_set=None, rating_thres
     if len(metrics) == 0:
         return [], []
     supported = (hasattr(model, "rank_batch_device") and exclude_unknowns
-                 and all(isinstance(m, _TOPK_ONLY) and m.k > 0 for m in metrics))
+                 and all(isinstance(m, _TOPK_ONLY) and 0 < m.k <= 4096 for m in metrics))      # b200_topk_rows: topk <= 4096
     if not supported:
         return _reference_ranking_eval(model, metrics, train_set, test_set, val_set=val_set,
                                        rating_threshold=rating_threshold, exclude_unknowns=exclude_unknowns,
@@ -80,7 +80,7 @@ def ranking_eval(model, metrics, train_set, test_set, val_set=None, rating_thres
     per_metric = np.empty((len(metrics), len(users)), dtype=np.float64)
     for b0 in range(0, len(users), batch_users):
         ub = users[b0:b0 + batch_users]
-        ids, _ = model.rank_batch_device(ub, max_k, exclude=excl)       # [n, max_k] int32 CUDA, -1 padded
+        ids, _ = model.rank_batch_device(ub, max_k, exclude=excl, n_items=n_items)    # [n, max_k] int32 CUDA, -1 padded
         vals = engine.topk_metrics(ids, pos_ptr, pos_idx, kinds, ks, user_idx=engine.to_device(ub, torch.int64))
         per_metric[:, b0:b0 + len(ub)] = vals.cpu().numpy()
     user_results = [dict(zip(users.tolist(), vals.tolist())) for vals in per_metric]

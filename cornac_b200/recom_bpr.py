@@ -26,11 +26,40 @@ from ._scoring import DeviceScoringMixin
 
 DTYPE = np.float32
 
+# interactions above which a seeded ("auto" -> replay) fit prints a one-time hint: the serial-equivalent replay
+# reproduces the seeded reference but runs at ~1e7 samples/s, like one CPU thread; mode="hogwild" keeps the seed
+# for initialisation and the sampler key and trains at ~1e9 samples/s
+_REPLAY_HINT_NNZ = 5_000_000
+_replay_hint_given = False
+
+
+def check_factor_width(k):
+    """The Hogwild kernels keep a factor row in registers, 4 floats (k % 4 == 0) or 1 float per lane and slot, at most
+    8 slots of 32 lanes: k <= 1024 when k % 4 == 0, else k <= 256 (b200_bpr_epoch / b200_mf_epoch)."""
+    k = int(k)
+    if k < 1 or k > 1024 or (k % 4 != 0 and k > 256):
+        raise ValueError("k=%d is not supported: the B200 kernels take 1 <= k <= 1024 with k %% 4 == 0, or k <= 256 otherwise "
+                         "(pad k to a multiple of 4)" % k)
+    return k
+
+
+def replay_hint(nnz, name):
+    global _replay_hint_given
+    if nnz > _REPLAY_HINT_NNZ and not _replay_hint_given:
+        _replay_hint_given = True
+        import warnings
+        warnings.warn("%s: seed given -> deterministic replay mode (reference-identical, serial-equivalent, ~1e7 samples/s); "
+                      "%d interactions per epoch will take a while.  Pass mode='hogwild' to train on the whole GPU "
+                      "(the seed then fixes the initialisation and the sampler key only)." % (name, nnz), stacklevel=3)
+
 
 class BPR(DeviceScoringMixin, Recommender, ANNMixin):
-    _b200_hinge = False          # MMMF switches the loop body to the hinge variant
-
     """Bayesian Personalized Ranking trained and served on a B200.
+
+    NOTE on `seed`: like the reference (which drops to ONE thread when a seed is given, recom_bpr.pyx:132-133), a seeded
+    model trains in the deterministic replay mode -- reference-identical but serial-equivalent (~1e7 samples/s).  For
+    large data pass mode="hogwild": the seed still fixes the initial factors and the sampler key, and the epoch runs on
+    the whole GPU (~1e9 samples/s).
 
     Parameters are those of cornac.models.BPR (k, max_iter, learning_rate, lambda_reg,
     use_bias, num_threads, trainable, verbose, init_params, seed) plus `mode` and
@@ -38,12 +67,13 @@ class BPR(DeviceScoringMixin, Recommender, ANNMixin):
     B200; False = the reference's racy plain stores) in Hogwild mode.
     `num_threads` is accepted for API compatibility and ignored (the GPU is the pool).
     """
+    _b200_hinge = False          # MMMF switches the loop body to the hinge variant
 
     def __init__(self, name="BPR", k=10, max_iter=100, learning_rate=0.001, lambda_reg=0.01, use_bias=True,
                  num_threads=0, trainable=True, verbose=False, init_params=None, seed=None, mode="auto",
                  atomic_updates=True):
         super().__init__(name=name, trainable=trainable, verbose=verbose)
-        self.k = int(k)
+        self.k = check_factor_width(k)
         self.max_iter = max_iter
         self.learning_rate = learning_rate
         self.lambda_reg = lambda_reg
@@ -83,6 +113,8 @@ class BPR(DeviceScoringMixin, Recommender, ANNMixin):
         if X.nnz == 0 or self.max_iter <= 0:
             return self
         replay = (self.seed is not None) if self.mode == "auto" else (self.mode == "replay")
+        if replay and self.mode == "auto":
+            replay_hint(X.nnz, self.name)
         # the two RNGVector seeds are always drawn, in this order (recom_bpr.pyx:190-191)
         s_pos = self.rng.randint(2 ** 31)
         s_neg = self.rng.randint(2 ** 31)

@@ -20,7 +20,7 @@ from cornac.utils.init_utils import normal, zeros
 
 from . import engine
 from ._scoring import DeviceScoringMixin
-from .recom_bpr import _copy_back
+from .recom_bpr import _copy_back, check_factor_width, replay_hint
 
 DTYPE = np.float32
 
@@ -30,7 +30,7 @@ class MF(DeviceScoringMixin, Recommender, ANNMixin):
                  batch_size=256, lambda_reg=0.02, dropout=0.0, use_bias=True, early_stop=False, num_threads=0,
                  trainable=True, verbose=False, init_params=None, seed=None, mode="auto", atomic_updates=True):
         super().__init__(name=name, trainable=trainable, verbose=verbose)
-        self.k = k
+        self.k = check_factor_width(k)
         self.backend = backend
         self.optimizer = optimizer
         self.max_iter = max_iter
@@ -90,6 +90,8 @@ class MF(DeviceScoringMixin, Recommender, ANNMixin):
         Bi = engine.to_device(np.ascontiguousarray(self.i_biases, dtype=DTYPE))
         loss_dev = torch.zeros(1, dtype=torch.float32, device="cuda")
         ordered = (self.seed is not None) if self.mode == "auto" else (self.mode == "replay")
+        if ordered and self.mode == "auto":
+            replay_hint(n, self.name)
         lr, reg = float(np.float32(self.learning_rate)), float(np.float32(self.lambda_reg))
         loss = np.float32(0)
         self.loss_history = []

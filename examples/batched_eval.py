@@ -16,7 +16,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "examples"))
-ref = os.path.join(ROOT, "oracle", "_ref")
+ref = os.path.join(ROOT, "baseline", "_ref")
 if os.path.isdir(os.path.join(ref, "cornac")):
     sys.path.insert(0, ref)
 

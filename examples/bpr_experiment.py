@@ -13,7 +13,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-ref = os.path.join(ROOT, "oracle", "_ref")
+ref = os.path.join(ROOT, "baseline", "_ref")
 if os.path.isdir(os.path.join(ref, "cornac")):
     sys.path.insert(0, ref)
 

@@ -48,6 +48,9 @@ extern "C" {
 
 B200_API const char* b200_last_error(void);
 B200_API int b200_abi_version(void);
+/* Number of CUDA kernels this library has launched in the calling process so far (all entry points, all
+ * streams): what bench.py reports as `gpu_launches` around its timed region. */
+B200_API int64_t b200_kernel_launches(void);
 /* multiProcessorCount / compute capability of the current device (host call). */
 B200_API int b200_device_info(int* sm_count, int* cc_major, int* cc_minor);
 

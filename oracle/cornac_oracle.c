@@ -8,10 +8,9 @@
  * Parity status: PINNED.  The reference's own tests hold no golden vectors for
  * trained BPR/MF parameters, so this restatement is pinned
  *   (1) against tests/cornac/utils/test_fastdot.py:26-37 (known answers), and
- *   (2) against outputs of the UNMODIFIED compiled reference (oracle/_ref,
- *       built by oracle/build_ref.sh) committed as .npz fixtures under tests/golden/ by
- *       tests/golden/make_golden.py, and re-checked live whenever oracle/_ref
- *       is importable (tests/test_oracle_vs_reference.py).
+ *   (2) against outputs of the UNMODIFIED compiled reference (baseline/_ref,
+ *       built by baseline/build_ref.sh) committed as .npz fixtures under tests/golden/ by
+ *       tests/golden/make_golden.py and checked by tests/test_oracle_golden.py.
  *
  * Every function cites the reference file:line it follows (paths relative to
  * the reference root).  Arithmetic is written out in scalar f32 with
@@ -265,7 +264,7 @@ ORA_API void ora_bpr_replay(const int64_t *i_index, const int32_t *j_ids, int64_
 
 /* Multi-threaded Hogwild port of the same epoch (`prange(schedule='guided')`
  * with one mt19937 pair per thread, recom_bpr.pyx:54-62,231-234).  Only used
- * as the "port" CPU baseline when oracle/_ref is unavailable; racy by design. */
+ * as the "port" CPU baseline when baseline/_ref is unavailable; racy by design. */
 ORA_API void ora_bpr_fit_sgd_omp(const uint32_t *seeds_pos, const uint32_t *seeds_neg, int n_threads,
                                  int64_t nnz, int64_t n_neg,
                                  const int32_t *user_ids, const int32_t *item_ids,

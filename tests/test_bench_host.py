@@ -72,9 +72,38 @@ def test_reference_arm_prints_one_json_line_without_a_gpu():
         import pytest
         pytest.skip("covered by the GPU run of the reference arm")
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
-                        "--scale", "0.002"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+                        "--workload", "c2", "--scale", "0.02"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
     assert p.returncode == 0, p.stderr[-2000:]
-    line = [l for l in p.stdout.splitlines() if l.startswith("{")][-1]
-    d = json.loads(line)
+    lines = p.stdout.splitlines()
+    assert len(lines) == 1, lines                          # stdout carries the JSON record and nothing else
+    d = json.loads(lines[0])
+    assert d["scaling"] == "strong" and d["cpu_baseline"]["host"]["threads_used"] == d["cpu_baseline"]["cores"] >= 1
     assert d["impl"] == "reference" and d["value"] > 0 and d["unit"] == "updates/s" and d["cpu_baseline"]["kind"] in ("reference", "port")
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_model_blocks_are_the_same_for_every_world_size():
+    """Strong scaling shards ONE model: the union of the ranks' blocks is the same matrix for N = 1, 2, 4, 8, every rank owns
+    the same number of interactions, and all blocks share one item-popularity law."""
+    W = dict(bench.WORKLOADS["c2"])
+    W["n_users"], W["nnz"] = 8000, 160000
+    cpu = torch.device("cpu")
+    whole_ptr, whole_idx = bench.synth_shard(W, bench.rank_blocks(0, 1), cpu)
+    assert whole_ptr.numel() == W["n_users"] + 1 and whole_idx.numel() == W["nnz"] and int(whole_ptr[-1]) == W["nnz"]
+    for world in (2, 4, 8):
+        parts = [bench.synth_shard(W, bench.rank_blocks(r, world), cpu) for r in range(world)]
+        assert all(p[1].numel() == W["nnz"] // world for p in parts)
+        assert torch.equal(torch.cat([p[1] for p in parts]), whole_idx)
+        deg = torch.cat([p[0][1:] - p[0][:-1] for p in parts])
+        assert torch.equal(deg, whole_ptr[1:] - whole_ptr[:-1])
+    # one popularity law: the most popular items of two different blocks largely coincide
+    a = torch.bincount(bench.synth_shard(W, [0], cpu)[1].long(), minlength=W["n_items"]).topk(50).indices
+    b = torch.bincount(bench.synth_shard(W, [5], cpu)[1].long(), minlength=W["n_items"]).topk(50).indices
+    assert len(set(a.tolist()) & set(b.tolist())) >= 35
+
+
+def test_host_cores_reports_what_the_process_owns():
+    h = bench.host_cores()
+    assert 1 <= h["threads_used"] <= h["sched_affinity"] <= (h["os_cpu_count"] or 10 ** 6)
+    if h["cgroup_cpu_quota"] is not None:
+        assert h["threads_used"] <= max(1, int(h["cgroup_cpu_quota"] + 0.5))

@@ -24,7 +24,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), "include/b200cornac.h declares %s but the library does not export it" % name
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert L.b200_abi_version() == 1
+    assert L.b200_abi_version() == 2 and L.b200_kernel_launches() >= 0
 
 
 def test_sampler_matches_oracle_streams():
@@ -68,7 +68,8 @@ def test_device_draw_law_is_uniform_and_in_range():
 
 
 def test_product_never_touches_the_oracle():
-    pat = re.compile(r"oracle", re.I)
+    # neither the oracle nor the reference install may be named on the product path (imports, paths, dlopen)
+    pat = re.compile(r"oracle|baseline[/\\.]|_ref\b", re.I)
     for base, _, files in os.walk(os.path.join(ROOT, "cornac_b200")):
         if os.path.basename(base) in ("build", "lib", "__pycache__"):
             continue

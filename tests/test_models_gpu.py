@@ -1,5 +1,5 @@
 """The drop-in plug-ins through the reference's own Python stack (unchanged cornac from
-oracle/_ref): fit / score / rank / ranking_eval / Experiment / clone / save-load.  GPU only.
+baseline/_ref): fit / score / rank / ranking_eval / Experiment / clone / save-load.  GPU only.
 Mirrors the reference's smoke tests (tests/cornac/models/test_recommender.py:28-53,
 tests/cornac/eval_methods/test_ratio_split.py:92-109, tests/cornac/test_hyperopt.py:39-55)
 and adds the value checks the reference lacks."""
@@ -298,3 +298,25 @@ def test_mmmf_plugin_reproduces_seeded_reference_and_trains_hogwild():
     assert m.clone().name == "MMMF" and "use_bias" not in m._get_init_params()
     h = MMMF(k=16, max_iter=10, learning_rate=0.02, lambda_reg=0.01).fit(ds)           # Hogwild
     assert np.isfinite(h.u_factors).all() and np.abs(h.i_biases).max() > 1e-3
+
+
+def test_recommend_batch_on_the_gpu_equals_per_user_recommend():
+    """`recommend_batch` (one fused b200_rank_topk call for the batch) returns, user by user, the first k
+    items of the per-user `Recommender.recommend` (recommender.py:532-580) -- with and without seen-item removal, for
+    BPR (scores over total_items) and MF (user offsets, scores over num_items), in original ids."""
+    from cornac_b200 import BPR, MF
+    _, train_set, _, _, _ = _split_sets()
+    users = list(train_set.user_ids)[:60] + list(train_set.user_ids)[-17:]
+    for mdl in (BPR(k=16, max_iter=15, learning_rate=0.05), MF(k=16, max_iter=10)):
+        mdl.fit(train_set)
+        for remove_seen in (False, True):
+            for k in (1, 10, 50):
+                got = mdl.recommend_batch(users, k=k, remove_seen=remove_seen, train_set=train_set)
+                assert len(got) == len(users)
+                for uid, lst in zip(users, got):
+                    want = mdl.recommend(uid, k=k, remove_seen=remove_seen, train_set=train_set)
+                    assert lst == list(want), (mdl.name, uid, k, remove_seen, lst[:5], list(want)[:5])
+        # full rankings and unknown users leave the batched path but still answer like recommend()
+        assert mdl.recommend_batch(users[:3], k=-1) == [list(mdl.recommend(u, k=-1)) for u in users[:3]]
+        with pytest.raises(ValueError):
+            mdl.recommend_batch(["no-such-user"], k=5)

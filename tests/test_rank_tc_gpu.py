@@ -170,3 +170,43 @@ def test_tensor_path_and_exact_path_agree(monkeypatch):
     monkeypatch.setenv("B200_RANK_TC", "0")
     b = _rank_topk(U, V, base, None, None, None, 100)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+@pytest.mark.parametrize("k,n_items,n_q,topk", [(129, 3000, 70, 50), (144, 2500, 40, 20), (64, 3000, 50, 257),
+                                                (64, 3000, 33, 300), (64, 1023, 20, 10), (4, 2000, 10, 5)])
+def test_limits_of_the_fused_kernel_take_the_exact_path(k, n_items, n_q, topk):
+    """outside k <= 128 / topk <= 256 / n_items >= 1024 / k >= 8 the tensor-core pass is not used (rank_tc_supported):
+    b200_rank_topk answers through the exact kernels and the results are the oracle's all the same"""
+    rng = np.random.RandomState(k * 7 + topk)
+    U = rng.normal(0, 0.3, (n_q, k)).astype(np.float32)
+    V = rng.normal(0, 0.3, (n_items, k)).astype(np.float32)
+    base = rng.normal(0, 0.3, n_items).astype(np.float32)
+    excl = [np.unique(rng.randint(n_items, size=rng.randint(0, 60))) for _ in range(n_q)]
+    ids, sc = _rank_topk(U, V, base, None, None, excl, topk)
+    want = O.score_batch(U, V, base)
+    for q in range(n_q):
+        wi, ws, w = O.topk(want[q], topk, excl[q])
+        assert np.array_equal(ids[q], wi) and np.array_equal(sc[q][:w], ws[:w])
+
+
+def test_packed_item_side_is_reused_across_calls_and_refreshed_when_the_factors_change():
+    """the fp16 item tiles and norms are cached in the workspace between calls on the same (V, base): a second call gives
+    the same answer, and a call after V changed IN PLACE (same pointer -- what a training epoch does) must not reuse it"""
+    import torch
+    from cornac_b200 import engine
+    rng = np.random.RandomState(4)
+    U = torch.from_numpy(rng.normal(0, 0.3, (200, 64)).astype(np.float32)).cuda()
+    Vh = rng.normal(0, 0.3, (5000, 64)).astype(np.float32)
+    V = torch.from_numpy(Vh.copy()).cuda()
+    B = torch.from_numpy(rng.normal(0, 0.3, 5000).astype(np.float32)).cuda()
+    nb = int(engine.require_cuda().b200_rank_topk_workspace_bytes(200, 5000, 64, 20))
+    ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    a = engine.rank_topk(U, V, 20, item_base=B, workspace=ws)
+    b = engine.rank_topk(U, V, 20, item_base=B, workspace=ws)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    V.copy_(torch.from_numpy(Vh[::-1].copy()).cuda())              # same storage, new content
+    c = engine.rank_topk(U, V, 20, item_base=B, workspace=ws)
+    want = O.score_batch(U.cpu().numpy(), Vh[::-1].copy(), B.cpu().numpy())
+    for q in range(0, 200, 13):
+        wi, wsc, _ = O.topk(want[q], 20)
+        assert np.array_equal(c[0][q].cpu().numpy(), wi) and np.array_equal(c[1][q].cpu().numpy(), wsc)
