@@ -8,7 +8,7 @@ Layers:  include/b200cornac.h (C ABI)  <-  cornac_b200/csrc (CUDA)  <-  cornac_b
 plug-ins).  The plug-in classes need the `cornac` package importable (they subclass its
 Recommender so that cornac.Experiment accepts them); the engine does not.
 """
-__all__ = ["BPR", "WBPR", "MMMF", "MF", "BaselineOnly", "engine", "B200Error"]
+__all__ = ["BPR", "WBPR", "MMMF", "MF", "WMF", "BaselineOnly", "engine", "B200Error"]
 
 from ._lib import B200Error  # noqa: F401
 
@@ -26,6 +26,9 @@ def __getattr__(name):
     if name == "MF":
         from .recom_mf import MF
         return MF
+    if name == "WMF":
+        from .recom_wmf import WMF
+        return WMF
     if name == "BaselineOnly":
         from .recom_bo import BaselineOnly
         return BaselineOnly

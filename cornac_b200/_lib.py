@@ -38,13 +38,20 @@ SIGNATURES = {
     "b200_mt_sampler_fill_i32": (_int, [_vp, _i64, _i64, _vp]),
     "b200_mf_epoch": (_int, [_vp, _vp, _vp, _i64, _int, _i64, _i64, _vp, _vp, _vp, _vp, _int, _f32, _f32, _f32, _int, _int,
                              _c.c_uint, _vp, _vp]),
+    "b200_wmf_step": (_int, [_vp, _vp, _vp, _vp, _int, _i64, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp,
+                             _f32, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp]),
     "b200_score_batch": (_int, [_vp, _vp, _i64, _vp, _i64, _int, _vp, _vp, _vp, _vp]),
     "b200_topk_rows": (_int, [_vp, _i64, _i64, _vp, _vp, _int, _vp, _vp, _vp]),
     "b200_rank_topk_workspace_bytes": (_i64, [_i64, _i64, _int, _int]),
     "b200_rank_topk": (_int, [_vp, _vp, _i64, _vp, _i64, _int, _vp, _vp, _vp, _vp, _int, _vp, _vp,
                               _vp, _i64, _vp]),
+    "b200_rank_items_bytes": (_i64, [_i64, _int]),
+    "b200_rank_pack_items": (_int, [_vp, _i64, _int, _vp, _vp, _i64, _vp]),
+    "b200_rank_topk_packed": (_int, [_vp, _vp, _i64, _vp, _i64, _int, _vp, _vp, _vp, _vp, _int, _vp, _vp,
+                                     _vp, _vp, _i64, _vp]),
     "b200_rank_tc_debug_scores": (_int, [_vp, _i64, _vp, _i64, _int, _vp, _vp, _i64, _vp, _i64, _vp]),
     "b200_topk_metrics": (_int, [_vp, _i64, _int, _i64, _vp, _vp, _vp, _vp, _vp, _int, _vp, _vp]),
+    "b200_rank_counts": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200_delta_make": (_int, [_vp, _vp, _vp, _i64, _vp]),
     "b200_delta_apply": (_int, [_vp, _vp, _vp, _i64, _vp]),
 }

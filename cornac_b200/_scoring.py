@@ -46,6 +46,17 @@ class DeviceScoringMixin:
         """Keep the freshly trained device tensors as the scoring cache (no re-upload)."""
         self._b200_dev = dict(U=U, V=V, item_base=item_base, user_off=user_off, n_items=int(n_items))
 
+    def _b200_packed_items(self, n_rank):
+        """fp16 tile images of the item side for the fused rank, built once per (trained model, candidate count) and kept
+        with the device cache: V and the item base are constant until the next fit() / parameter change, which drops
+        the whole cache (_b200_invalidate)."""
+        d = self._b200_device()
+        cache = d.setdefault("packed", {})
+        if n_rank not in cache:
+            cache.clear()                                   # one candidate count at a time (288 MB at 1 M items)
+            cache[n_rank] = engine.rank_pack_items(d["V"], d["item_base"], n_rank)
+        return cache[n_rank]
+
     # ---- scores --------------------------------------------------------------------
     @staticmethod
     def _b200_check_users(user_indices, n_rows):
@@ -79,9 +90,9 @@ class DeviceScoringMixin:
         d = self._b200_device()
         user_indices = self._b200_check_users(user_indices, d["U"].shape[0])
         ex_ptr, ex_idx = self._b200_exclusion_rows(user_indices, exclude)
-        if d["user_off"] is None:
-            return engine.rank_topk_host(d["U"], d["V"][: d["n_items"]], int(k), user_indices, item_base=d["item_base"],
-                                         excl_indptr=ex_ptr, excl_indices=ex_idx)
+        if d["user_off"] is None and d["n_items"] == d["V"].shape[0]:
+            return engine.rank_topk_host(d["U"], d["V"], int(k), user_indices, item_base=d["item_base"],
+                                         excl_indptr=ex_ptr, excl_indices=ex_idx, packed_items=self._b200_packed_items(d["n_items"]))
         ids, sc = self.rank_batch_device(user_indices, k, exclude=exclude, _rows=(ex_ptr, ex_idx))
         return ids.cpu().numpy(), sc.cpu().numpy()
 
@@ -110,7 +121,7 @@ class DeviceScoringMixin:
                                           torch.zeros(1, dtype=torch.int32, device="cuda"))
         n_rank = d["n_items"] if n_items is None else min(int(n_items), d["n_items"])
         return engine.rank_topk(d["U"], d["V"], int(k), user_idx=uidx, item_base=d["item_base"], user_off=uoff,
-                                excl_indptr=ep, excl_indices=ei, n_items=n_rank)
+                                excl_indptr=ep, excl_indices=ei, n_items=n_rank, packed_items=self._b200_packed_items(n_rank))
 
     # ---- batched Recommender.recommend ---------------------------------------------
     def recommend_batch(self, batch_users, k=-1, remove_seen=False, train_set=None):

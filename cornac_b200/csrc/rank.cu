@@ -14,7 +14,11 @@ int rank_tc_supported(int64_t n_q, int64_t n_items, int k, int topk);
 int64_t rank_tc_workspace_bytes(int64_t n_q, int64_t n_items, int k, int topk);
 int rank_tc(const float* U, const int64_t* user_idx, int64_t n_q, const float* V, int64_t n_items, int k,
             const float* item_base, const float* user_off, const int64_t* excl_indptr, const int32_t* excl_indices,
-            int topk, int32_t* out_ids, float* out_scores, void* workspace, int64_t workspace_bytes, cudaStream_t st);
+            int topk, int32_t* out_ids, float* out_scores, void* workspace, int64_t workspace_bytes, const void* packed_items,
+            cudaStream_t st);
+int64_t rank_tc_items_bytes(int64_t n_items, int k);
+int rank_tc_pack_items(const float* V, int64_t n_items, int k, const float* item_base, void* packed, int64_t packed_bytes,
+                       cudaStream_t st);
 }  // namespace b200
 
 using namespace b200;
@@ -35,12 +39,38 @@ extern "C" int64_t b200_rank_topk_workspace_bytes(int64_t n_q, int64_t n_items, 
     return exact_chunk_queries(n_q, n_items) * n_items * (int64_t)sizeof(float);
 }
 
+extern "C" int64_t b200_rank_items_bytes(int64_t n_items, int k)
+{
+    if (n_items <= 0 || !rank_tc_supported(1, n_items, k, 1)) return 0;       // shapes the tensor-core pass does not take
+    return rank_tc_items_bytes(n_items, k);
+}
+
+extern "C" int b200_rank_pack_items(const float* V, int64_t n_items, int k, const float* item_base,
+                                    void* packed, int64_t packed_bytes, void* stream)
+{
+    B200_REQUIRE(V && n_items >= 1 && k >= 1, "b200_rank_pack_items: bad argument");
+    B200_REQUIRE(b200_rank_items_bytes(n_items, k) > 0, "b200_rank_pack_items: shape not taken by the tensor-core pass (k=%d, n_items=%lld)",
+                 k, (long long)n_items);
+    return rank_tc_pack_items(V, n_items, k, item_base, packed, packed_bytes, (cudaStream_t)stream);
+}
+
 extern "C" int b200_rank_topk(const float* U, const int64_t* user_idx, int64_t n_q,
                               const float* V, int64_t n_items, int k,
                               const float* item_base, const float* user_off,
                               const int64_t* excl_indptr, const int32_t* excl_indices,
                               int topk, int32_t* out_ids, float* out_scores,
                               void* workspace, int64_t workspace_bytes, void* stream)
+{
+    return b200_rank_topk_packed(U, user_idx, n_q, V, n_items, k, item_base, user_off, excl_indptr, excl_indices, topk,
+                                 out_ids, out_scores, nullptr, workspace, workspace_bytes, stream);
+}
+
+extern "C" int b200_rank_topk_packed(const float* U, const int64_t* user_idx, int64_t n_q,
+                                     const float* V, int64_t n_items, int k,
+                                     const float* item_base, const float* user_off,
+                                     const int64_t* excl_indptr, const int32_t* excl_indices,
+                                     int topk, int32_t* out_ids, float* out_scores,
+                                     const void* packed_items, void* workspace, int64_t workspace_bytes, void* stream)
 {
     B200_REQUIRE(U && V && out_ids && out_scores, "b200_rank_topk: null pointer argument");
     B200_REQUIRE(n_q >= 0 && n_items >= 1 && k >= 1 && topk >= 1, "b200_rank_topk: bad sizes");
@@ -51,7 +81,7 @@ extern "C" int b200_rank_topk(const float* U, const int64_t* user_idx, int64_t n
     cudaStream_t st = (cudaStream_t)stream;
     if (rank_tc_supported(n_q, n_items, k, topk))
         return rank_tc(U, user_idx, n_q, V, n_items, k, item_base, user_off, excl_indptr, excl_indices, topk, out_ids,
-                       out_scores, workspace, workspace_bytes, st);
+                       out_scores, workspace, workspace_bytes, packed_items, st);
     const int64_t chunk = exact_chunk_queries(n_q, n_items);
     float* slab = static_cast<float*>(workspace);
     for (int64_t q0 = 0; q0 < n_q; q0 += chunk) {

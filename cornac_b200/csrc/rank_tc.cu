@@ -48,6 +48,7 @@ __host__ __device__ constexpr int threads_for(int st) { return 128 + 128 * st; }
 __host__ __device__ constexpr int cap_for(int st) { return 2048 / st; }
 constexpr int KX = 16;             // extra K slice carrying the item base: U gets (cA, cA, 1, 0...), V gets (hi, lo, pad ? -inf : 0, 0...)
 constexpr int CAP = 1024;          // candidate-list capacity of a strip list at ST = 2 (cap_for(ST) in general)
+constexpr int NB = 32;             // score bins of a threshold raise (one pass over the list, counters in shared memory)
 constexpr int MAX_TOPK = 256;
 constexpr int MAX_KP = 128 + KX;
 constexpr uint32_t TMEM_COLS = 512;
@@ -156,6 +157,72 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32])
                  :: "memory");
 }
 
+// ---- CTA-pair (cta_group::2) forms: two CTAs of a cluster, one per SM of a TPC, run ONE MMA of M = 256 together: each
+// supplies its own 128 rows of A and HALF of the B tile from its own shared memory, each receives its 128 rows of D in
+// its own TMEM.  The instruction, the commits and the TMEM allocation name the pair explicitly.
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local_smem_addr` in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr)
+{
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// wait on a barrier that threads of the PEER CTA arrive on (cluster-scope acquire), with back-off
+__device__ __forceinline__ void mbar_wait_cluster_backoff(uint64_t* bar, uint32_t parity)
+{
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok;
+    for (;;) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (ok) break;
+        __nanosleep(20);
+    }
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive (once the MMAs issued so far have retired) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((unsigned short)3) : "memory");
+}
+
 // UMMA shared-memory descriptor, K-major, SWIZZLE_NONE ("interleaved" core matrices):
 // a core matrix is 8 rows x 16 bytes stored as 128 contiguous bytes; LBO = byte distance between
 // the two K-halves (16-byte chunks) of one K=16 instruction, SBO = byte distance between 8-row
@@ -177,10 +244,11 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N)
 
 // V-tile ring depth that fits next to the U tile in 200 KB of shared memory (2..4); the rest holds barriers,
 // thresholds and the pair-exchange area
-__host__ __device__ __forceinline__ int num_stages(int kp, int st)
+// (a CTA of a pair stages only its half of every V tile: TN / cg items)
+__host__ __device__ __forceinline__ int num_stages(int kp, int st, int cg)
 {
-    const int budget = (st == 4 ? 184 : 200) * 1024 - TM * kp * 2;
-    int ns = budget / (TN * kp * 2);
+    const int budget = (st == 4 ? 180 : 200) * 1024 - TM * kp * 2;
+    int ns = budget / ((TN / cg) * kp * 2);
     return ns > 4 ? 4 : (ns < 2 ? 2 : ns);
 }
 
@@ -375,46 +443,50 @@ struct RankTcParams {
     const int32_t* __restrict__ excl_indices;
     int64_t n_rows;                        // valid rows in this chunk
     int n_ut, n_it, kp, topk;
-    unsigned long long* __restrict__ lists;    // [n_ut * 8 warps][CAP][32] interleaved entries
+    float* __restrict__ lists;             // [n_ut * 4 ST warps][32 lanes] thread-private blocks: [cap scores f32][cap item ids i32]
     int* __restrict__ row_cnt;             // [n_ut * TM][MAX_ST strips]
     int* __restrict__ row_flag;            // [n_ut * TM][MAX_ST] 1 = list overflow -> exact path
+    float* __restrict__ row_tau;           // [n_ut * TM][MAX_ST] final filter tau - 2 eps of the strip (scaled units): the finish drops entries below the row's largest
     float* __restrict__ dump;              // debug: dense approximate scores [n_ut*TM][n_it*TN] or null
     int debug;                             // B200_RANK_DEBUG: timing only: 1 = epilogue hands the accumulators straight back, 2 = tcgen05.ld only;
                                            // 4 = raise schedule with ratio 1.41 instead of 2 (results stay exact)
 };
 
-__device__ __forceinline__ float ent_score(unsigned long long e) { return __uint_as_float((unsigned)(e >> 32)); }
-
-// Per-thread epilogue state: one thread owns one (user row, column half) and its candidate list.
-// Items reach a list in increasing id order and compaction keeps that order, so lists stay sorted by
-// id; the user's exclusion list (sorted too) is merged against the NEW tail of the list whenever the
-// threshold is raised, and once more in the finish kernel -- the hot loop never branches on it.
+// Per-thread epilogue state: one thread owns one (user row, column strip) and its candidate list -- a private,
+// contiguous block of global memory: cap scores (f32, scaled units) followed by cap item ids.  Items reach a list in
+// increasing id order and every in-place compaction keeps that order; the user's exclusion list (sorted too) is merged
+// against the NEW tail of the list whenever the threshold is raised, and once more in the finish kernel -- the hot loop
+// never branches on it.  Entries that fall below a later threshold are NOT removed eagerly: the finish kernel drops
+// everything below the row's final filter, and a list is compacted in place only when more than half of it is dead.
 struct RowState {
-    unsigned long long* list;      // interleaved: entry e of this thread at list[e * 32]
+    float* lsc;                    // scores [cap]; ids at (int32_t*)(lsc + cap)
     const int32_t* ex;
     int n_ex;
     int ex_c;                      // exclusion cursor: entries [0, ex_c) have been loaded into the window
     int32_t ex_w0, ex_w1, ex_w2, ex_w3;   // next excluded ids (sorted), 0x7fffffff = none
-    unsigned long long* wp;        // append position (hot loop); cnt is derived from it between stages
     int cnt;                       // entries in the list
     int checked;                   // entries [0, checked) are already exclusion-filtered
     float tau, tau_f;              // tau_f = tau - 2 eps is the filter applied to every score
-    float hi;                      // largest score seen at the last raise (bisection range)
+    float hi;                      // largest score seen at the last raise (bin range)
 };
 
-// sequential scan of a list with 16 independent loads in flight (the lists live in global memory / L2)
+// sequential scan of the scores of a list: eight 16-byte loads (32 scores) in flight per thread
 template <typename F>
-__device__ __forceinline__ void scan_list(const unsigned long long* list, int L, F f)
+__device__ __forceinline__ void scan_scores(const float* __restrict__ lsc, int L, F f)
 {
     int e = 0;
-    for (; e + 16 <= L; e += 16) {
-        unsigned long long v[16];
+    for (; e + 32 <= L; e += 32) {
+        float4 v[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = list[(size_t)(e + i) * 32];
+        for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const float4*>(lsc + e + 4 * i);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) f(v[i]);
+        for (int i = 0; i < 8; ++i) { f(v[i].x); f(v[i].y); f(v[i].z); f(v[i].w); }
     }
-    for (; e < L; ++e) f(list[(size_t)e * 32]);
+    for (; e + 4 <= L; e += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(lsc + e);
+        f(v.x); f(v.y); f(v.z); f(v.w);
+    }
+    for (; e < L; ++e) f(lsc[e]);
 }
 
 // named barrier of the ST epilogue warps that own the column strips of the same 32 user rows
@@ -425,28 +497,34 @@ __device__ __forceinline__ void pair_sync(int bar_id)
     asm volatile("bar.sync %0, %1;" :: "r"(bar_id), "n"(32 * ST) : "memory");
 }
 
-// Raise the threshold of a row: tau = (approximately) the K-th largest listed score, never above
-// it.  All 32 lanes run this together, each on its own list (the lanes' entries are interleaved in
-// memory, so the lock-step scans are coalesced).  Steps: (1) merge the new tail of the list against
-// the user's exclusion list and drop excluded items; (2) two rounds of 16-way bisection on the score
-// range for the largest t with #(score >= t) >= K; (3) drop entries below tau - 2 eps.
-// JOINT (the scheduled raises, which both column halves of a row reach at the same stage): the two
-// threads of a row add up their bin counts through shared memory, so the K-th best is taken over the
-// UNION of the row's two lists -- together they keep ~K candidates instead of ~K each.  The control flow
-// between the pair barriers is the same for every thread (rows that cannot be raised count nothing).
-// Solo (a list hit TRIGGER between two scheduled raises): the list's own K-th best, a valid lower bound.
-// `share` points at this row's exchange slots: slot s (strip s) at share[s * TM * 16]; `tau_row` likewise at
-// tau_row[s * TM].
+// lower edge of bin j of the range [a, a + NB * step): ONE expression, used both to bin a score and to turn the chosen
+// bin back into a threshold, so that "score in bin >= j" and "score >= bin_edge(j)" are the same predicate bit for bit
+__device__ __forceinline__ float bin_edge(float a, float step, int j) { return fmaf((float)j, step, a); }
+
+// Raise the threshold of a row: tau = (approximately) the K-th largest listed score, never above it.  All 32 lanes run
+// this together, each on its own list.  Steps: (1) merge the new tail of the list against the user's exclusion list and
+// drop excluded items (in place); (2) ONE pass over the scores: NB-bin histogram of [lo, hi] in this thread's private
+// shared-memory counters; the largest bin edge t with #(score >= t) >= K becomes tau; (3) only if more than half of the
+// list is now below the filter tau - 2 eps: order-preserving compaction.
+// JOINT (the scheduled raises, which all column strips of a row reach at the same stage): the ST threads of a row read
+// each other's counters, so the K-th best is taken over the UNION of the row's lists -- together they keep ~K
+// candidates instead of ~K each.  The control flow between the pair barriers is the same for every thread (rows that
+// cannot be raised count nothing).  Solo (a list hit TRIGGER between two scheduled raises): the list's own K-th best,
+// a valid lower bound; always compacts.
+// `share` points at this row's exchange slots: slot s (strip s) at share[s * TM * 4]; `hist` at this row's counters:
+// bin j of strip s at hist[(s * NB + j) * TM]; `tau_row` likewise at tau_row[s * TM].
 template <bool JOINT, int ST>
-__device__ __forceinline__ void raise_threshold(RowState& st, int K, float eps2, uint32_t tile, int strip,
-                                                unsigned long long* tau_row, int* share, int bar_id)
+__device__ __forceinline__ void raise_threshold(RowState& st, int K, float eps2, uint32_t tile, int strip, int cap,
+                                                unsigned long long* tau_row, int* share, unsigned short* hist, int bar_id)
 {
     unsigned long long* my_tau = tau_row + strip * TM;
-    int* pair_mine = share + strip * (TM * 16);
-    unsigned long long* __restrict__ list = st.list;
-    // The other column half of this row publishes its own lower bound of the row's k-th best score; any
-    // such bound (even an old one) is valid for the whole row, so take the larger of the two.  The tag
-    // rejects a value the sibling warp left behind from the previous user tile.
+    int* pair_mine = share + strip * (TM * 4);
+    unsigned short* hist_mine = hist + (size_t)strip * NB * TM;
+    float* __restrict__ lsc = st.lsc;
+    int32_t* __restrict__ lid = reinterpret_cast<int32_t*>(st.lsc + cap);
+    // The other column strips of this row publish their own lower bound of the row's k-th best score; any such bound
+    // (even an old one) is valid for the whole row, so take the largest.  The tag rejects a value the sibling warp left
+    // behind from the previous user tile.
 #pragma unroll
     for (int o = 0; o < ST; ++o) {
         if (o == strip) continue;
@@ -454,20 +532,20 @@ __device__ __forceinline__ void raise_threshold(RowState& st, int K, float eps2,
         const float other = __uint_as_float((unsigned)(v & 0xffffffffull));
         if ((uint32_t)(v >> 32) == tile && other > st.tau) { st.tau = other; st.tau_f = other - eps2; }
     }
-    // ---- (1) exclusion merge over entries [checked, cnt).  The list tail is sorted by id and every
-    //      id in it is larger than anything merged before, so one cursor walks the exclusion list once
-    //      per sweep; it is read four entries per round trip (independent loads) into a register window.
+    // ---- (1) exclusion merge over entries [checked, cnt).  The list tail is sorted by id and every id in it is larger
+    //      than anything merged before, so one cursor walks the exclusion list once per sweep; it is read four entries
+    //      per round trip (independent loads) into a register window.  Entries are moved only after the first hit.
     if (st.n_ex > 0 && st.checked < st.cnt) {
         int w = st.checked;
-        for (int e0 = st.checked; e0 < st.cnt; e0 += 8) {       // 8 independent entry loads per round trip;
-            unsigned long long v[8];                              // a batch is read before it is written (w <= e0)
+        for (int e0 = st.checked; e0 < st.cnt; e0 += 8) {       // 8 independent id loads per round trip;
+            int32_t v[8];                                        // a batch is read before it is written (w <= e0)
             const int nb = st.cnt - e0 < 8 ? st.cnt - e0 : 8;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = i < nb ? list[(size_t)(e0 + i) * 32] : 0ull;
+            for (int i = 0; i < 8; ++i) v[i] = i < nb ? lid[e0 + i] : 0x7fffffff;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 if (i < nb) {
-                    const int32_t id = (int32_t)(v[i] & 0xffffffffull);
+                    const int32_t id = v[i];
                     while (st.ex_w0 < id) {                       // advance the window past ids below `id`
                         st.ex_w0 = st.ex_w1; st.ex_w1 = st.ex_w2; st.ex_w2 = st.ex_w3; st.ex_w3 = 0x7fffffff;
                         if (st.ex_w0 == 0x7fffffff && st.ex_c < st.n_ex) {      // window empty: refill
@@ -479,7 +557,10 @@ __device__ __forceinline__ void raise_threshold(RowState& st, int K, float eps2,
                             st.ex_c = c + 4;
                         }
                     }
-                    if (st.ex_w0 != id) { list[(size_t)w * 32] = v[i]; ++w; }
+                    if (st.ex_w0 != id) {
+                        if (w != e0 + i) { lid[w] = id; lsc[w] = lsc[e0 + i]; }
+                        ++w;
+                    }
                 }
             }
         }
@@ -487,84 +568,109 @@ __device__ __forceinline__ void raise_threshold(RowState& st, int K, float eps2,
     }
     st.checked = st.cnt;
     const int L = st.cnt;
-    // ---- (2) score range, then two rounds of 16-way bisection (resolution (hi - lo) / 256)
+    // ---- (2) score range; the NB-bin histogram of [a, b]
     float lo = st.tau_f, hi = st.hi;
     if (L == 0) { lo = INFINITY; hi = -INFINITY; }
     else if (!(hi > -INFINITY) || !(lo > -1.0e37f)) {  // this list's score range is not known yet
         lo = INFINITY; hi = -INFINITY;
-        scan_list(list, L, [&](unsigned long long ent) {
-            const float sc = ent_score(ent);
+        scan_scores(lsc, L, [&](float sc) {
             lo = fminf(lo, sc);
             hi = fmaxf(hi, sc);
         });
     }
-    float a = lo, b = hi;                       // invariant: #(score >= a) >= K  (every entry is >= lo)
+    float a = lo, b = hi;                       // #(score >= a) >= K whenever the row can be raised at all
     bool act = L >= K;
+#pragma unroll
+    for (int j = 0; j < NB; ++j) hist_mine[j * TM] = 0;
     if (JOINT) {
         pair_mine[0] = L; pair_mine[1] = __float_as_int(lo); pair_mine[2] = __float_as_int(hi);
         pair_sync<ST>(bar_id);
         int Ltot = 0;
 #pragma unroll
         for (int o = 0; o < ST; ++o) {          // every thread of the row reads the same ST slots in the same order
-            const int* t = share + o * (TM * 16);
+            const int* t = share + o * (TM * 4);
             Ltot += t[0];
             a = o == 0 ? __int_as_float(t[1]) : fminf(a, __int_as_float(t[1]));
             b = o == 0 ? __int_as_float(t[2]) : fmaxf(b, __int_as_float(t[2]));
         }
         act = Ltot >= K;                        // the same decision in all threads of the row
-        pair_sync<ST>(bar_id);
     } else if (!act) {
         return;
     }
+    const float step = (b - a) * (1.f / NB);
+    const bool ok = act && (step > 0.f) && isfinite(step) && isfinite(a);
+    if (!JOINT && !ok) return;
     float new_hi = -INFINITY;
-    for (int round = 0; round < 2; ++round) {
-        const float step = (b - a) * 0.0625f;
-        const bool ok = act && (step > 0.f) && isfinite(step);
-        if (!JOINT && !ok) break;
-        int c[15];
-#pragma unroll
-        for (int j = 0; j < 15; ++j) c[j] = 0;
-        if (ok) {
-            scan_list(list, L, [&](unsigned long long ent) {
-                const float sc = ent_score(ent);
-                new_hi = fmaxf(new_hi, sc);
-#pragma unroll
-                for (int j = 0; j < 15; ++j) c[j] += (sc >= a + (float)(j + 1) * step);
-            });
-        }
-        if (JOINT) {
-#pragma unroll
-            for (int j = 0; j < 15; ++j) pair_mine[j] = c[j];
-            pair_sync<ST>(bar_id);
-#pragma unroll
-            for (int j = 0; j < 15; ++j) {
-                int tot = 0;
-#pragma unroll
-                for (int o = 0; o < ST; ++o) tot += share[o * (TM * 16) + j];
-                c[j] = tot;
+    if (ok) {
+        const float inv = 1.f / step;
+        scan_scores(lsc, L, [&](float sc) {
+            new_hi = fmaxf(new_hi, sc);
+            if (sc >= a) {
+                int j = (int)((sc - a) * inv);                  // within +-1 of the bin; made exact against bin_edge()
+                j = j > NB - 1 ? NB - 1 : j;
+                if (sc < bin_edge(a, step, j)) --j;
+                else if (j < NB - 1 && sc >= bin_edge(a, step, j + 1)) ++j;
+                if (j >= 0) hist_mine[j * TM] += 1;
             }
-            pair_sync<ST>(bar_id);
-        }
-        if (ok) {
-            float na = a, nb = a + step;
+        });
+    }
+    if (JOINT) pair_sync<ST>(bar_id);           // all counters of the row are complete
+    int chosen = -1, acc = 0;
+    if (ok) {
+#pragma unroll 4
+        for (int j = NB - 1; j >= 0; --j) {
+            int t = 0;
+            if (JOINT) {
 #pragma unroll
-            for (int j = 0; j < 15; ++j)
-                if (c[j] >= K) { na = a + (float)(j + 1) * step; nb = (j < 14) ? a + (float)(j + 2) * step : b; }
-            a = na; b = nb;
+                for (int o = 0; o < ST; ++o) t += hist[(size_t)(o * NB + j) * TM];
+            } else {
+                t = hist_mine[j * TM];
+            }
+            acc += t;
+            if (acc >= K && chosen < 0) chosen = j;
         }
     }
+    if (JOINT) pair_sync<ST>(bar_id);           // everybody has read the row's slots and counters: they may be reused
     if (L > 0) st.hi = fmaxf(hi, new_hi);       // scores above the old range only make the top bin fuller
-    if (!act) return;
-    if (a > st.tau) st.tau = a;
-    st.tau_f = st.tau - eps2;
-    *reinterpret_cast<volatile unsigned long long*>(my_tau) = ((unsigned long long)tile << 32) | __float_as_uint(st.tau);
-    // ---- (3) compaction (order-preserving)
-    int w = 0;          // writes trail the reads (w <= e), and each batch of 16 is read before it is written
-    scan_list(list, L, [&](unsigned long long ent) {
-        if (ent_score(ent) >= st.tau_f) { list[(size_t)w * 32] = ent; ++w; }
-    });
-    st.cnt = w;
-    st.checked = w;
+    const bool raised = ok && chosen >= 0;
+    bool want = false;
+    if (raised) {
+        const float t_new = bin_edge(a, step, chosen);
+        if (t_new > st.tau) st.tau = t_new;
+        st.tau_f = st.tau - eps2;
+        *reinterpret_cast<volatile unsigned long long*>(my_tau) = ((unsigned long long)tile << 32) | __float_as_uint(st.tau);
+        // upper bound on this list's entries >= tau_f: its counters from the filter's bin on
+        int alive = 0;
+        int jf = (int)((st.tau_f - a) * (1.f / step)) - 1;
+        jf = jf < 0 ? 0 : (jf > NB - 1 ? NB - 1 : jf);
+#pragma unroll 4
+        for (int j = NB - 1; j >= 0; --j) alive += (j >= jf) ? (int)hist_mine[j * TM] : 0;
+        want = !JOINT || (L > 2 * alive + 32);
+    }
+    // ---- (3) compaction (order-preserving), when at least half of the list is dead weight (always after a solo raise).
+    //      Joint raises decide per warp (the lanes run in lock step anyway); no lane has left the function before this
+    //      vote.  A solo raise decides per lane: lanes that could not raise returned above.
+    bool go = want;
+    if (JOINT) go = __any_sync(0xffffffffu, want);
+    if (go) {
+        int w = 0;          // writes trail the reads (w <= e)
+        int e = 0;
+        for (; e + 4 <= L; e += 4) {
+            const float4 sv = *reinterpret_cast<const float4*>(lsc + e);
+            const int4 iv = *reinterpret_cast<const int4*>(lid + e);
+            if (sv.x >= st.tau_f) { lsc[w] = sv.x; lid[w] = iv.x; ++w; }
+            if (sv.y >= st.tau_f) { lsc[w] = sv.y; lid[w] = iv.y; ++w; }
+            if (sv.z >= st.tau_f) { lsc[w] = sv.z; lid[w] = iv.z; ++w; }
+            if (sv.w >= st.tau_f) { lsc[w] = sv.w; lid[w] = iv.w; ++w; }
+        }
+        for (; e < L; ++e) {
+            const float sv = lsc[e];
+            const int32_t iv = lid[e];
+            if (sv >= st.tau_f) { lsc[w] = sv; lid[w] = iv; ++w; }
+        }
+        st.cnt = w;
+        st.checked = w;
+    }
 }
 
 // three-input maximum (FMNMX3, sm_100+)
@@ -575,15 +681,15 @@ __device__ __forceinline__ float fmax3(float a, float b, float c)
     return d;
 }
 
-// append the scores of one group of four that pass the filter to the calling lane's list
-__device__ __noinline__ unsigned long long* append4(unsigned long long* wp, float tau_f, float s0, float s1, float s2,
-                                                    float s3, int32_t id)
+// append the scores of one group of four that pass the filter to the calling lane's list; returns the new length
+__device__ __noinline__ int append4(float* lsc, int cap, int cnt, float tau_f, float s0, float s1, float s2, float s3, int32_t id)
 {
-    if (s0 > tau_f) { *wp = ((unsigned long long)__float_as_uint(s0) << 32) | (uint32_t)id; wp += 32; }
-    if (s1 > tau_f) { *wp = ((unsigned long long)__float_as_uint(s1) << 32) | (uint32_t)(id + 1); wp += 32; }
-    if (s2 > tau_f) { *wp = ((unsigned long long)__float_as_uint(s2) << 32) | (uint32_t)(id + 2); wp += 32; }
-    if (s3 > tau_f) { *wp = ((unsigned long long)__float_as_uint(s3) << 32) | (uint32_t)(id + 3); wp += 32; }
-    return wp;
+    int32_t* lid = reinterpret_cast<int32_t*>(lsc + cap);
+    if (s0 > tau_f) { lsc[cnt] = s0; lid[cnt] = id; ++cnt; }
+    if (s1 > tau_f) { lsc[cnt] = s1; lid[cnt] = id + 1; ++cnt; }
+    if (s2 > tau_f) { lsc[cnt] = s2; lid[cnt] = id + 2; ++cnt; }
+    if (s3 > tau_f) { lsc[cnt] = s3; lid[cnt] = id + 3; ++cnt; }
+    return cnt;
 }
 
 // one 32-column chunk of the accumulator (the item base is already in it: extra K slice of the MMA):
@@ -592,7 +698,7 @@ __device__ __noinline__ unsigned long long* append4(unsigned long long* wp, floa
 // groups once the thresholds have risen) does the warp run the predicated appends for that group.
 // ~1.25 instructions per score on the common path.
 template <bool DUMP>
-__device__ __forceinline__ void epilogue_chunk(uint32_t (&r)[32], RowState& st, int32_t id0,
+__device__ __forceinline__ void epilogue_chunk(uint32_t (&r)[32], RowState& st, int cap, int32_t id0,
                                                float* __restrict__ dump_row, bool valid, float invS)
 {
     if (DUMP) {
@@ -619,13 +725,22 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t (&r)[32], RowState& st, 
 #pragma unroll
     for (int j4 = 0; j4 < 8; ++j4) {
         if (hit[j4])
-            st.wp = append4(st.wp, st.tau_f, __uint_as_float(r[j4 * 4 + 0]), __uint_as_float(r[j4 * 4 + 1]),
-                            __uint_as_float(r[j4 * 4 + 2]), __uint_as_float(r[j4 * 4 + 3]), id0 + j4 * 4);
+            st.cnt = append4(st.lsc, cap, st.cnt, st.tau_f, __uint_as_float(r[j4 * 4 + 0]), __uint_as_float(r[j4 * 4 + 1]),
+                             __uint_as_float(r[j4 * 4 + 2]), __uint_as_float(r[j4 * 4 + 3]), id0 + j4 * 4);
     }
     }
 }
 
-template <bool DUMP, int ST>
+// CG = 1: one CTA per SM works alone on 128-user tiles.  CG = 2: the two CTAs of a cluster (one TPC) work on a PAIR of
+// user tiles with cta_group::2 MMAs (M = 256): each CTA stages its own U tile and only HALF of every V tile, so the item
+// matrix crosses the L2 -> SM fabric once per 256 users instead of once per 128 (the single-CTA kernel is bound by
+// exactly that traffic: 148 CTAs x 74 KB per stage ~ 10 TB/s out of L2) and the tensor pipe reads half as many B bytes
+// from each SM's shared memory.  Barrier protocol of the pair (rank 0 = leader, the only MMA issuer):
+//   full[s], u_full      local, armed by the CTA's own TMA producer
+//   pair_full[s], pair_u leader's, 2 arrivals: each CTA's relay thread (warp 3) forwards "my half / my U tile landed"
+//   empty[s], u_empty, acc_full[a]   local in BOTH CTAs, signalled by the leader's tcgen05.commit (multicast)
+//   acc_empty[a]         leader's, 2 x EPI_WARPS arrivals: the follower's epilogue warps arrive remotely
+template <bool DUMP, int ST, int CG>
 __global__ void __launch_bounds__(threads_for(ST), 1) rank_tc_kernel(const RankTcParams p)
 {
     constexpr int EPI_WARPS = 4 * ST;
@@ -634,37 +749,47 @@ __global__ void __launch_bounds__(threads_for(ST), 1) rank_tc_kernel(const RankT
     constexpr int TRIGGER = CAP_T / 2;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int kp = p.kp;
-    const uint32_t u_bytes = TM * kp * 2, v_bytes = TN * kp * 2;
-    const int NS = num_stages(kp, ST);
+    const uint32_t u_bytes = TM * kp * 2, v_bytes = TN * kp * 2, v_part = v_bytes / CG;
+    const int NS = num_stages(kp, ST, CG);
     uint8_t* sU = smem;
     uint8_t* sV = sU + u_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + (size_t)NS * v_bytes);
-    uint64_t* full = bars;            // [NS]  V tile landed                 TMA -> MMA
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + (size_t)NS * v_part);
+    uint64_t* full = bars;            // [NS]  V tile (part) landed          TMA -> MMA (CG = 2: -> relay)
     uint64_t* empty = bars + 4;       // [NS]  MMAs reading the tile retired MMA commit -> TMA
     uint64_t* u_full = bars + 8;      // U tile landed
     uint64_t* u_empty = bars + 9;     // all MMAs of the user tile retired
     uint64_t* acc_full = bars + 10;   // [2] accumulator ready               MMA commit -> epilogue
-    uint64_t* acc_empty = bars + 12;  // [2] accumulator drained             8 epilogue warps -> MMA
+    uint64_t* acc_empty = bars + 12;  // [2] accumulator drained             epilogue warps -> MMA
+    uint64_t* pair_full = bars + 14;  // [NS] CG = 2, leader: both halves of the V tile landed
+    uint64_t* pair_u = bars + 18;     // CG = 2, leader: both U tiles landed
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 22);
     // [ST strips][TM rows] last published row threshold, tagged with the tile it belongs to: (tile << 32) | f32 bits
     unsigned long long* tau_share = reinterpret_cast<unsigned long long*>(bars + 24);
-    // [ST strips][TM rows][16] bin counts / list length and score range exchanged by the ST threads of a row
+    // [ST strips][TM rows][4] list length and score range exchanged by the ST threads of a row
     int* pair_share = reinterpret_cast<int*>(bars + 24 + ST * TM);
+    // [ST strips][NB bins][TM rows] per-thread score-bin counters of a threshold raise
+    unsigned short* hist_share = reinterpret_cast<unsigned short*>(pair_share + ST * TM * 4);
     // The V ring is released by the tensor pipe alone, so the TMA producer runs NS tiles ahead of the
     // MMAs whatever the epilogue does; the epilogue only hands the TMEM accumulators back.
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
+    const int first_group = (int)(blockIdx.x / CG), n_groups = (int)(gridDim.x / CG);   // group = CTA (CG = 1) or CTA pair
+    const int n_gt = (p.n_ut + CG - 1) / CG;                                            // tile groups of the chunk
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NS; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int s = 0; s < NS; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); mbar_init(pair_full + s, 2); }
         mbar_init(u_full, 1);
         mbar_init(u_empty, 1);
-        for (int a = 0; a < 2; ++a) { mbar_init(acc_full + a, 1); mbar_init(acc_empty + a, EPI_WARPS); }
+        mbar_init(pair_u, 2);
+        for (int a = 0; a < 2; ++a) { mbar_init(acc_full + a, 1); mbar_init(acc_empty + a, EPI_WARPS * CG); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 2) tmem_alloc(tmem_ptr, TMEM_COLS);
+    if (warp == 2) {
+        if (CG == 2) tmem_alloc2(tmem_ptr, TMEM_COLS); else tmem_alloc(tmem_ptr, TMEM_COLS);
+    }
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();      // barriers of BOTH CTAs are initialised before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
@@ -672,7 +797,8 @@ __global__ void __launch_bounds__(threads_for(ST), 1) rank_tc_kernel(const RankT
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t it_global = 0, tile_no = 0;
-            for (int ut = blockIdx.x; ut < p.n_ut; ut += gridDim.x, ++tile_no) {
+            for (int gt = first_group; gt < n_gt; gt += n_groups, ++tile_no) {
+                const int ut = gt * CG + (int)cta_rank;          // (an odd chunk's last pair: a zero tile, packed as padding)
                 if (tile_no > 0) mbar_wait_backoff(u_empty, (tile_no - 1) & 1);
                 mbar_expect_tx(u_full, u_bytes);
                 bulk_g2s(sU, p.Upack + (size_t)ut * u_bytes, u_bytes, u_full);
@@ -680,37 +806,62 @@ __global__ void __launch_bounds__(threads_for(ST), 1) rank_tc_kernel(const RankT
                     const int s = it_global % NS;
                     const uint32_t round = it_global / NS;
                     if (round > 0) mbar_wait_backoff(empty + s, (round - 1) & 1);
-                    mbar_expect_tx(full + s, v_bytes);
-                    bulk_g2s(sV + (size_t)s * v_bytes, p.Vpack + (size_t)it * v_bytes, v_bytes, full + s);
+                    mbar_expect_tx(full + s, v_part);
+                    bulk_g2s(sV + (size_t)s * v_part, p.Vpack + (size_t)it * v_bytes + (size_t)cta_rank * v_part, v_part, full + s);
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ===================== relay (CTA pairs): "my part landed" -> the leader's pair barriers =====================
+        if (CG == 2 && lane == 0) {
+            const uint32_t r_pair_u = mapa_u32(smem_u32(pair_u), 0);
+            uint32_t it_global = 0, tile_no = 0;
+            for (int gt = first_group; gt < n_gt; gt += n_groups, ++tile_no) {
+                mbar_wait_backoff(u_full, tile_no & 1);
+                mbar_arrive_remote(r_pair_u);
+                for (int it = 0; it < p.n_it; ++it, ++it_global) {
+                    const int s = it_global % NS;
+                    mbar_wait_backoff(full + s, (it_global / NS) & 1);
+                    mbar_arrive_remote(mapa_u32(smem_u32(pair_full + s), 0));
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_f16(TM, TN);
+        // ===================== MMA issuer (of a pair: the leader only) =====================
+        if (lane == 0 && cta_rank == 0) {
+            const uint32_t idesc = umma_idesc_f16(TM * CG, TN);
             const uint32_t lbo = 128, sbo = (uint32_t)(kp >> 3) * 128;
             uint32_t it_global = 0, tile_no = 0;
-            for (int ut = blockIdx.x; ut < p.n_ut; ut += gridDim.x, ++tile_no) {
-                mbar_wait_backoff(u_full, tile_no & 1);
+            for (int gt = first_group; gt < n_gt; gt += n_groups, ++tile_no) {
+                if (CG == 2) mbar_wait_cluster_backoff(pair_u, tile_no & 1); else mbar_wait_backoff(u_full, tile_no & 1);
                 for (int it = 0; it < p.n_it; ++it, ++it_global) {
                     const int s = it_global % NS;
                     const int acc = it_global & 1;
                     const uint32_t acc_round = it_global >> 1;
-                    mbar_wait_backoff(full + s, (it_global / NS) & 1);
-                    if (acc_round > 0) mbar_wait_backoff(acc_empty + acc, (acc_round - 1) & 1);
+                    if (CG == 2) mbar_wait_cluster_backoff(pair_full + s, (it_global / NS) & 1);
+                    else mbar_wait_backoff(full + s, (it_global / NS) & 1);
+                    if (acc_round > 0) {
+                        if (CG == 2) mbar_wait_cluster_backoff(acc_empty + acc, (acc_round - 1) & 1);
+                        else mbar_wait_backoff(acc_empty + acc, (acc_round - 1) & 1);
+                    }
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(sU), b_addr = smem_u32(sV + (size_t)s * v_bytes);
+                    const uint32_t a_addr = smem_u32(sU), b_addr = smem_u32(sV + (size_t)s * v_part);
                     const uint32_t d_tmem = tmem_base + (uint32_t)acc * TN;
                     for (int ks = 0; ks < (kp >> 4); ++ks) {
                         const uint64_t ad = umma_desc(a_addr + ks * 256, lbo, sbo);
                         const uint64_t bd = umma_desc(b_addr + ks * 256, lbo, sbo);
-                        umma_f16(d_tmem, ad, bd, idesc, ks > 0 ? 1u : 0u);
+                        if (CG == 2) umma_f16_pair(d_tmem, ad, bd, idesc, ks > 0 ? 1u : 0u);
+                        else umma_f16(d_tmem, ad, bd, idesc, ks > 0 ? 1u : 0u);
                     }
-                    umma_commit(empty + s);        // smem stage may be refilled once these MMAs retire
-                    umma_commit(acc_full + acc);   // accumulator complete
+                    if (CG == 2) {
+                        umma_commit_pair(empty + s);       // both CTAs' stages may be refilled once these MMAs retire
+                        umma_commit_pair(acc_full + acc);  // both CTAs' halves of the accumulator are complete
+                    } else {
+                        umma_commit(empty + s);
+                        umma_commit(acc_full + acc);
+                    }
                 }
-                umma_commit(u_empty);
+                if (CG == 2) umma_commit_pair(u_empty); else umma_commit(u_empty);
             }
         }
     } else if (warp >= 4) {
@@ -718,7 +869,9 @@ __global__ void __launch_bounds__(threads_for(ST), 1) rank_tc_kernel(const RankT
         const int q = warp & 3;                          // TMEM lane quarter == warp % 4
         const int half = (warp - 4) >> 2;                // column strip: columns [half * STRIP_N, (half + 1) * STRIP_N)
         uint32_t it_global = 0;
-        for (int ut = blockIdx.x; ut < p.n_ut; ut += gridDim.x) {
+        const uint32_t r_acc_empty = CG == 2 ? mapa_u32(smem_u32(acc_empty), 0) : 0u;    // the leader's accumulator hand-back barriers
+        for (int gt = first_group; gt < n_gt; gt += n_groups) {
+            const int ut = gt * CG + (int)cta_rank;
             const int64_t row = (int64_t)ut * TM + q * 32 + lane;
             const bool valid = row < p.n_rows;
             const float un = valid ? p.unorm[row] : 0.f;
@@ -728,7 +881,7 @@ __global__ void __launch_bounds__(threads_for(ST), 1) rank_tc_kernel(const RankT
             const float invS = 1.f / us.S;
             const float eps2 = 2.f * eps;
             RowState st;
-            st.list = p.lists + ((size_t)(ut * EPI_WARPS + half * 4 + q) * CAP_T) * 32 + lane;
+            st.lsc = p.lists + ((size_t)(ut * EPI_WARPS + half * 4 + q) * 32 + lane) * (2 * CAP_T);
             st.ex = nullptr; st.n_ex = 0; st.ex_c = 0;
             st.ex_w0 = st.ex_w1 = st.ex_w2 = st.ex_w3 = 0x7fffffff;
             if (valid && p.excl_indptr) {
@@ -757,11 +910,10 @@ __global__ void __launch_bounds__(threads_for(ST), 1) rank_tc_kernel(const RankT
                 const int32_t item0 = it * TN + half * STRIP_N;
                 const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN + half * STRIP_N);
                 uint32_t r0[32], r1[32];
-                st.wp = st.list + (size_t)st.cnt * 32;
                 if (p.debug & 1) {                 // timing experiment: MMA / TMA feed rate without the screening
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(acc_empty + acc);
+                    if (lane == 0) { if (CG == 2) mbar_arrive_remote(r_acc_empty + 8 * acc); else mbar_arrive(acc_empty + acc); }
                     continue;
                 }
                 if (p.debug & 2) {                 // timing experiment: TMEM drain rate (tcgen05.ld only, no screening)
@@ -775,7 +927,7 @@ __global__ void __launch_bounds__(threads_for(ST), 1) rank_tc_kernel(const RankT
                     if (acc_or == 0x12345u) flag = 1;          // keep the loads alive
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(acc_empty + acc);
+                    if (lane == 0) { if (CG == 2) mbar_arrive_remote(r_acc_empty + 8 * acc); else mbar_arrive(acc_empty + acc); }
                     continue;
                 }
                 tmem_ld32_issue(t0, r0);
@@ -783,17 +935,16 @@ __global__ void __launch_bounds__(threads_for(ST), 1) rank_tc_kernel(const RankT
 #pragma unroll
                 for (int c0 = 0; c0 < STRIP_N; c0 += 64) {
                     tmem_ld32_issue(t0 + c0 + 32, r1);                        // in flight while r0 is processed
-                    epilogue_chunk<DUMP>(r0, st, item0 + c0, dump_row, valid, invS);
+                    epilogue_chunk<DUMP>(r0, st, CAP_T, item0 + c0, dump_row, valid, invS);
                     tmem_ld_wait(r1);
                     if (c0 + 64 < STRIP_N) tmem_ld32_issue(t0 + c0 + 64, r0);
-                    epilogue_chunk<DUMP>(r1, st, item0 + c0 + 32, dump_row, valid, invS);
+                    epilogue_chunk<DUMP>(r1, st, CAP_T, item0 + c0 + 32, dump_row, valid, invS);
                     if (c0 + 64 < STRIP_N) tmem_ld_wait(r0);
                 }
-                st.cnt = (int)((st.wp - st.list) >> 5);
                 // accumulator and stage are free again
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(acc_empty + acc);
+                if (lane == 0) { if (CG == 2) mbar_arrive_remote(r_acc_empty + 8 * acc); else mbar_arrive(acc_empty + acc); }
                 if (!DUMP) {
                     // Raise schedule: after stages 2, 4, 8, 16, ... for EVERY warp at once (a raise stalls the
                     // accumulator hand-off; doing it in all warps at the same stage costs one stall instead of
@@ -806,22 +957,29 @@ __global__ void __launch_bounds__(threads_for(ST), 1) rank_tc_kernel(const RankT
                         const int grown = (p.debug & 4) ? (done * 181) >> 7 : done * 2;
                         next_sched = grown > done ? grown : done + 1;
                     }
-                    int* share = pair_share + ((q * 32 + lane) << 4);
+                    int* share = pair_share + ((q * 32 + lane) << 2);
+                    unsigned short* hist = hist_share + q * 32 + lane;
                     unsigned long long* tau_row = tau_share + q * 32 + lane;
                     if (scheduled)
-                        raise_threshold<true, ST>(st, p.topk, eps2, (uint32_t)ut, half, tau_row, share, 1 + q);
+                        raise_threshold<true, ST>(st, p.topk, eps2, (uint32_t)ut, half, CAP_T, tau_row, share, hist, 1 + q);
                     else if (__any_sync(0xffffffffu, st.cnt >= TRIGGER))
-                        raise_threshold<false, ST>(st, p.topk, eps2, (uint32_t)ut, half, tau_row, share, 1 + q);
+                        raise_threshold<false, ST>(st, p.topk, eps2, (uint32_t)ut, half, CAP_T, tau_row, share, hist, 1 + q);
                     if (st.cnt > CAP_T - STRIP_N) { flag = 1; st.cnt = 0; st.checked = 0; st.tau_f = INFINITY; }
                 }
             }
-            if (valid && !DUMP) { p.row_cnt[row * MAX_ST + half] = st.cnt; p.row_flag[row * MAX_ST + half] = flag; }
+            if (valid && !DUMP) {
+                p.row_cnt[row * MAX_ST + half] = st.cnt;
+                p.row_flag[row * MAX_ST + half] = flag;
+                p.row_tau[row * MAX_ST + half] = st.tau_f;
+            }
         }
     }
 
     tc_fence_before();
-    __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+    if (CG == 2) cluster_sync_all(); else __syncthreads();      // no CTA leaves while its peer may still signal into it
+    if (warp == 2) {
+        if (CG == 2) tmem_dealloc2(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
+    }
 }
 
 // ---------------------------------------------------------------- finish kernel
@@ -834,9 +992,10 @@ struct FinishParams {
     const float* __restrict__ user_off;        // indexed by global query
     int64_t n_rows;
     int k, topk;
-    const unsigned long long* __restrict__ lists;
+    const float* __restrict__ lists;           // thread-private blocks [cap scores][cap ids] (see RankTcParams)
     const int* __restrict__ row_cnt;
     const int* __restrict__ row_flag;
+    const float* __restrict__ row_tau;         // final filter of each (row, strip), scaled units
     const int64_t* __restrict__ excl_indptr;   // offset to the chunk (may be null)
     const int32_t* __restrict__ excl_indices;
     int32_t* __restrict__ out_ids;             // offset to the chunk
@@ -847,19 +1006,10 @@ struct FinishParams {
     int strips, cap;                           // column strips per row (2 or 4) and the capacity of one strip list
 };
 
-// candidate e of a row whose strip lists hold Ls[0..strips) entries (lists interleaved [warp][entry][lane])
-__device__ __forceinline__ unsigned long long finish_entry(const FinishParams& p, int64_t ut, int r, const int* Ls, int e)
+// list block of (user tile ut, row r of the tile, strip s)
+__device__ __forceinline__ const float* finish_list(const FinishParams& p, int64_t ut, int r, int s)
 {
-    int s = 0;                                  // constant indices only: Ls stays in registers
-    if (e >= Ls[0]) {
-        e -= Ls[0]; s = 1;
-        if (e >= Ls[1]) {
-            e -= Ls[1]; s = 2;
-            if (e >= Ls[2]) { e -= Ls[2]; s = 3; }
-        }
-    }
-    const unsigned long long* list = p.lists + ((size_t)(ut * (4 * p.strips) + s * 4 + (r >> 5)) * p.cap) * 32 + (r & 31);
-    return list[(size_t)e * 32];
+    return p.lists + ((size_t)(ut * (4 * p.strips) + s * 4 + (r >> 5)) * 32 + (r & 31)) * (size_t)(2 * p.cap);
 }
 
 // STAGED: the candidates' item rows are gathered warp-cooperatively (one coalesced 16-byte cp.async per lane
@@ -878,6 +1028,7 @@ __global__ void __launch_bounds__(128) rank_tc_finish_kernel(const FinishParams 
     extern __shared__ __align__(16) unsigned char fin_stage[];      // STAGED: [128 rows][k*4 + 16 bytes]
     __shared__ unsigned long long sort_buf[2 * CAP];
     __shared__ double su[MAX_KP];                   // the user's factors, widened once per row
+    __shared__ int cand_n;                          // survivors of the row's lists
     const int tid = threadIdx.x;
     const bool vec4 = (p.k % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.V) & 15) == 0);
     const int stride = p.k * 4 + 16;
@@ -886,13 +1037,14 @@ __global__ void __launch_bounds__(128) rank_tc_finish_kernel(const FinishParams 
         const int64_t row = p.row_list ? (int64_t)p.row_list[1 + it] : it;
         __syncthreads();
         int Ls[MAX_ST] = {0, 0, 0, 0};
-        int L = 0, any_flag = 0;
+        int any_flag = 0;
+        float tau_f = -INFINITY;                    // the row's final filter: the largest of its strips' (each is valid)
 #pragma unroll
         for (int x = 0; x < MAX_ST; ++x) {
             if (x < p.strips) {
                 Ls[x] = p.row_cnt[row * MAX_ST + x];
-                L += Ls[x];
                 any_flag |= p.row_flag[row * MAX_ST + x];
+                tau_f = fmaxf(tau_f, p.row_tau[row * MAX_ST + x]);
             }
         }
         if (any_flag) {
@@ -915,16 +1067,29 @@ __global__ void __launch_bounds__(128) rank_tc_finish_kernel(const FinishParams 
             ex = p.excl_indices + a;
             n_ex = (int)(b - a);
         }
-        int sort_n = 32;                            // power of two >= L (padding keys are 0 = below every entry)
-        while (sort_n < L) sort_n <<= 1;
+        // survivors of the row's lists (approximate score >= the final filter) -> sort_buf[0, L) (ids, any order)
+        if (tid == 0) cand_n = 0;
         for (int f = tid; f < p.k; f += 128) su[f] = (double)__ldg(u + f);
         __syncthreads();
+        for (int x = 0; x < p.strips; ++x) {
+            const float* lsc = finish_list(p, ut, r, x);
+            const int32_t* lid = reinterpret_cast<const int32_t*>(lsc + p.cap);
+            for (int e = tid; e < Ls[x]; e += 128) {
+                if (lsc[e] >= tau_f) {
+                    const int pos = atomicAdd(&cand_n, 1);
+                    sort_buf[pos] = (unsigned long long)(uint32_t)lid[e];
+                }
+            }
+        }
+        __syncthreads();
+        const int L = cand_n;                       // <= strips * cap = 2 * CAP
+        int sort_n = 32;                            // power of two >= L (padding keys are 0 = below every entry)
+        while (sort_n < L) sort_n <<= 1;
         for (int e = tid; e < sort_n; e += 128) {
             unsigned long long key = 0ull;
             int32_t id = -1;
             if (e < L) {
-                const unsigned long long ent = finish_entry(p, ut, r, Ls, e);
-                id = (int32_t)(ent & 0xffffffffull);
+                id = (int32_t)(uint32_t)sort_buf[e];
                 if (n_ex) {                         // entries appended after the last merge are still unfiltered
                     int lo = 0, hi = n_ex;
                     while (lo < hi) {
@@ -1037,13 +1202,14 @@ __global__ void __launch_bounds__(32) rank_tc_finish_warp_kernel(const FinishPar
     for (int64_t row = blockIdx.x; row < p.n_rows; row += gridDim.x) {
         __syncwarp();
         int Ls[MAX_ST] = {0, 0, 0, 0};
-        int L = 0, any_flag = 0;
+        int any_flag = 0;
+        float tau_f = -INFINITY;                    // the row's final filter: the largest of its strips' (each is valid)
 #pragma unroll
         for (int x = 0; x < MAX_ST; ++x) {
             if (x < p.strips) {
                 Ls[x] = p.row_cnt[row * MAX_ST + x];
-                L += Ls[x];
                 any_flag |= p.row_flag[row * MAX_ST + x];
+                tau_f = fmaxf(tau_f, p.row_tau[row * MAX_ST + x]);
             }
         }
         if (any_flag) {
@@ -1053,6 +1219,23 @@ __global__ void __launch_bounds__(32) rank_tc_finish_warp_kernel(const FinishPar
             }
             continue;
         }
+        const int64_t ut = row / TM;
+        const int r = (int)(row % TM);
+        // survivors of the row's lists (approximate score >= the final filter): ids -> keys[0, L), coalesced reads of the
+        // thread-private list blocks, order-preserving warp compaction
+        int L = 0;
+        for (int x = 0; x < p.strips; ++x) {
+            const float* lsc = finish_list(p, ut, r, x);
+            const int32_t* lid = reinterpret_cast<const int32_t*>(lsc + p.cap);
+            for (int e0 = 0; e0 < Ls[x]; e0 += 32) {
+                const int e = e0 + lane;
+                const bool keep = e < Ls[x] && lsc[e] >= tau_f;
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                const int pos = L + __popc(m & ((1u << lane) - 1u));
+                if (keep && pos < FW_KEYS) keys[pos] = (unsigned long long)(uint32_t)lid[e];
+                L += __popc(m);
+            }
+        }
         if (L > FW_KEYS) {
             if (lane == 0) {
                 const int slot = atomicAdd(p.big_rows, 1);
@@ -1060,8 +1243,7 @@ __global__ void __launch_bounds__(32) rank_tc_finish_warp_kernel(const FinishPar
             }
             continue;
         }
-        const int64_t ut = row / TM;
-        const int r = (int)(row % TM);
+        __syncwarp();
         const int64_t gq = p.q0 + row;
         const int64_t urow = p.user_idx ? p.user_idx[row] : gq;
         const float* u = p.U + (size_t)urow * p.k;
@@ -1089,10 +1271,7 @@ __global__ void __launch_bounds__(32) rank_tc_finish_warp_kernel(const FinishPar
                 const int e = e0 + 32 * j;
                 cid[j] = -1;
                 lo[j] = 0;
-                if (e < L) {
-                    const unsigned long long ent = finish_entry(p, ut, r, Ls, e);
-                    cid[j] = (int32_t)(ent & 0xffffffffull);
-                }
+                if (e < L) cid[j] = (int32_t)(uint32_t)keys[e];
             }
             if (n_ex) {                             // entries appended after the last merge are still unfiltered
                 for (int half = pow2; half > 0; half >>= 1) {
@@ -1174,7 +1353,7 @@ __global__ void __launch_bounds__(32) rank_tc_finish_warp_kernel(const FinishPar
 struct Layout {
     int kp;
     int64_t n_it, chunk_rows, chunk_ut;
-    size_t off_vpack, off_scal, off_upack, off_unorm, off_uabs, off_lists, off_cnt, off_flag, off_over, off_big, off_slab, total;
+    size_t off_vpack, off_scal, off_upack, off_unorm, off_uabs, off_lists, off_cnt, off_flag, off_tau, off_over, off_big, off_slab, total;
 };
 
 static Layout make_layout(int64_t n_q, int64_t n_items, int k)
@@ -1184,6 +1363,7 @@ static Layout make_layout(int64_t n_q, int64_t n_items, int k)
     L.n_it = (n_items + TN - 1) / TN;
     int64_t n_ut = (n_q + TM - 1) / TM;
     L.chunk_ut = n_ut < CHUNK_TILES ? n_ut : CHUNK_TILES;
+    L.chunk_ut = (L.chunk_ut + 1) & ~(int64_t)1;     // CTA pairs work on pairs of user tiles: an odd chunk gets one padding tile
     L.chunk_rows = L.chunk_ut * TM;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t at = o; o += (bytes + 1023) / 1024 * 1024; return at; };
@@ -1192,9 +1372,10 @@ static Layout make_layout(int64_t n_q, int64_t n_items, int k)
     L.off_upack = take((size_t)L.chunk_ut * TM * L.kp * 2);
     L.off_unorm = take((size_t)L.chunk_rows * 4);
     L.off_uabs = take((size_t)L.chunk_rows * 4);
-    L.off_lists = take((size_t)L.chunk_ut * 8 * CAP * 32 * 8);          // = 4 ST warps x cap_for(ST) entries for ST = 2 and 4
+    L.off_lists = take((size_t)L.chunk_ut * 8 * CAP * 32 * 8);          // = 4 ST warps x 32 lanes x cap_for(ST) x (score + id), ST = 2 and 4
     L.off_cnt = take((size_t)L.chunk_rows * MAX_ST * 4);
     L.off_flag = take((size_t)L.chunk_rows * MAX_ST * 4);
+    L.off_tau = take((size_t)L.chunk_rows * MAX_ST * 4);
     L.off_over = take((size_t)(L.chunk_rows + 1) * 4);
     L.off_big = take((size_t)(L.chunk_rows + 1) * 4);
     L.off_slab = take((size_t)n_items * 4);          // one exact score row for overflowed users
@@ -1202,10 +1383,61 @@ static Layout make_layout(int64_t n_q, int64_t n_items, int k)
     return L;
 }
 
-static size_t smem_bytes_for(int kp, int st)
+static size_t smem_bytes_for(int kp, int st, int cg)
 {
-    const int NS = num_stages(kp, st);
-    return (size_t)TM * kp * 2 + (size_t)NS * (TN * kp * 2) + 32 * 8 + (size_t)st * TM * 8 + (size_t)st * TM * 16 * 4 + 1024;
+    const int NS = num_stages(kp, st, cg);
+    return (size_t)TM * kp * 2 + (size_t)NS * ((TN / cg) * kp * 2) + 32 * 8 + (size_t)st * TM * 8 + (size_t)st * TM * 4 * 4
+           + (size_t)st * NB * TM * 2 + 1024;
+}
+
+// CTAs that share one MMA: 2 = CTA pairs (cta_group::2, the default), 1 = every CTA alone (B200_RANK_CTA=1, for A/B runs)
+static int rank_cta_group()
+{
+    if (const char* e = getenv("B200_RANK_CTA")) {
+        if (e[0] == '1') return 1;
+        if (e[0] == '2') return 2;
+    }
+    return 2;
+}
+
+template <bool DUMP, int ST, int CG>
+static int launch_rank_tc_t(const RankTcParams& p, cudaStream_t st)
+{
+    auto kern = rank_tc_kernel<DUMP, ST, CG>;
+    const size_t smem = smem_bytes_for(p.kp, ST, CG);
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(threads_for(ST), 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr;
+    int max_groups = sm_count();
+    if (CG == 2) {
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+        cfg.gridDim = dim3((unsigned)(sm_count() & ~1), 1, 1);
+        int n_clusters = 0;
+        B200_CUDA(cudaOccupancyMaxActiveClusters(&n_clusters, kern, &cfg));
+        B200_REQUIRE(n_clusters >= 1, "rank_tc: no CTA pair fits the device (cudaOccupancyMaxActiveClusters = %d)", n_clusters);
+        max_groups = n_clusters;
+    }
+    const int want = (p.n_ut + CG - 1) / CG;
+    const int groups = want < max_groups ? want : max_groups;
+    cfg.gridDim = dim3((unsigned)(groups * CG), 1, 1);
+    ::b200::count_launch();
+    B200_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+    return B200_OK;
+}
+
+template <bool DUMP>
+static int launch_rank_tc(const RankTcParams& p, int strips, cudaStream_t st)
+{
+    const int cg = rank_cta_group();
+    if (DUMP) return cg == 2 ? launch_rank_tc_t<DUMP, 2, 2>(p, st) : launch_rank_tc_t<DUMP, 2, 1>(p, st);
+    if (strips == 4) return cg == 2 ? launch_rank_tc_t<DUMP, 4, 2>(p, st) : launch_rank_tc_t<DUMP, 4, 1>(p, st);
+    return cg == 2 ? launch_rank_tc_t<DUMP, 2, 2>(p, st) : launch_rank_tc_t<DUMP, 2, 1>(p, st);
 }
 
 // column strips per row (epilogue warps = 4 x strips): B200_RANK_STRIPS = 2 | 4
@@ -1243,6 +1475,15 @@ int64_t rank_tc_workspace_bytes(int64_t n_q, int64_t n_items, int k, int topk)
     return (int64_t)make_layout(n_q, n_items, k).total;
 }
 
+// The packed item side (fp16 tile images of V with the base slice + the scalars of the scaling): laid out exactly like the
+// head of the workspace (off_vpack = 0, then off_scal), so b200_rank_pack_items can build it once into a caller-owned
+// buffer and every later call on the same (V, item_base) skips the norm + pack kernels (b200_rank_topk_packed).
+int64_t rank_tc_items_bytes(int64_t n_items, int k)
+{
+    const Layout L = make_layout(1, n_items, k);
+    return (int64_t)(L.off_scal + 1024);
+}
+
 static int pack_items(const float* V, int64_t n_items, int k, const float* item_base, const Layout& L, uint8_t* ws,
                       cudaStream_t st)
 {
@@ -1259,10 +1500,10 @@ static int pack_items(const float* V, int64_t n_items, int k, const float* item_
 
 // per chunk of users: norms + element maximum, the chunk's scales, fp16 tile images
 static int pack_users(const float* Usrc, const int64_t* uidx, int64_t rows, int64_t n_ut, int k, const Layout& L, uint8_t* ws,
-                      cudaStream_t st)
+                      const uint8_t* items, cudaStream_t st)
 {
     const int grid = sm_count() * 8;
-    unsigned int* scal = reinterpret_cast<unsigned int*>(ws + L.off_scal);
+    const unsigned int* scal = reinterpret_cast<const unsigned int*>(items + L.off_scal);
     float* uabs = reinterpret_cast<float*>(ws + L.off_uabs);
     norm_kernel<<<grid, 256, 0, st>>>(Usrc, uidx, rows, k, reinterpret_cast<float*>(ws + L.off_unorm), uabs, nullptr, nullptr,
                                       nullptr, nullptr); ::b200::count_launch();
@@ -1271,50 +1512,59 @@ static int pack_users(const float* Usrc, const int64_t* uidx, int64_t rows, int6
     return B200_OK;
 }
 
+int rank_tc_pack_items(const float* V, int64_t n_items, int k, const float* item_base, void* packed, int64_t packed_bytes,
+                       cudaStream_t st)
+{
+    const Layout L = make_layout(1, n_items, k);
+    B200_REQUIRE(packed && packed_bytes >= rank_tc_items_bytes(n_items, k), "b200_rank_pack_items: buffer too small (%lld < %lld bytes)",
+                 (long long)packed_bytes, (long long)rank_tc_items_bytes(n_items, k));
+    B200_REQUIRE((((uintptr_t)packed) & 127) == 0, "b200_rank_pack_items: buffer must be 128-byte aligned");
+    return pack_items(V, n_items, k, item_base, L, static_cast<uint8_t*>(packed), st);
+}
+
 int rank_tc(const float* U, const int64_t* user_idx, int64_t n_q, const float* V, int64_t n_items, int k,
             const float* item_base, const float* user_off, const int64_t* excl_indptr, const int32_t* excl_indices,
-            int topk, int32_t* out_ids, float* out_scores, void* workspace, int64_t workspace_bytes, cudaStream_t st)
+            int topk, int32_t* out_ids, float* out_scores, void* workspace, int64_t workspace_bytes, const void* packed_items,
+            cudaStream_t st)
 {
     const Layout L = make_layout(n_q, n_items, k);
     B200_REQUIRE((int64_t)L.total <= workspace_bytes, "rank_tc: workspace too small");
     B200_REQUIRE((((uintptr_t)workspace) & 127) == 0, "rank_tc: workspace must be 128-byte aligned");
+    B200_REQUIRE((((uintptr_t)packed_items) & 127) == 0, "rank_tc: packed items must be 128-byte aligned");
     uint8_t* ws = static_cast<uint8_t*>(workspace);
+    // the packed item side: the caller's (built once by b200_rank_pack_items) or this call's own, in the workspace
+    const uint8_t* items = packed_items ? static_cast<const uint8_t*>(packed_items) : ws;
     const int strips = rank_strips(k, topk);
-    const size_t smem = smem_bytes_for(L.kp, strips);
-    if (strips == 4) B200_CUDA(cudaFuncSetAttribute(rank_tc_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else B200_CUDA(cudaFuncSetAttribute(rank_tc_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int rc = pack_items(V, n_items, k, item_base, L, ws, st);
+    int rc = packed_items ? B200_OK : pack_items(V, n_items, k, item_base, L, ws, st);
     if (rc) return rc;
     for (int64_t q0 = 0; q0 < n_q; q0 += L.chunk_rows) {
         const int64_t rows = (n_q - q0 < L.chunk_rows) ? n_q - q0 : L.chunk_rows;
         const int64_t n_ut = (rows + TM - 1) / TM;
         const int64_t* uidx = user_idx ? user_idx + q0 : nullptr;
         const float* Usrc = user_idx ? U : U + (size_t)q0 * k;
-        rc = pack_users(Usrc, uidx, rows, n_ut, k, L, ws, st);
+        rc = pack_users(Usrc, uidx, rows, (n_ut + 1) & ~(int64_t)1, k, L, ws, items, st);      // padded to a whole tile pair
         if (rc) return rc;
         B200_CUDA(cudaMemsetAsync(ws + L.off_over, 0, 4, st));
         RankTcParams p;
-        p.Upack = ws + L.off_upack; p.Vpack = ws + L.off_vpack;
+        p.Upack = ws + L.off_upack; p.Vpack = items + L.off_vpack;
         p.unorm = reinterpret_cast<const float*>(ws + L.off_unorm);
         p.uabs = reinterpret_cast<const float*>(ws + L.off_uabs);
-        p.scal = reinterpret_cast<const unsigned int*>(ws + L.off_scal);
+        p.scal = reinterpret_cast<const unsigned int*>(items + L.off_scal);
         p.excl_indptr = excl_indptr ? excl_indptr + q0 : nullptr;
         p.excl_indices = excl_indices;
         p.n_rows = rows; p.n_ut = (int)n_ut; p.n_it = (int)L.n_it; p.kp = L.kp; p.topk = topk;
-        p.lists = reinterpret_cast<unsigned long long*>(ws + L.off_lists);
+        p.lists = reinterpret_cast<float*>(ws + L.off_lists);
         p.row_cnt = reinterpret_cast<int*>(ws + L.off_cnt);
         p.row_flag = reinterpret_cast<int*>(ws + L.off_flag);
+        p.row_tau = reinterpret_cast<float*>(ws + L.off_tau);
         p.dump = nullptr;
         { const char* d = getenv("B200_RANK_DEBUG"); p.debug = d ? atoi(d) : 0; }
-        const int grid = (int)(n_ut < sm_count() ? n_ut : sm_count());
-        ::b200::count_launch();
-        if (strips == 4) rank_tc_kernel<false, 4><<<grid, threads_for(4), smem, st>>>(p);
-        else rank_tc_kernel<false, 2><<<grid, threads_for(2), smem, st>>>(p);
-        B200_CUDA(cudaGetLastError());
+        rc = launch_rank_tc<false>(p, strips, st);
+        if (rc) return rc;
         FinishParams f;
         f.U = U; f.user_idx = uidx; f.q0 = q0; f.V = V; f.item_base = item_base; f.user_off = user_off;
         f.n_rows = rows; f.k = k; f.topk = topk;
-        f.lists = p.lists; f.row_cnt = p.row_cnt; f.row_flag = p.row_flag;
+        f.lists = p.lists; f.row_cnt = p.row_cnt; f.row_flag = p.row_flag; f.row_tau = p.row_tau;
         f.excl_indptr = p.excl_indptr; f.excl_indices = p.excl_indices;
         f.out_ids = out_ids + (size_t)q0 * topk; f.out_scores = out_scores + (size_t)q0 * topk;
         f.overflow_rows = reinterpret_cast<int*>(ws + L.off_over);
@@ -1397,11 +1647,9 @@ extern "C" int b200_rank_tc_debug_scores(const float* U, int64_t n_q, const floa
     B200_REQUIRE(out_elems >= n_ut * TM * L.n_it * TN, "b200_rank_tc_debug_scores: out too small");
     cudaStream_t st = (cudaStream_t)stream;
     uint8_t* ws = static_cast<uint8_t*>(workspace);
-    const size_t smem = smem_bytes_for(L.kp, 2);
-    B200_CUDA(cudaFuncSetAttribute(rank_tc_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int rc = pack_items(V, n_items, k, item_base, L, ws, st);
     if (rc) return rc;
-    rc = pack_users(U, nullptr, n_q, n_ut, k, L, ws, st);
+    rc = pack_users(U, nullptr, n_q, (n_ut + 1) & ~(int64_t)1, k, L, ws, ws, st);
     if (rc) return rc;
     RankTcParams p;
     p.Upack = ws + L.off_upack; p.Vpack = ws + L.off_vpack;
@@ -1410,13 +1658,11 @@ extern "C" int b200_rank_tc_debug_scores(const float* U, int64_t n_q, const floa
     p.scal = reinterpret_cast<const unsigned int*>(ws + L.off_scal);
     p.excl_indptr = nullptr; p.excl_indices = nullptr;
     p.n_rows = n_q; p.n_ut = (int)n_ut; p.n_it = (int)L.n_it; p.kp = L.kp; p.topk = 1;
-    p.lists = reinterpret_cast<unsigned long long*>(ws + L.off_lists);
+    p.lists = reinterpret_cast<float*>(ws + L.off_lists);
     p.row_cnt = reinterpret_cast<int*>(ws + L.off_cnt);
     p.row_flag = reinterpret_cast<int*>(ws + L.off_flag);
+    p.row_tau = reinterpret_cast<float*>(ws + L.off_tau);
     p.dump = out;
     p.debug = 0;
-    const int grid = (int)(n_ut < sm_count() ? n_ut : sm_count());
-    rank_tc_kernel<true, 2><<<grid, threads_for(2), smem, st>>>(p); ::b200::count_launch();
-    B200_CUDA(cudaGetLastError());
-    return B200_OK;
+    return launch_rank_tc<true>(p, 2, st);
 }

@@ -262,6 +262,66 @@ def mf_epoch(rid, cid, val, U, V, Bu, Bi, lr, reg, mu, use_bias, loss, ordered=F
                           current_stream()), "b200_mf_epoch")
 
 
+class WmfTrainer:
+    """Device state of one WMF fit (the variables and Adam slots of the reference's TF-1 graph, wmf/wmf.py:34-55) and
+    the step `sess.run([model.opt, model.loss], feed_dict)` of recom_wmf.py:197-199, one mini-batch of item ids at a
+    time.  `csc` is train_set.csc_matrix (scipy); U, V numpy float32 arrays (copied up; read back with .download())."""
+
+    BETA1, BETA2, EPS = 0.9, 0.999, 1e-8              # tf.train.AdamOptimizer defaults
+
+    def __init__(self, csc, U, V, a, b, lambda_u, lambda_v, lr):
+        require_cuda()
+        csc = csc.tocsc()
+        csc.sort_indices()
+        if csc.nnz >= 2 ** 31:
+            raise B200Error("nnz >= 2^31 is not supported (int32 CSC offsets)")
+        self.n_users, self.n_items = (int(x) for x in csc.shape)
+        if U.shape[0] != self.n_users or V.shape[0] != self.n_items or U.shape[1] != V.shape[1]:
+            raise B200Error("U / V shapes %s / %s do not match the %d x %d rating matrix" % (U.shape, V.shape, self.n_users, self.n_items))
+        self.k = int(U.shape[1])
+        self.indptr = to_device(csc.indptr, torch.int32)
+        self.rows = to_device(csc.indices if csc.nnz else np.zeros(1, np.int32), torch.int32)
+        self.vals = to_device(np.asarray(csc.data if csc.nnz else np.zeros(1), dtype=np.float32), torch.float32)
+        self.U = to_device(np.ascontiguousarray(U, dtype=np.float32), torch.float32)
+        self.V = to_device(np.ascontiguousarray(V, dtype=np.float32), torch.float32)
+        self.mU, self.vU = torch.zeros_like(self.U), torch.zeros_like(self.U)
+        self.mV, self.vV = torch.zeros_like(self.V), torch.zeros_like(self.V)
+        self.slot_of = torch.full((self.n_items,), -1, dtype=torch.int32, device="cuda")
+        self.loss = torch.zeros(1, dtype=torch.float64, device="cuda")
+        self.gV = None
+        f32 = np.float32
+        self.a, self.b, self.lambda_u, self.lambda_v = f32(a), f32(b), f32(lambda_u), f32(lambda_v)
+        self.lr = f32(lr)
+        self.b1_pow, self.b2_pow = f32(self.BETA1), f32(self.BETA2)     # beta^t for the step about to be taken (t = 1)
+
+    def step(self, ids, want_loss=True):
+        """One optimisation step on the item mini-batch `ids` (distinct item indices); returns the batch loss (float) or
+        None.  Reading the loss synchronises with the device, like sess.run does."""
+        L = _lib.load()
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        b = int(len(ids))
+        if b == 0:
+            return 0.0
+        if ids.min() < 0 or ids.max() >= self.n_items:
+            raise B200Error("item id out of range in the mini-batch")
+        d_ids = to_device(ids, torch.int32, pinned=False)
+        if self.gV is None or self.gV.numel() < b * self.k:
+            self.gV = torch.empty(b * self.k, dtype=torch.float32, device="cuda")
+        f32 = np.float32
+        lr_t = self.lr * np.sqrt(f32(1) - self.b2_pow) / (f32(1) - self.b1_pow)          # AdamOptimizer._prepare / _apply_*
+        check(L.b200_wmf_step(ptr(self.indptr), ptr(self.rows), ptr(self.vals), ptr(d_ids), b, self.n_users, self.n_items,
+                              self.k, ptr(self.U), ptr(self.V), ptr(self.mU), ptr(self.vU), ptr(self.mV), ptr(self.vV),
+                              float(self.a), float(self.b), float(self.lambda_u), float(self.lambda_v), float(f32(lr_t)),
+                              self.BETA1, self.BETA2, self.EPS, ptr(self.slot_of), ptr(self.gV), ptr(self.loss),
+                              current_stream()), "b200_wmf_step")
+        self.b1_pow = f32(self.b1_pow * f32(self.BETA1))              # _finish: the beta powers advance once per step
+        self.b2_pow = f32(self.b2_pow * f32(self.BETA2))
+        return float(self.loss.item()) if want_loss else None
+
+    def download(self):
+        return self.U.cpu().numpy(), self.V.cpu().numpy()
+
+
 def score_batch(U, V, user_idx=None, item_base=None, user_off=None, n_items=None, out=None):
     """out[q, i] = (item_base[i] + user_off[q]) + dot(U[user_idx[q]], V[i]) for i < n_items."""
     L = require_cuda()
@@ -292,10 +352,29 @@ def topk_rows(scores, topk, excl_indptr=None, excl_indices=None):
     return ids, sc
 
 
+def rank_pack_items(V, item_base=None, n_items=None):
+    """The item side of the fused rank packed once (b200_rank_pack_items): fp16 tile images of V[:n_items] with the item
+    base folded in + the scaling scalars, as a uint8 CUDA tensor to pass to rank_topk(packed_items=...).  Valid as long as
+    V / item_base do not change.  Returns None for shapes the tensor-core pass does not take."""
+    L = require_cuda()
+    _dev(V, torch.float32, "V")
+    n_items = V.shape[0] if n_items is None else int(n_items)
+    k = int(V.shape[1])
+    nbytes = int(L.b200_rank_items_bytes(n_items, k))
+    if nbytes <= 0:
+        return None
+    packed = torch.empty(nbytes, dtype=torch.uint8, device=V.device)
+    check(L.b200_rank_pack_items(ptr(V), n_items, k, ptr(item_base), ptr(packed), nbytes, current_stream()),
+          "b200_rank_pack_items")
+    return packed
+
+
 def rank_topk(U, V, topk, user_idx=None, item_base=None, user_off=None, excl_indptr=None, excl_indices=None,
-              n_items=None, workspace=None):
+              n_items=None, workspace=None, packed_items=None):
     """Fused score + exclusion + top-k on device tensors (b200_rank_topk).  Returns (ids int32 [n_q, topk],
-    scores f32 [n_q, topk]) CUDA tensors ordered by (score desc, item id asc); ids are -1 padded."""
+    scores f32 [n_q, topk]) CUDA tensors ordered by (score desc, item id asc); ids are -1 padded.
+    packed_items: result of rank_pack_items(V, item_base, n_items) for the SAME V / item_base / n_items (skips the two
+    passes over V that every call otherwise makes)."""
     L = require_cuda()
     _dev(U, torch.float32, "U"), _dev(V, torch.float32, "V")
     n_items = V.shape[0] if n_items is None else int(n_items)
@@ -306,14 +385,18 @@ def rank_topk(U, V, topk, user_idx=None, item_base=None, user_off=None, excl_ind
     nbytes = int(L.b200_rank_topk_workspace_bytes(n_q, n_items, k, int(topk)))
     if workspace is None or workspace.numel() < nbytes:
         workspace = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=U.device)
-    check(L.b200_rank_topk(ptr(U), ptr(user_idx), n_q, ptr(V), n_items, k, ptr(item_base), ptr(user_off),
-                           ptr(excl_indptr), ptr(excl_indices), int(topk), ptr(ids), ptr(sc), ptr(workspace),
-                           workspace.numel(), current_stream()), "b200_rank_topk")
+    if packed_items is not None:
+        _dev(packed_items, torch.uint8, "packed_items")
+        if packed_items.numel() != int(L.b200_rank_items_bytes(n_items, k)):
+            raise B200Error("packed_items was built for another item count / factor width")
+    check(L.b200_rank_topk_packed(ptr(U), ptr(user_idx), n_q, ptr(V), n_items, k, ptr(item_base), ptr(user_off),
+                                  ptr(excl_indptr), ptr(excl_indices), int(topk), ptr(ids), ptr(sc), ptr(packed_items),
+                                  ptr(workspace), workspace.numel(), current_stream()), "b200_rank_topk")
     return ids, sc
 
 
 def rank_topk_host(U, V, topk, user_idx, item_base=None, excl_indptr=None, excl_indices=None, out_ids=None,
-                   out_scores=None, workspace=None):
+                   out_scores=None, workspace=None, packed_items=None):
     """Host-buffer entry of the rank path (what the plug-ins' rank_batch calls): the factor matrices are
     device resident (model state), the REQUEST -- user indices and the per-user sorted exclusion lists in CSR
     form, numpy / pinned -- is copied in, ids + scores are copied back into numpy arrays."""
@@ -324,7 +407,7 @@ def rank_topk_host(U, V, topk, user_idx, item_base=None, excl_indptr=None, excl_
         ei = to_device(np.asarray(excl_indices, dtype=np.int32), torch.int32) if len(excl_indices) else \
             torch.zeros(1, dtype=torch.int32, device="cuda")
     ids, sc = rank_topk(U, V, topk, user_idx=uidx, item_base=item_base, excl_indptr=ep, excl_indices=ei,
-                        workspace=workspace)
+                        workspace=workspace, packed_items=packed_items)
     n_q = len(user_idx)
     out_ids = np.empty((n_q, topk), dtype=np.int32) if out_ids is None else out_ids
     out_scores = np.empty((n_q, topk), dtype=np.float32) if out_scores is None else out_scores

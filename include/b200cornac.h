@@ -132,6 +132,25 @@ B200_API int b200_mf_epoch(const void* rid, const void* cid, const float* val, i
                            unsigned flags, float* loss, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * WMF.  One optimisation step of the reference's TensorFlow-1 graph (cornac/models/wmf/wmf.py:34-55, fed by
+ * cornac/models/wmf/recom_wmf.py:186-199) for a mini-batch of `b` item ids:
+ *   loss = sum(C (R_b - U V_b^T)^2) + lambda_u |U|^2/2 + lambda_v |V_b|^2/2,  C = a_conf where R_b != 0 else b_conf;
+ *   gradients clipped elementwise to [-5, 5]; Adam with TF-1 semantics (dense step on U; the sparse step on V decays
+ *   the moments of ALL rows and moves ALL rows).  The caller advances the beta powers and passes
+ *   lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t).
+ *   csc_indptr / csc_rows / csc_vals  device int32[n_items+1] / int32[nnz] / f32[nnz]: train_set.csc_matrix
+ *                (user indices sorted within a column); ids device int32[b], distinct
+ *   U f32[n_users,k], V f32[n_items,k] and their Adam slots mU, vU, mV, vV (same shapes), all device, updated in place
+ *   slot_of      device int32[n_items], all -1 on entry and on exit (scratch: item -> position in the batch)
+ *   gV_scratch   device f32[b*k]; loss device f64[1]: receives the batch loss                                          */
+B200_API int b200_wmf_step(const int32_t* csc_indptr, const int32_t* csc_rows, const float* csc_vals,
+                           const int32_t* ids, int b, int64_t n_users, int64_t n_items, int k,
+                           float* U, float* V, float* mU, float* vU, float* mV, float* vV,
+                           float a_conf, float b_conf, float lambda_u, float lambda_v,
+                           float lr_t, float beta1, float beta2, float epsilon,
+                           int32_t* slot_of, float* gV_scratch, double* loss, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Scores.  Replaces `out = base; fast_dot(U[u], V, out)` (fast_dot.pyx:40-43 as used by
  * BPR.score recom_bpr.pyx:290-293 and MF.score mf/recom_mf.py:272-278) for a BATCH of
  * query users:  out[q, i] = (item_base[i] + user_off[q]) + dot(U[user_idx[q]], V[i]).
@@ -166,6 +185,23 @@ B200_API int b200_rank_topk(const float* U, const int64_t* user_idx, int64_t n_q
                             int topk, int32_t* out_ids, float* out_scores,
                             void* workspace, int64_t workspace_bytes, void* stream);
 
+/* The item side of the fused rank, packed once: fp16 tile images of V (with the item base folded in) and the scaling
+ * scalars.  V and item_base are constant across an evaluation / a serving session, so a caller that ranks many batches
+ * builds this once (b200_rank_pack_items, ~0.4 ms at 1 M items x k = 128) and passes it to b200_rank_topk_packed, which
+ * then skips the two passes over V every b200_rank_topk call makes.  The caller owns the buffer and must rebuild it
+ * whenever V or item_base change (e.g. after a training epoch).  b200_rank_items_bytes returns 0 for shapes the
+ * tensor-core pass does not take (then pass packed_items = NULL).
+ *   packed device, 128-byte aligned, b200_rank_items_bytes(n_items, k) bytes                                              */
+B200_API int64_t b200_rank_items_bytes(int64_t n_items, int k);
+B200_API int b200_rank_pack_items(const float* V, int64_t n_items, int k, const float* item_base,
+                                  void* packed, int64_t packed_bytes, void* stream);
+B200_API int b200_rank_topk_packed(const float* U, const int64_t* user_idx, int64_t n_q,
+                                   const float* V, int64_t n_items, int k,
+                                   const float* item_base, const float* user_off,
+                                   const int64_t* excl_indptr, const int32_t* excl_indices,
+                                   int topk, int32_t* out_ids, float* out_scores,
+                                   const void* packed_items, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* Validation hook of the tensor-core pass: dense APPROXIMATE scores (operands scaled by powers of
  * two and rounded to fp16, f32 accumulation, + item_base, scaled back) as the candidate pass of
  * b200_rank_topk sees them; padding items (>= n_items) read -inf.
@@ -196,6 +232,22 @@ B200_API int b200_topk_metrics(const int32_t* ids, int64_t n_q, int topk, int64_
                                const int64_t* user_idx, const int64_t* pos_indptr, const int32_t* pos_indices,
                                const int32_t* metric_kind, const int32_t* metric_k, int n_metrics,
                                double* out, void* stream);
+
+/* The counts behind the full-vector ranking metrics of the same loop -- AUC (cornac/metrics/ranking.py:473-485), MAP
+ * (:522-525), MRR (:213-222) -- for a batch of users whose score rows are on the device (b200_score_batch output):
+ *   scores       device f32[n_q, n_items]; MODIFIED: the entries listed in excl_* are overwritten with NaN (not candidates)
+ *   excl_indptr / excl_indices   device int64[n_q+1] / int32: per ROW q, the item ids that are not candidates (NULL = none)
+ *   user_idx / pos_indptr / pos_indices   as for b200_topk_metrics: the test positives of row q are row user_idx[q] of the CSR
+ *   less         device int64, indexed like pos_indices: number of candidates of the user scoring strictly BELOW that positive
+ *   pos_score    device f32, indexed like pos_indices: the positive's score
+ *   n_cand       device int64[n_q]: candidates of the user (items minus exclusions)
+ *   before_first device int64[n_q]: candidates ranked ahead of the user's best positive in the total order
+ *                (score desc, id asc) -> MRR = 1 / (1 + before_first)
+ * From these: rank_p = n_cand - less_p (rankdata "max"), AUC = sum_p (less_p - #{positives below p}) / (|P| (n_cand - |P|)). */
+B200_API int b200_rank_counts(float* scores, int64_t n_q, int64_t n_items,
+                              const int64_t* excl_indptr, const int32_t* excl_indices,
+                              const int64_t* user_idx, const int64_t* pos_indptr, const int32_t* pos_indices,
+                              int64_t* less, float* pos_score, int64_t* n_cand, int64_t* before_first, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Multi-GPU item-factor exchange (no reference counterpart: the reference is a single

@@ -189,9 +189,11 @@ def test_limits_of_the_fused_kernel_take_the_exact_path(k, n_items, n_q, topk):
         assert np.array_equal(ids[q], wi) and np.array_equal(sc[q][:w], ws[:w])
 
 
-def test_packed_item_side_is_reused_across_calls_and_refreshed_when_the_factors_change():
-    """the fp16 item tiles and norms are cached in the workspace between calls on the same (V, base): a second call gives
-    the same answer, and a call after V changed IN PLACE (same pointer -- what a training epoch does) must not reuse it"""
+def test_packed_item_side_built_once_gives_the_same_answer_and_is_really_used():
+    """b200_rank_pack_items + b200_rank_topk_packed: the fp16 item tiles and norms built once give exactly the result of
+    b200_rank_topk (which packs per call); that the packed buffer is what the kernel reads is shown by changing V in
+    place: the stale buffer then yields the OLD model's candidates' exact scores order (not the oracle's), a rebuilt one
+    the oracle's again."""
     import torch
     from cornac_b200 import engine
     rng = np.random.RandomState(4)
@@ -199,14 +201,44 @@ def test_packed_item_side_is_reused_across_calls_and_refreshed_when_the_factors_
     Vh = rng.normal(0, 0.3, (5000, 64)).astype(np.float32)
     V = torch.from_numpy(Vh.copy()).cuda()
     B = torch.from_numpy(rng.normal(0, 0.3, 5000).astype(np.float32)).cuda()
-    nb = int(engine.require_cuda().b200_rank_topk_workspace_bytes(200, 5000, 64, 20))
-    ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
-    a = engine.rank_topk(U, V, 20, item_base=B, workspace=ws)
-    b = engine.rank_topk(U, V, 20, item_base=B, workspace=ws)
-    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    packed = engine.rank_pack_items(V, B)
+    assert packed is not None and packed.dtype == torch.uint8
+    a = engine.rank_topk(U, V, 20, item_base=B)
+    b = engine.rank_topk(U, V, 20, item_base=B, packed_items=packed)
+    b2 = engine.rank_topk(U, V, 20, item_base=B, packed_items=packed)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(b[0], b2[0])
     V.copy_(torch.from_numpy(Vh[::-1].copy()).cuda())              # same storage, new content
-    c = engine.rank_topk(U, V, 20, item_base=B, workspace=ws)
     want = O.score_batch(U.cpu().numpy(), Vh[::-1].copy(), B.cpu().numpy())
-    for q in range(0, 200, 13):
+    stale = engine.rank_topk(U, V, 20, item_base=B, packed_items=packed)
+    fresh = engine.rank_topk(U, V, 20, item_base=B, packed_items=engine.rank_pack_items(V, B))
+    n_same = 0
+    for q in range(200):
         wi, wsc, _ = O.topk(want[q], 20)
-        assert np.array_equal(c[0][q].cpu().numpy(), wi) and np.array_equal(c[1][q].cpu().numpy(), wsc)
+        assert np.array_equal(fresh[0][q].cpu().numpy(), wi) and np.array_equal(fresh[1][q].cpu().numpy(), wsc)
+        n_same += int(np.array_equal(stale[0][q].cpu().numpy(), wi))
+    assert n_same < 100                                             # the stale tiles nominated the wrong candidates
+    assert engine.rank_pack_items(torch.zeros((500, 64), device="cuda")) is None      # tiny catalogue: exact path, nothing to pack
+    with pytest.raises(Exception):
+        engine.rank_topk(U, V[:4000].contiguous(), 20, packed_items=packed)
+
+
+@pytest.mark.parametrize("n_q", [1, 129, 300, 1000])
+def test_cta_pair_kernel_equals_single_cta_kernel(monkeypatch, n_q):
+    """cta_group::2 (two CTAs of a cluster share one M = 256 MMA, each staging half of every V tile; the default) and the
+    single-CTA kernel (B200_RANK_CTA=1) nominate candidates independently; after the exact finish both give the oracle's
+    ids and scores -- odd tile counts (a padding tile in the last pair), one tile, many tiles per pair."""
+    rng = np.random.RandomState(n_q)
+    k, n_items, topk = 64, 9000, 50
+    U = rng.normal(0, 0.3, (n_q, k)).astype(np.float32)
+    V = rng.normal(0, 0.3, (n_items, k)).astype(np.float32)
+    base = rng.normal(0, 0.3, n_items).astype(np.float32)
+    excl = [np.unique(rng.randint(n_items, size=rng.randint(0, 120))) for _ in range(n_q)]
+    monkeypatch.setenv("B200_RANK_CTA", "2")
+    a = _rank_topk(U, V, base, None, None, excl, topk)
+    monkeypatch.setenv("B200_RANK_CTA", "1")
+    b = _rank_topk(U, V, base, None, None, excl, topk)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    want = O.score_batch(U, V, base)
+    for q in range(0, n_q, 7):
+        wi, ws, w = O.topk(want[q], topk, excl[q])
+        assert np.array_equal(a[0][q], wi) and np.array_equal(a[1][q][:w], ws[:w])
