@@ -363,6 +363,221 @@ __global__ void __launch_bounds__(256, MINB) bpr_hogwild_chunk_kernel(const BprP
 }
 
 // ---------------------------------------------------------------------------------------
+// Streamed variant (the default for k % 4 == 0, k <= 128): the chunked kernel above keeps the rows of the samples in
+// flight in REGISTERS (one sample ahead: 24 registers), is fully unrolled over the G samples of a chunk (190 KB of code:
+// 17 % of its stall samples were instruction-cache misses, ncu r02) and exposes the two dependent DRAM gathers of the
+// sampling (pair -> bucket) once per chunk.  Here
+//   * the factor rows of the next D samples are staged in SHARED MEMORY with cp.async (LDGSTS.BYPASS, L2-coherent like
+//     the ld.global.cg they replace): every lane copies and later reads back only its own 16-byte column, so no barrier
+//     is needed, no register is held by a row in flight, and D = 4 samples (6 KB per warp at k = 128) are in flight
+//     per group instead of 2;
+//   * the sampling of the NEXT chunk (Philox, pair gather, membership bucket) is issued while the current chunk's
+//     samples are applied, one step per quarter of the chunk, so its latency is off the critical path;
+//   * the loop over the chunk is a real loop (unrolled by 2), the per-sample integer work is cut down (triplet packed
+//     in three shuffles, deltas as (lr z) x - (lr reg) y): ~100 warp instructions per sample instead of ~200.
+__device__ __forceinline__ void cp_async_16(uint32_t dst_smem, const void* src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+__device__ __forceinline__ float4 lds_f4(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
+// sampling of one chunk, in three steps so that it can be spread over the previous chunk's sample loop
+struct ChunkMeta {
+    int32_t u, i, j;        // this lane's sample of the chunk (u < 0: not live -- out of range or skipped)
+    uint64_t key, bucket;
+    ulonglong2 b0, b1;      // the membership bucket in flight
+    int2 pr;                // the pair in flight
+    int in_range;
+};
+
+template <int G>
+__device__ __forceinline__ void meta_step_a(const BprParams& p, ChunkMeta& m, int64_t chunk, int lg)
+{
+    const int64_t sl = chunk * G + lg;
+    m.in_range = sl < p.n_samples;
+    const uint64_t s = p.sample_base + (uint64_t)sl;
+    const Philox4 r = philox4x32_10((uint32_t)s, (uint32_t)(s >> 32), p.epoch_lo, p.epoch_hi, p.seed_lo, p.seed_hi);
+    const int64_t ii = (int64_t)range64(r.x, r.y, (uint64_t)p.nnz);
+    m.j = p.neg_weighted ? __ldg(p.pairs + range64(r.z, r.w, (uint64_t)p.nnz)).y     // recom_wbpr.pyx:131
+                         : (int32_t)range64(r.z, r.w, (uint64_t)p.n_neg);
+    m.pr = __ldg(p.pairs + ii);
+}
+__device__ __forceinline__ void meta_step_b(const BprParams& p, ChunkMeta& m)
+{
+    m.u = m.pr.x; m.i = m.pr.y;
+    m.key = ((uint64_t)(uint32_t)m.u << 32) | (uint32_t)m.j;
+    m.bucket = mix64(m.key) & p.bucket_mask;
+    m.b0 = __ldg(reinterpret_cast<const ulonglong2*>(p.table + 4 * m.bucket));
+    m.b1 = __ldg(reinterpret_cast<const ulonglong2*>(p.table + 4 * m.bucket) + 1);
+}
+// returns 1 when the sample was skipped (has_non_zero(u, j), recom_bpr.pyx:241-243); marks dead samples with u = ~u
+__device__ __forceinline__ int meta_step_c(const BprParams& p, ChunkMeta& m)
+{
+    bool found = (m.b0.x == m.key) | (m.b0.y == m.key) | (m.b1.x == m.key) | (m.b1.y == m.key);
+    bool full = (m.b1.y != TABLE_EMPTY);
+    uint64_t bb = m.bucket;
+    while (!found && full) {                    // rare: the bucket overflowed into the next one
+        bb = (bb + 1) & p.bucket_mask;
+        const ulonglong2 c0 = __ldg(reinterpret_cast<const ulonglong2*>(p.table + 4 * bb));
+        const ulonglong2 c1 = __ldg(reinterpret_cast<const ulonglong2*>(p.table + 4 * bb) + 1);
+        found = (c0.x == m.key) | (c0.y == m.key) | (c1.x == m.key) | (c1.y == m.key);
+        full = (c1.y != TABLE_EMPTY);
+    }
+    const int skipped = m.in_range && found;
+    if (!m.in_range || found) m.u = ~m.u;      // u >= 0 always: the complement is negative = "not live"
+    return skipped;
+}
+
+template <int G, bool ATOMIC, int D, int MINB>
+__global__ void __launch_bounds__(256, MINB) bpr_hogwild_stream_kernel(const BprParams p)
+{
+    extern __shared__ __align__(16) unsigned char stream_smem[];
+    constexpr int SLOT = 3 * G * 16;            // bytes of one sample's three rows (G lanes x 16 B each)
+    const int lane = threadIdx.x & 31;
+    const int lg = lane & (G - 1);
+    const int gbase = lane & ~(G - 1);
+    const unsigned gmask = group_mask<G>();
+    const int n_units = p.k / 4;                // float4 units of a row (<= G)
+    const bool col = lg < n_units;              // this lane owns a column of the rows
+    const int64_t groups_per_block = blockDim.x / G;
+    const int64_t n_groups = (int64_t)gridDim.x * groups_per_block;
+    const int64_t gid = (int64_t)blockIdx.x * groups_per_block + threadIdx.x / G;
+    const int64_t n_chunks = (p.n_samples + G - 1) / G;
+    const size_t k = (size_t)p.k;
+    const float lr = p.lr, lrreg = p.lr * p.reg;
+    // this lane's 16-byte column of the group's D slots: slot s, row r (0 = U, 1 = V+, 2 = V-) at my_s + s*SLOT + r*G*16
+    const uint32_t my_s = (uint32_t)__cvta_generic_to_shared(stream_smem) + (uint32_t)(threadIdx.x / G) * (D * SLOT) + lg * 16;
+
+    unsigned int n_correct = 0, n_skipped = 0;
+    ChunkMeta cur, nxt;
+    cur.u = cur.i = cur.j = -1;
+    int64_t c = gid;
+    if (c < n_chunks) {
+        meta_step_a<G>(p, cur, c, lg);
+        meta_step_b(p, cur);
+        n_skipped += meta_step_c(p, cur);
+    }
+    for (; c < n_chunks; c += n_groups) {
+        const int64_t cn = c + n_groups;
+        const bool has_next = cn < n_chunks;
+        nxt = cur;
+        float bslot = 0.f;                      // lane 2s / 2s+1 of the group: B[i] / B[j] of the sample in slot s
+        // rows (and biases) of sample t of the chunk -> slot t % D; one commit group per sample, live or not
+        auto issue = [&](int t) {
+            const int32_t su = __shfl_sync(gmask, cur.u, gbase + t);
+            const int32_t si = __shfl_sync(gmask, cur.i, gbase + t);
+            const int32_t sj = __shfl_sync(gmask, cur.j, gbase + t);
+            if (su >= 0) {
+                const int s = t % D;
+                if (col) {
+                    const uint32_t dst = my_s + s * SLOT;
+                    cp_async_16(dst, p.U + (size_t)su * k + lg * 4);
+                    cp_async_16(dst + G * 16, p.V + (size_t)si * k + lg * 4);
+                    cp_async_16(dst + 2 * G * 16, p.V + (size_t)sj * k + lg * 4);
+                }
+                if (lg == 2 * s) bslot = __ldcg(p.B + si);
+                if (lg == 2 * s + 1) bslot = __ldcg(p.B + sj);
+            }
+            cp_async_commit();
+        };
+#pragma unroll
+        for (int t = 0; t < D; ++t) issue(t);
+#pragma unroll 2
+        for (int t = 0; t < G; ++t) {
+            // ---- the next chunk's sampling, one step per quarter of this chunk
+            if (has_next) {
+                if (t == 0) meta_step_a<G>(p, nxt, cn, lg);
+                else if (t == G / 4) meta_step_b(p, nxt);
+                else if (t == (3 * G) / 4) n_skipped += meta_step_c(p, nxt);
+            }
+            // ---- sample t: rows have landed in slot t % D
+            cp_async_wait<D - 1>();
+            const int s = t % D;
+            const int32_t su = __shfl_sync(gmask, cur.u, gbase + t);
+            const int32_t si = __shfl_sync(gmask, cur.i, gbase + t);
+            const int32_t sj = __shfl_sync(gmask, cur.j, gbase + t);
+            const float bi = __shfl_sync(gmask, bslot, gbase + 2 * s);
+            const float bj = __shfl_sync(gmask, bslot, gbase + 2 * s + 1);
+            float4 u4 = make_float4(0.f, 0.f, 0.f, 0.f), vi4 = u4, vj4 = u4;
+            if (su >= 0 && col) {
+                const uint32_t src = my_s + s * SLOT;
+                u4 = lds_f4(src); vi4 = lds_f4(src + G * 16); vj4 = lds_f4(src + 2 * G * 16);
+            }
+            if (t + D < G) issue(t + D); else cp_async_commit();      // refill the slot just read (same lane, same bytes)
+            if (su < 0) continue;                   // group-uniform: skipped / out of range
+            const float dx = vi4.x - vj4.x, dy = vi4.y - vj4.y, dz = vi4.z - vj4.z, dw = vi4.w - vj4.w;
+            float part = u4.x * dx;
+            part = fmaf(u4.y, dy, part); part = fmaf(u4.z, dz, part); part = fmaf(u4.w, dw, part);
+            const float score = (bi - bj) + group_sum<G>(part);       // recom_bpr.pyx:249-251
+            float z;
+            if (p.hinge) {                              // recom_mmmf.pyx:137-139
+                if (score > 0.f) { ++n_correct; continue; }
+                z = 1.f;
+            } else {
+                z = bpr_z(score, p.exact_exp);
+                n_correct += (z < .5f);
+            }
+            const float a = lr * z;                     // delta = lr (z x - reg y) = a x - lrreg y
+            float* pu = p.U + (size_t)su * k + lg * 4;
+            float* pi = p.V + (size_t)si * k + lg * 4;
+            float* pj = p.V + (size_t)sj * k + lg * 4;
+            if (col) {
+                if (ATOMIC) {
+                    if (!(p.debug_skip & 1))
+                        red_add_v4(pu, fmaf(a, dx, -lrreg * u4.x), fmaf(a, dy, -lrreg * u4.y), fmaf(a, dz, -lrreg * u4.z), fmaf(a, dw, -lrreg * u4.w));
+                    if (!(p.debug_skip & 2))
+                        red_add_v4(pi, fmaf(a, u4.x, -lrreg * vi4.x), fmaf(a, u4.y, -lrreg * vi4.y), fmaf(a, u4.z, -lrreg * vi4.z), fmaf(a, u4.w, -lrreg * vi4.w));
+                    if (!(p.debug_skip & 4))
+                        red_add_v4(pj, fmaf(-a, u4.x, -lrreg * vj4.x), fmaf(-a, u4.y, -lrreg * vj4.y), fmaf(-a, u4.z, -lrreg * vj4.z), fmaf(-a, u4.w, -lrreg * vj4.w));
+                } else {
+                    __stcg(reinterpret_cast<float4*>(pu), make_float4(u4.x + fmaf(a, dx, -lrreg * u4.x), u4.y + fmaf(a, dy, -lrreg * u4.y),
+                                                                      u4.z + fmaf(a, dz, -lrreg * u4.z), u4.w + fmaf(a, dw, -lrreg * u4.w)));
+                    __stcg(reinterpret_cast<float4*>(pi), make_float4(vi4.x + fmaf(a, u4.x, -lrreg * vi4.x), vi4.y + fmaf(a, u4.y, -lrreg * vi4.y),
+                                                                      vi4.z + fmaf(a, u4.z, -lrreg * vi4.z), vi4.w + fmaf(a, u4.w, -lrreg * vi4.w)));
+                    __stcg(reinterpret_cast<float4*>(pj), make_float4(vj4.x + fmaf(-a, u4.x, -lrreg * vj4.x), vj4.y + fmaf(-a, u4.y, -lrreg * vj4.y),
+                                                                      vj4.z + fmaf(-a, u4.z, -lrreg * vj4.z), vj4.w + fmaf(-a, u4.w, -lrreg * vj4.w)));
+                }
+            }
+            if (p.use_bias && lg == 0) {
+                if (ATOMIC) {
+                    red_add_f32(p.B + si, a - lrreg * bi);
+                    red_add_f32(p.B + sj, -a - lrreg * bj);
+                } else {
+                    __stcg(p.B + si, bi + (a - lrreg * bi));
+                    __stcg(p.B + sj, bj + (-a - lrreg * bj));
+                }
+            }
+        }
+        cur = nxt;
+    }
+    cp_async_wait<0>();
+
+    __shared__ unsigned int sh_stats[2];
+    if (threadIdx.x < 2) sh_stats[threadIdx.x] = 0;
+    __syncthreads();
+    unsigned int cc = (lg == 0) ? n_correct : 0u, sk = n_skipped;     // skips were counted per lane
+    cc = __reduce_add_sync(0xffffffffu, cc);
+    sk = __reduce_add_sync(0xffffffffu, sk);
+    if (lane == 0) {
+        atomicAdd(&sh_stats[0], cc);
+        atomicAdd(&sh_stats[1], sk);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atomicAdd(p.stats + 0, (unsigned long long)sh_stats[0]);
+        atomicAdd(p.stats + 1, (unsigned long long)sh_stats[1]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Parity mode: one warp, serial-equivalent.  Unfused f32 arithmetic in the operation order
 // of recom_bpr.pyx:249-267 (the dot is a lane-strided partial sum + shuffle tree).
 struct ReplayParams {
@@ -656,18 +871,48 @@ static int launch_hogwild_chunk(const BprParams& p, cudaStream_t st, const Hogwi
     return B200_OK;
 }
 
+template <int G, bool ATOMIC, int D, int MINB>
+static int launch_hogwild_stream(const BprParams& p, cudaStream_t st, const HogwildTune& tune)
+{
+    auto kern = bpr_hogwild_stream_kernel<G, ATOMIC, D, MINB>;
+    const int threads = 256;
+    const size_t smem = (size_t)(threads / G) * D * (3 * G * 16);
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+    if (occ < 1) occ = 1;
+    if (tune.blocks_per_sm > 0 && tune.blocks_per_sm < occ) occ = tune.blocks_per_sm;
+    const int64_t groups_per_block = threads / G;
+    const int64_t n_chunks = (p.n_samples + G - 1) / G;
+    int64_t want = (n_chunks + groups_per_block - 1) / groups_per_block;
+    int64_t grid = (int64_t)sm_count() * occ;
+    if (want < grid) grid = want;
+    // staleness bound (see launch_hogwild_s): a group has D samples in flight
+    const int64_t cap = (p.max_groups / D + groups_per_block - 1) / groups_per_block;
+    if (cap < grid) grid = cap;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, threads, smem, st>>>(p); ::b200::count_launch();
+    B200_CUDA(cudaGetLastError());
+    return B200_OK;
+}
+
 template <int G, int NPL, bool VEC, bool ATOMIC>
 static int launch_hogwild(const BprParams& p, cudaStream_t st)
 {
     // samples in flight per group: bounded by the register footprint of the 3*S row fragments
     constexpr int E = NPL * (VEC ? 4 : 1);
     const HogwildTune tune = read_tune();
+    if constexpr (VEC && NPL == 1 && G >= 16) {
+        // one float4 per lane (k % 4 == 0, 52 <= k <= 128): rows staged in shared memory, 4 samples in flight per group
+        if (tune.S == 0) return launch_hogwild_stream<G, ATOMIC, 4, 4>(p, st, tune);
+        if (tune.S == 2) return launch_hogwild_stream<G, ATOMIC, 2, 4>(p, st, tune);          // A/B: depth 2
+    }
     if constexpr (E <= 8) {
         // measured on B200 (profiles/r01_bpr_scatter_experiments.txt): 16-lane groups run best two row-gathers
         // ahead at 3 blocks/SM (4.14 vs 3.90 G samples/s on C2); 32-lane groups (k = 128: 512-byte rows, V beyond
         // the L2 at 1 M items) gain nothing from the second slot but 15 % from a fourth resident block
         // (60 registers; 1.55 vs 1.35 G updates/s on the configs[2] shard shape)
-        if (tune.S == 0) {
+        if (tune.S == 0 || tune.S == 64) {       // (64 = the register-staged chunk kernel where the streamed one is the default)
             if (G >= 32) return launch_hogwild_chunk<G, NPL, VEC, ATOMIC, 4, 1>(p, st, tune);
             return launch_hogwild_chunk<G, NPL, VEC, ATOMIC, 3, 2>(p, st, tune);
         }

@@ -449,6 +449,7 @@ struct RankTcParams {
     float* __restrict__ row_tau;           // [n_ut * TM][MAX_ST] final filter tau - 2 eps of the strip (scaled units): the finish drops entries below the row's largest
     float* __restrict__ dump;              // debug: dense approximate scores [n_ut*TM][n_it*TN] or null
     int debug;                             // B200_RANK_DEBUG: timing only: 1 = epilogue hands the accumulators straight back, 2 = tcgen05.ld only;
+                                           // 8 = screening only (no candidate is listed);
                                            // 4 = raise schedule with ratio 1.41 instead of 2 (results stay exact)
 };
 
@@ -900,6 +901,7 @@ __global__ void __launch_bounds__(threads_for(ST), 1) rank_tc_kernel(const RankT
             st.tau = -INFINITY; st.hi = -INFINITY;
             tau_share[half * TM + q * 32 + lane] = ((unsigned long long)(uint32_t)ut << 32) | 0xff800000u;   // -inf
             st.tau_f = valid ? -1.0e38f : INFINITY;       // padding items score -inf: never above the filter
+            if (p.debug & 8) st.tau_f = INFINITY;         // timing experiment: screening only (nothing is ever listed)
             int flag = 0;
             float* dump_row = DUMP ? p.dump + (size_t)(valid ? row : 0) * ((size_t)p.n_it * TN) : nullptr;
             int next_sched = 2;

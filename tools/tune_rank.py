@@ -22,14 +22,24 @@ def run(n_users, n_items, k, n_q, topk, n_excl, reps=3):
         ex_idx = torch.sort(ex, dim=1)[0].contiguous().view(-1)
         ex_ptr = (torch.arange(n_q + 1, device=dev, dtype=torch.int64) * n_excl).contiguous()
     L = load()
+    if os.environ.get("B200_ALT_LIB"):          # A/B against another build of the library (only the two rank entry points are bound)
+        import ctypes
+        L = ctypes.CDLL(os.environ["B200_ALT_LIB"])
+        vp, i64, ci = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
+        L.b200_rank_topk_workspace_bytes.restype = i64
+        L.b200_rank_topk_workspace_bytes.argtypes = [i64, i64, ci, ci]
+        L.b200_rank_topk.restype = ci
+        L.b200_rank_topk.argtypes = [vp, vp, i64, vp, i64, ci, vp, vp, vp, vp, ci, vp, vp, vp, i64, vp]
+        L.b200_last_error.restype = ctypes.c_char_p
     ids = torch.empty((n_q, topk), dtype=torch.int32, device=dev)
     sc = torch.empty((n_q, topk), dtype=torch.float32, device=dev)
     nb = int(L.b200_rank_topk_workspace_bytes(n_q, n_items, k, topk))
     ws = torch.empty(max(nb, 16), dtype=torch.uint8, device=dev)
 
     def go():
-        check(L.b200_rank_topk(ptr(U), ptr(uidx), n_q, ptr(V), n_items, k, ptr(B), None, ptr(ex_ptr), ptr(ex_idx), topk,
-                               ptr(ids), ptr(sc), ptr(ws), nb, current_stream()), "b200_rank_topk")
+        rc = L.b200_rank_topk(ptr(U), ptr(uidx), n_q, ptr(V), n_items, k, ptr(B), None, ptr(ex_ptr), ptr(ex_idx), topk,
+                              ptr(ids), ptr(sc), ptr(ws), nb, current_stream())
+        assert rc == 0, L.b200_last_error()
     go()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
