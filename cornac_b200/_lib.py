@@ -30,6 +30,8 @@ SIGNATURES = {
     "b200_bpr_epoch": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _int, _f32, _f32, _int,
                               _u64, _u64, _u64, _c.c_uint, _vp, _vp]),
     "b200_bpr_draw_host": (_int, [_u64, _u64, _u64, _i64, _i64, _i64, _vp, _vp]),
+    "b200_bpr_draw_host2": (_int, [_u64, _u64, _u64, _i64, _i64, _i64, _u32, _u32, _vp, _vp]),
+    "b200_bpr_block_plan": (_int, [_i64, _i64, _int, _vp, _vp]),
     "b200_bpr_epoch_replay": (_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _int, _f32, _f32, _int,
                                      _c.c_uint, _vp, _vp]),
     "b200_mt_sampler_create": (_vp, [_u32]),
@@ -61,6 +63,7 @@ SGD_EXACT_EXP = 2
 SGD_UNBOUNDED = 4
 BPR_NEG_WEIGHTED = 8
 BPR_LOSS_HINGE = 16
+BPR_BLOCKED = 32
 METRIC_NDCG, METRIC_PRECISION, METRIC_RECALL, METRIC_FMEASURE, METRIC_HIT, METRIC_NCRR = range(6)
 
 _lib = None

@@ -15,17 +15,101 @@ class DeviceScoringMixin:
     """Expects the subclass to provide `_b200_host_params()` returning
     (U, V, item_base, user_off_vector_or_None, n_score_items) as numpy arrays."""
 
-    _B200_IGNORED = ("_b200_dev",)
+    _B200_IGNORED = ("_b200_dev", "_b200_eval_cache")
+    _B200_EVAL_CACHE_BYTES = 1 << 30            # host budget of the transform() cache (score rows of the test users)
+    _B200_EVAL_TOP = 1024                       # length of the cached per-user global ranking
 
     def _b200_register_ignored(self):
         for a in self._B200_IGNORED:
             if a not in self.ignored_attrs:
                 self.ignored_attrs.append(a)
         self._b200_dev = None
+        self._b200_eval_cache = None
 
     # ---- device cache --------------------------------------------------------------
     def _b200_invalidate(self):
         self._b200_dev = None
+        self._b200_eval_cache = None
+
+    # ---- Recommender.transform: batch-precompute what the per-user eval loop will ask for -------------------------
+    def transform(self, test_set):
+        """`Recommender.transform` hook (cornac/models/recommender.py:410-421), called once by `BaseMethod.evaluate`
+        (cornac/eval_methods/base_method.py:746, 766) before the per-user loops of rating_eval / ranking_eval.
+
+        All users of `test_set` are scored in a few batched kernel calls (b200_score_batch, exact scores) and, per user,
+        the head of the global ranking (score desc, id asc) is selected on the device (b200_topk_rows); both are kept in
+        host memory.  `rank()` / `score()` of a cached user are then pure host work -- no kernel launch, no device copy
+        per user -- and return exactly what the uncached path returns: the top-k of ANY candidate set is the first k
+        members of the global ranking that belong to it.  The cache is skipped when it would not fit the host budget
+        (then, and for callers that never call transform -- hyperopt, cornac/hyperopt.py:162 -- rank() falls back to the
+        per-user device path); it is dropped whenever the parameters change (fit)."""
+        self._b200_eval_cache = None
+        try:
+            users = np.unique(np.asarray(test_set.uir_tuple[0], dtype=np.int64))
+        except Exception:
+            return
+        self._b200_precompute_users(users)
+
+    def _b200_precompute_users(self, users):
+        d = self._b200_device()
+        n_rows, n_score = int(d["U"].shape[0]), int(d["n_items"])
+        users = users[(users >= 0) & (users < n_rows)]
+        if len(users) == 0 or len(users) * n_score * 4 > self._B200_EVAL_CACHE_BYTES:
+            return
+        m_top = min(n_score, self._B200_EVAL_TOP)
+        scores_h = np.empty((len(users), n_score), dtype=np.float32)
+        top_h = np.empty((len(users), m_top), dtype=np.int32)
+        batch = max(1, min(len(users), (256 << 20) // (4 * n_score)))
+        for b0 in range(0, len(users), batch):
+            ub = users[b0:b0 + batch]
+            uidx = engine.to_device(ub, torch.int64)
+            uoff = None if d["user_off"] is None else d["user_off"][uidx].contiguous()
+            sc = engine.score_batch(d["U"], d["V"], user_idx=uidx, item_base=d["item_base"], user_off=uoff, n_items=n_score)
+            ids, _ = engine.topk_rows(sc, m_top)
+            scores_h[b0:b0 + len(ub)] = sc.cpu().numpy()
+            top_h[b0:b0 + len(ub)] = ids.cpu().numpy()
+        pos_of = np.full(n_rows, -1, dtype=np.int64)
+        pos_of[users] = np.arange(len(users))
+        self._b200_eval_cache = dict(pos_of=pos_of, scores=scores_h, top=top_h)
+
+    def _b200_cached_scores(self, user_idx):
+        """The cached full score vector of a user (read-only view) or None."""
+        c = getattr(self, "_b200_eval_cache", None)
+        if c is None or not (0 <= user_idx < len(c["pos_of"])) or c["pos_of"][user_idx] < 0:
+            return None
+        return c["scores"][c["pos_of"][user_idx]]
+
+    def _b200_cached_rank(self, user_idx, item_indices, k):
+        """`Recommender.rank` (recommender.py:476-530) from the transform() cache, or None on a miss: same
+        (ranked_items, item_scores) as `_b200_rank` on the device scores."""
+        row = self._b200_cached_scores(user_idx)
+        if row is None:
+            return None
+        c = self._b200_eval_cache
+        total = self.total_items
+        if len(row) == total:
+            all_scores = row
+        else:                                               # unknown items get the MIN score (recommender.py:507-511)
+            all_scores = np.full(total, row.min(), dtype=np.float32)
+            all_scores[: len(row)] = row
+        item_indices = np.arange(self.num_items) if item_indices is None else np.asarray(item_indices)
+        item_scores = all_scores[item_indices]
+        n_cand = len(item_indices)
+        if k == -1 or k >= n_cand:
+            order = np.lexsort((item_indices, -item_scores.astype(np.float64)))
+            return item_indices[order], item_scores
+        top = c["top"][c["pos_of"][user_idx]]
+        member = np.zeros(total, dtype=bool)
+        member[item_indices] = True
+        surv = top[member[top]]
+        if len(surv) >= k:
+            topk = surv[:k].astype(item_indices.dtype)
+        else:                                               # the cached head holds fewer than k candidates: exact host selection
+            order = np.lexsort((item_indices, -item_scores.astype(np.float64)))
+            topk = item_indices[order[:k]]
+        in_top = np.zeros(total, dtype=bool)
+        in_top[topk] = True
+        return np.concatenate([topk, item_indices[~in_top[item_indices]]]), item_scores
 
     def _b200_device(self):
         dev = getattr(self, "_b200_dev", None)

@@ -119,16 +119,26 @@ extern "C" int b200_delta_apply(float* x, float* snapshot, const float* delta, i
     return B200_OK;
 }
 
-extern "C" int b200_bpr_draw_host(uint64_t seed, uint64_t epoch, uint64_t sample_base, int64_t n,
-                                  int64_t nnz, int64_t n_neg, int64_t* out_i_index, int32_t* out_j_id)
+extern "C" int b200_bpr_draw_host2(uint64_t seed, uint64_t epoch, uint64_t sample_base, int64_t n,
+                                   int64_t nnz, int64_t n_neg, uint32_t n_windows, uint32_t n_blocks,
+                                   int64_t* out_i_index, int32_t* out_j_id)
 {
     B200_REQUIRE(n >= 0 && nnz >= 1 && n_neg >= 1 && (n == 0 || (out_i_index && out_j_id)), "b200_bpr_draw_host: bad argument");
+    const SampleLaw law = make_law(nnz, n_neg, n_windows, n_blocks, epoch);
     for (int64_t t = 0; t < n; ++t) {
         const uint64_t s = sample_base + (uint64_t)t;
         const Philox4 r = philox4x32_10((uint32_t)s, (uint32_t)(s >> 32), (uint32_t)epoch, (uint32_t)(epoch >> 32),
                                         (uint32_t)seed, (uint32_t)(seed >> 32));
-        out_i_index[t] = (int64_t)range64(r.x, r.y, (uint64_t)nnz);
-        out_j_id[t] = (int32_t)range64(r.z, r.w, (uint64_t)n_neg);
+        int64_t i_lo, i_len, j_lo, j_len;
+        law_ranges(law, s, i_lo, i_len, j_lo, j_len);
+        out_i_index[t] = i_lo + (int64_t)range64(r.x, r.y, (uint64_t)i_len);
+        out_j_id[t] = (int32_t)(j_lo + (int64_t)range64(r.z, r.w, (uint64_t)j_len));
     }
     return B200_OK;
+}
+
+extern "C" int b200_bpr_draw_host(uint64_t seed, uint64_t epoch, uint64_t sample_base, int64_t n,
+                                  int64_t nnz, int64_t n_neg, int64_t* out_i_index, int32_t* out_j_id)
+{
+    return b200_bpr_draw_host2(seed, epoch, sample_base, n, nnz, n_neg, 1, 1, out_i_index, out_j_id);
 }

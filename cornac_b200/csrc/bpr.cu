@@ -48,6 +48,7 @@ struct BprParams {
     int debug_skip;              // profiling only (B200_BPR_DEBUG_SKIP): bit0 U, bit1 V+, bit2 V- scatter off
     int hinge;                   // MMMF (recom_mmmf.pyx:129-154): skip correctly ranked pairs, z = 1 otherwise
     int neg_weighted;            // WBPR: negatives drawn from the interaction list (popularity-weighted)
+    SampleLaw law;               // unblocked or cache-blocked sample order (common.cuh)
     float* U;
     float* V;
     float* B;
@@ -103,9 +104,11 @@ __global__ void __launch_bounds__(256, MINB) bpr_hogwild_kernel(const BprParams 
             const uint64_t s = p.sample_base + (uint64_t)(s0 + t);
             live[t] = (s0 + t) < p.n_samples;
             Philox4 r = philox4x32_10((uint32_t)s, (uint32_t)(s >> 32), p.epoch_lo, p.epoch_hi, p.seed_lo, p.seed_hi);
-            const int64_t ii = (int64_t)range64(r.x, r.y, (uint64_t)p.nnz);
+            int64_t i_lo, i_len, j_lo, j_len;
+            law_ranges(p.law, s, i_lo, i_len, j_lo, j_len);
+            const int64_t ii = i_lo + (int64_t)range64(r.x, r.y, (uint64_t)i_len);
             jt[t] = p.neg_weighted ? __ldg(p.pairs + range64(r.z, r.w, (uint64_t)p.nnz)).y
-                                   : (int32_t)range64(r.z, r.w, (uint64_t)p.n_neg);
+                                   : (int32_t)(j_lo + (int64_t)range64(r.z, r.w, (uint64_t)j_len));
             pr[t] = __ldg(p.pairs + ii);
             row_load<G, NPL, VEC>(fj[t], p.V + (size_t)jt[t] * k, lg, n_units);
             bj[t] = __ldcg(p.B + jt[t]);
@@ -250,9 +253,11 @@ __global__ void __launch_bounds__(256, MINB) bpr_hogwild_chunk_kernel(const BprP
         int mlive = sl < p.n_samples;
         const uint64_t s = p.sample_base + (uint64_t)sl;
         const Philox4 r = philox4x32_10((uint32_t)s, (uint32_t)(s >> 32), p.epoch_lo, p.epoch_hi, p.seed_lo, p.seed_hi);
-        const int64_t ii = (int64_t)range64(r.x, r.y, (uint64_t)p.nnz);
+        int64_t i_lo, i_len, j_lo, j_len;
+        law_ranges(p.law, s, i_lo, i_len, j_lo, j_len);
+        const int64_t ii = i_lo + (int64_t)range64(r.x, r.y, (uint64_t)i_len);
         const int32_t mj = p.neg_weighted ? __ldg(p.pairs + range64(r.z, r.w, (uint64_t)p.nnz)).y     // recom_wbpr.pyx:131
-                                          : (int32_t)range64(r.z, r.w, (uint64_t)p.n_neg);
+                                          : (int32_t)(j_lo + (int64_t)range64(r.z, r.w, (uint64_t)j_len));
         const int2 pr = __ldg(p.pairs + ii);
         const int32_t mu = pr.x, mi = pr.y;
         {
@@ -405,9 +410,11 @@ __device__ __forceinline__ void meta_step_a(const BprParams& p, ChunkMeta& m, in
     m.in_range = sl < p.n_samples;
     const uint64_t s = p.sample_base + (uint64_t)sl;
     const Philox4 r = philox4x32_10((uint32_t)s, (uint32_t)(s >> 32), p.epoch_lo, p.epoch_hi, p.seed_lo, p.seed_hi);
-    const int64_t ii = (int64_t)range64(r.x, r.y, (uint64_t)p.nnz);
+    int64_t i_lo, i_len, j_lo, j_len;
+    law_ranges(p.law, s, i_lo, i_len, j_lo, j_len);
+    const int64_t ii = i_lo + (int64_t)range64(r.x, r.y, (uint64_t)i_len);
     m.j = p.neg_weighted ? __ldg(p.pairs + range64(r.z, r.w, (uint64_t)p.nnz)).y     // recom_wbpr.pyx:131
-                         : (int32_t)range64(r.z, r.w, (uint64_t)p.n_neg);
+                         : (int32_t)(j_lo + (int64_t)range64(r.z, r.w, (uint64_t)j_len));
     m.pr = __ldg(p.pairs + ii);
 }
 __device__ __forceinline__ void meta_step_b(const BprParams& p, ChunkMeta& m)
@@ -903,9 +910,13 @@ static int launch_hogwild(const BprParams& p, cudaStream_t st)
     constexpr int E = NPL * (VEC ? 4 : 1);
     const HogwildTune tune = read_tune();
     if constexpr (VEC && NPL == 1 && G >= 16) {
-        // one float4 per lane (k % 4 == 0, 52 <= k <= 128): rows staged in shared memory, 4 samples in flight per group
-        if (tune.S == 0) return launch_hogwild_stream<G, ATOMIC, 4, 4>(p, st, tune);
-        if (tune.S == 2) return launch_hogwild_stream<G, ATOMIC, 2, 4>(p, st, tune);          // A/B: depth 2
+        // one float4 per lane (k % 4 == 0, 52 <= k <= 128): rows staged in shared memory.  Measured on the configs[2] block
+        // (1.25 M x 1 M x 125 M, k = 128; profiles/r02_bpr.md): streamed, 2 samples in flight, 70.6 ms / epoch; 4 in
+        // flight 82.3 ms (the memory system, not the warp, is the queue); register-staged chunk kernel 81.3 ms.
+        // 16-lane groups (k <= 64, V L2-resident at configs[1]) stay on the chunk kernel: 24.2 ms vs 35.7 ms streamed x4.
+        if (tune.S == 0 && G >= 32) return launch_hogwild_stream<G, ATOMIC, 2, 4>(p, st, tune);
+        if (tune.S == 2) return launch_hogwild_stream<G, ATOMIC, 2, 4>(p, st, tune);          // A/B: force the streamed kernels
+        if (tune.S == 4) return launch_hogwild_stream<G, ATOMIC, 4, 4>(p, st, tune);
     }
     if constexpr (E <= 8) {
         // measured on B200 (profiles/r01_bpr_scatter_experiments.txt): 16-lane groups run best two row-gathers
@@ -958,6 +969,24 @@ extern "C" int b200_bpr_prepare(const int32_t* indptr, const int32_t* indices, i
     return B200_OK;
 }
 
+// Windows of the interaction list / blocks of the items such that one window's user rows and one block's item rows
+// (40 MB each) stay resident in the 126 MB L2 next to the hot positive rows; 1 / 1 when the matrix already fits.
+extern "C" int b200_bpr_block_plan(int64_t n_users, int64_t n_neg, int k, uint32_t* n_windows, uint32_t* n_blocks)
+{
+    B200_REQUIRE(n_users >= 1 && n_neg >= 1 && k >= 1 && n_windows && n_blocks, "b200_bpr_block_plan: bad argument");
+    const double part = 40.0 * 1024 * 1024;
+    const double ub = (double)n_users * k * 4, vb = (double)n_neg * k * 4;
+    uint32_t wn = 1, bn = 1;
+    if (ub + vb > 2 * part) {
+        wn = (uint32_t)((ub + part - 1) / part);
+        bn = (uint32_t)((vb + part - 1) / part);
+        if (wn < 1) wn = 1;
+        if (bn < 1) bn = 1;
+    }
+    *n_windows = wn; *n_blocks = bn;
+    return B200_OK;
+}
+
 extern "C" int b200_bpr_epoch(const int32_t* pairs, const uint64_t* table, int64_t table_slots,
                               int64_t nnz, int64_t n_users, int64_t n_neg, int64_t n_samples,
                               float* U, float* V, float* B, int k,
@@ -989,6 +1018,20 @@ extern "C" int b200_bpr_epoch(const int32_t* pairs, const uint64_t* table, int64
     }
     p.neg_weighted = (flags & B200_BPR_NEG_WEIGHTED) ? 1 : 0;
     p.hinge = (flags & B200_BPR_LOSS_HINGE) ? 1 : 0;
+    {
+        uint32_t wn = 1, bn = 1;
+        if (flags & B200_BPR_BLOCKED) {
+            const int rc = b200_bpr_block_plan(n_users, n_neg, k, &wn, &bn);
+            if (rc) return rc;
+            if (p.neg_weighted) bn = 1;      // WBPR negatives follow the interaction list: only the user side is blocked
+        }
+        p.law = make_law(nnz, n_neg, wn, bn, epoch);
+        if (wn > 1 || bn > 1) {              // the staleness cap counts the rows of ONE window / block
+            int64_t rows = (n_users / wn) < (n_neg / bn) ? (n_users / wn) : (n_neg / bn);
+            const int64_t cap = rows / 4 < 16 ? 16 : rows / 4;
+            if (!(flags & B200_SGD_UNBOUNDED) && cap < p.max_groups) p.max_groups = cap;
+        }
+    }
     p.debug_skip = 0;
     if (const char* e = getenv("B200_BPR_DEBUG_SKIP")) p.debug_skip = atoi(e);
     p.U = U; p.V = V; p.B = B; p.k = k; p.lr = lr; p.reg = reg; p.use_bias = use_bias;

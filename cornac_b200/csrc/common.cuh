@@ -75,6 +75,59 @@ __host__ __device__ __forceinline__ uint64_t range64(uint32_t lo, uint32_t hi, u
 }
 
 // ---------------------------------------------------------------------------
+// The sample law of the throughput-mode BPR epoch, shared by the kernels and by b200_bpr_draw_host.
+// Unblocked (wn = bn = 1): sample s draws i_index uniformly from [0, nnz) and j uniformly from [0, n_neg) -- the
+// reference's law (recom_bpr.pyx:237-239).
+// Cache-blocked (B200_BPR_BLOCKED): the SAME marginal law -- every interaction is drawn once per epoch in expectation,
+// every negative is uniform over all items and independent of the interaction -- but the epoch's nnz samples are
+// visited in an order that keeps the rows they touch in the L2: the interaction list (CSR order = grouped by user) is
+// cut into `wn` windows and the items into `bn` blocks; the epoch is cut into wn * bn runs of s_sub = ceil(nnz / (wn bn))
+// consecutive sample indices; run (w, b) draws its interactions from window w and its negatives from item block
+// (b + epoch) % bn.  Every window meets every item block once per epoch, so each user still sees negatives from the whole
+// catalogue every epoch; what changes is only the order in which the triplets of an epoch are applied, which Hogwild
+// does not define anyway (stratified SGD: Gemulla et al., KDD 2011).
+struct SampleLaw {
+    int64_t nnz, n_neg;
+    int64_t s_sub;          // samples per (window, block) run
+    uint32_t wn, bn;        // windows of the interaction list / blocks of the items (1, 1 = unblocked)
+    uint32_t epoch_mod_bn;
+    int64_t w_base, b_base; // floor(nnz / wn), floor(n_neg / bn): window w = [w w_base + min(w, w_rem), ...) of w_base (+1) entries
+    uint32_t w_rem, b_rem;
+};
+
+__host__ __device__ __forceinline__ SampleLaw make_law(int64_t nnz, int64_t n_neg, uint32_t wn, uint32_t bn, uint64_t epoch)
+{
+    SampleLaw L;
+    L.nnz = nnz; L.n_neg = n_neg;
+    L.wn = wn < 1 ? 1 : wn; L.bn = bn < 1 ? 1 : bn;
+    if ((int64_t)L.wn > nnz) L.wn = nnz > 0 ? (uint32_t)nnz : 1;
+    if ((int64_t)L.bn > n_neg) L.bn = n_neg > 0 ? (uint32_t)n_neg : 1;
+    const int64_t runs = (int64_t)L.wn * L.bn;
+    L.s_sub = (nnz + runs - 1) / runs;
+    if (L.s_sub < 1) L.s_sub = 1;
+    L.epoch_mod_bn = (uint32_t)(epoch % L.bn);
+    L.w_base = nnz / L.wn; L.w_rem = (uint32_t)(nnz % L.wn);
+    L.b_base = n_neg / L.bn; L.b_rem = (uint32_t)(n_neg % L.bn);
+    return L;
+}
+
+// ranges [lo, lo + len) the sample with epoch-local index s draws its interaction index and its negative from
+__host__ __device__ __forceinline__ void law_ranges(const SampleLaw& L, uint64_t s, int64_t& i_lo, int64_t& i_len,
+                                                    int64_t& j_lo, int64_t& j_len)
+{
+    if (L.wn == 1 && L.bn == 1) { i_lo = 0; i_len = L.nnz; j_lo = 0; j_len = L.n_neg; return; }
+    const uint32_t runs = L.wn * L.bn;
+    const uint32_t run = (uint32_t)((s / (uint64_t)L.s_sub) % runs);           // the one 64-bit division of the law
+    const uint32_t w = run / L.bn;
+    uint32_t b = run - w * L.bn + L.epoch_mod_bn;
+    if (b >= L.bn) b -= L.bn;
+    i_lo = (int64_t)w * L.w_base + (w < L.w_rem ? w : L.w_rem);
+    i_len = L.w_base + (w < L.w_rem ? 1 : 0);
+    j_lo = (int64_t)b * L.b_base + (b < L.b_rem ? b : L.b_rem);
+    j_len = L.b_base + (b < L.b_rem ? 1 : 0);
+}
+
+// ---------------------------------------------------------------------------
 // sub-warp (G-lane group) sum; G is a power of two <= 32, groups are aligned.  The shuffle
 // mask names only the group's own lanes, so groups of one warp may diverge (different trip
 // counts, skipped samples) without dead-locking each other.

@@ -443,7 +443,7 @@ struct RankTcParams {
     const int32_t* __restrict__ excl_indices;
     int64_t n_rows;                        // valid rows in this chunk
     int n_ut, n_it, kp, topk;
-    float* __restrict__ lists;             // [n_ut * 4 ST warps][32 lanes] thread-private blocks: [cap scores f32][cap item ids i32]
+    unsigned long long* __restrict__ lists;    // [n_ut * 4 ST warps][32 lanes][cap] thread-private lists: (score bits << 32) | item id
     int* __restrict__ row_cnt;             // [n_ut * TM][MAX_ST strips]
     int* __restrict__ row_flag;            // [n_ut * TM][MAX_ST] 1 = list overflow -> exact path
     float* __restrict__ row_tau;           // [n_ut * TM][MAX_ST] final filter tau - 2 eps of the strip (scaled units): the finish drops entries below the row's largest
@@ -454,13 +454,15 @@ struct RankTcParams {
 };
 
 // Per-thread epilogue state: one thread owns one (user row, column strip) and its candidate list -- a private,
-// contiguous block of global memory: cap scores (f32, scaled units) followed by cap item ids.  Items reach a list in
-// increasing id order and every in-place compaction keeps that order; the user's exclusion list (sorted too) is merged
-// against the NEW tail of the list whenever the threshold is raised, and once more in the finish kernel -- the hot loop
-// never branches on it.  Entries that fall below a later threshold are NOT removed eagerly: the finish kernel drops
-// everything below the row's final filter, and a list is compacted in place only when more than half of it is dead.
+// contiguous block of `cap` 8-byte entries (score bits << 32 | item id) in global memory, appended to with one store and
+// a pointer bump.  Items reach a list in increasing id order and every in-place compaction keeps that order; the user's
+// exclusion list (sorted too) is merged against the NEW tail of the list whenever the threshold is raised, and once
+// more in the finish kernel -- the hot loop never branches on it.  Entries that fall below a later threshold are NOT
+// removed eagerly: the finish kernel drops everything below the row's final filter, and a list is compacted in place
+// only when more than half of it is dead.
 struct RowState {
-    float* lsc;                    // scores [cap]; ids at (int32_t*)(lsc + cap)
+    unsigned long long* list;      // entries [cap]
+    unsigned long long* wp;        // append position (hot loop); cnt is derived from it between stages
     const int32_t* ex;
     int n_ex;
     int ex_c;                      // exclusion cursor: entries [0, ex_c) have been loaded into the window
@@ -471,23 +473,25 @@ struct RowState {
     float hi;                      // largest score seen at the last raise (bin range)
 };
 
-// sequential scan of the scores of a list: eight 16-byte loads (32 scores) in flight per thread
+__device__ __forceinline__ float ent_score(unsigned long long e) { return __uint_as_float((unsigned)(e >> 32)); }
+
+// sequential scan of a list: eight 16-byte loads (16 entries) in flight per thread
 template <typename F>
-__device__ __forceinline__ void scan_scores(const float* __restrict__ lsc, int L, F f)
+__device__ __forceinline__ void scan_list(const unsigned long long* __restrict__ list, int L, F f)
 {
     int e = 0;
-    for (; e + 32 <= L; e += 32) {
-        float4 v[8];
+    for (; e + 16 <= L; e += 16) {
+        ulonglong2 v[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const float4*>(lsc + e + 4 * i);
+        for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const ulonglong2*>(list + e + 2 * i);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { f(v[i].x); f(v[i].y); f(v[i].z); f(v[i].w); }
+        for (int i = 0; i < 8; ++i) { f(v[i].x); f(v[i].y); }
     }
-    for (; e + 4 <= L; e += 4) {
-        const float4 v = *reinterpret_cast<const float4*>(lsc + e);
-        f(v.x); f(v.y); f(v.z); f(v.w);
+    for (; e + 2 <= L; e += 2) {
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(list + e);
+        f(v.x); f(v.y);
     }
-    for (; e < L; ++e) f(lsc[e]);
+    if (e < L) f(list[e]);
 }
 
 // named barrier of the ST epilogue warps that own the column strips of the same 32 user rows
@@ -521,8 +525,8 @@ __device__ __forceinline__ void raise_threshold(RowState& st, int K, float eps2,
     unsigned long long* my_tau = tau_row + strip * TM;
     int* pair_mine = share + strip * (TM * 4);
     unsigned short* hist_mine = hist + (size_t)strip * NB * TM;
-    float* __restrict__ lsc = st.lsc;
-    int32_t* __restrict__ lid = reinterpret_cast<int32_t*>(st.lsc + cap);
+    unsigned long long* __restrict__ list = st.list;
+    (void)cap;
     // The other column strips of this row publish their own lower bound of the row's k-th best score; any such bound
     // (even an old one) is valid for the whole row, so take the largest.  The tag rejects a value the sibling warp left
     // behind from the previous user tile.
@@ -539,14 +543,14 @@ __device__ __forceinline__ void raise_threshold(RowState& st, int K, float eps2,
     if (st.n_ex > 0 && st.checked < st.cnt) {
         int w = st.checked;
         for (int e0 = st.checked; e0 < st.cnt; e0 += 8) {       // 8 independent id loads per round trip;
-            int32_t v[8];                                        // a batch is read before it is written (w <= e0)
+            unsigned long long v[8];                              // a batch is read before it is written (w <= e0)
             const int nb = st.cnt - e0 < 8 ? st.cnt - e0 : 8;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = i < nb ? lid[e0 + i] : 0x7fffffff;
+            for (int i = 0; i < 8; ++i) v[i] = i < nb ? list[e0 + i] : 0ull;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 if (i < nb) {
-                    const int32_t id = v[i];
+                    const int32_t id = (int32_t)(v[i] & 0xffffffffull);
                     while (st.ex_w0 < id) {                       // advance the window past ids below `id`
                         st.ex_w0 = st.ex_w1; st.ex_w1 = st.ex_w2; st.ex_w2 = st.ex_w3; st.ex_w3 = 0x7fffffff;
                         if (st.ex_w0 == 0x7fffffff && st.ex_c < st.n_ex) {      // window empty: refill
@@ -559,7 +563,7 @@ __device__ __forceinline__ void raise_threshold(RowState& st, int K, float eps2,
                         }
                     }
                     if (st.ex_w0 != id) {
-                        if (w != e0 + i) { lid[w] = id; lsc[w] = lsc[e0 + i]; }
+                        if (w != e0 + i) list[w] = v[i];
                         ++w;
                     }
                 }
@@ -574,7 +578,8 @@ __device__ __forceinline__ void raise_threshold(RowState& st, int K, float eps2,
     if (L == 0) { lo = INFINITY; hi = -INFINITY; }
     else if (!(hi > -INFINITY) || !(lo > -1.0e37f)) {  // this list's score range is not known yet
         lo = INFINITY; hi = -INFINITY;
-        scan_scores(lsc, L, [&](float sc) {
+        scan_list(list, L, [&](unsigned long long ent) {
+            const float sc = ent_score(ent);
             lo = fminf(lo, sc);
             hi = fmaxf(hi, sc);
         });
@@ -604,7 +609,8 @@ __device__ __forceinline__ void raise_threshold(RowState& st, int K, float eps2,
     float new_hi = -INFINITY;
     if (ok) {
         const float inv = 1.f / step;
-        scan_scores(lsc, L, [&](float sc) {
+        scan_list(list, L, [&](unsigned long long ent) {
+            const float sc = ent_score(ent);
             new_hi = fmaxf(new_hi, sc);
             if (sc >= a) {
                 int j = (int)((sc - a) * inv);                  // within +-1 of the bin; made exact against bin_edge()
@@ -654,21 +660,10 @@ __device__ __forceinline__ void raise_threshold(RowState& st, int K, float eps2,
     bool go = want;
     if (JOINT) go = __any_sync(0xffffffffu, want);
     if (go) {
-        int w = 0;          // writes trail the reads (w <= e)
-        int e = 0;
-        for (; e + 4 <= L; e += 4) {
-            const float4 sv = *reinterpret_cast<const float4*>(lsc + e);
-            const int4 iv = *reinterpret_cast<const int4*>(lid + e);
-            if (sv.x >= st.tau_f) { lsc[w] = sv.x; lid[w] = iv.x; ++w; }
-            if (sv.y >= st.tau_f) { lsc[w] = sv.y; lid[w] = iv.y; ++w; }
-            if (sv.z >= st.tau_f) { lsc[w] = sv.z; lid[w] = iv.z; ++w; }
-            if (sv.w >= st.tau_f) { lsc[w] = sv.w; lid[w] = iv.w; ++w; }
-        }
-        for (; e < L; ++e) {
-            const float sv = lsc[e];
-            const int32_t iv = lid[e];
-            if (sv >= st.tau_f) { lsc[w] = sv; lid[w] = iv; ++w; }
-        }
+        int w = 0;          // writes trail the reads (w <= e); each batch of 16 is read before it is written
+        scan_list(list, L, [&](unsigned long long ent) {
+            if (ent_score(ent) >= st.tau_f) { list[w] = ent; ++w; }
+        });
         st.cnt = w;
         st.checked = w;
     }
@@ -682,15 +677,15 @@ __device__ __forceinline__ float fmax3(float a, float b, float c)
     return d;
 }
 
-// append the scores of one group of four that pass the filter to the calling lane's list; returns the new length
-__device__ __noinline__ int append4(float* lsc, int cap, int cnt, float tau_f, float s0, float s1, float s2, float s3, int32_t id)
+// append the scores of one group of four that pass the filter to the calling lane's list
+__device__ __noinline__ unsigned long long* append4(unsigned long long* wp, float tau_f, float s0, float s1, float s2,
+                                                    float s3, int32_t id)
 {
-    int32_t* lid = reinterpret_cast<int32_t*>(lsc + cap);
-    if (s0 > tau_f) { lsc[cnt] = s0; lid[cnt] = id; ++cnt; }
-    if (s1 > tau_f) { lsc[cnt] = s1; lid[cnt] = id + 1; ++cnt; }
-    if (s2 > tau_f) { lsc[cnt] = s2; lid[cnt] = id + 2; ++cnt; }
-    if (s3 > tau_f) { lsc[cnt] = s3; lid[cnt] = id + 3; ++cnt; }
-    return cnt;
+    if (s0 > tau_f) { *wp = ((unsigned long long)__float_as_uint(s0) << 32) | (uint32_t)id; ++wp; }
+    if (s1 > tau_f) { *wp = ((unsigned long long)__float_as_uint(s1) << 32) | (uint32_t)(id + 1); ++wp; }
+    if (s2 > tau_f) { *wp = ((unsigned long long)__float_as_uint(s2) << 32) | (uint32_t)(id + 2); ++wp; }
+    if (s3 > tau_f) { *wp = ((unsigned long long)__float_as_uint(s3) << 32) | (uint32_t)(id + 3); ++wp; }
+    return wp;
 }
 
 // one 32-column chunk of the accumulator (the item base is already in it: extra K slice of the MMA):
@@ -699,7 +694,7 @@ __device__ __noinline__ int append4(float* lsc, int cap, int cnt, float tau_f, f
 // groups once the thresholds have risen) does the warp run the predicated appends for that group.
 // ~1.25 instructions per score on the common path.
 template <bool DUMP>
-__device__ __forceinline__ void epilogue_chunk(uint32_t (&r)[32], RowState& st, int cap, int32_t id0,
+__device__ __forceinline__ void epilogue_chunk(uint32_t (&r)[32], RowState& st, int32_t id0,
                                                float* __restrict__ dump_row, bool valid, float invS)
 {
     if (DUMP) {
@@ -726,8 +721,8 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t (&r)[32], RowState& st, 
 #pragma unroll
     for (int j4 = 0; j4 < 8; ++j4) {
         if (hit[j4])
-            st.cnt = append4(st.lsc, cap, st.cnt, st.tau_f, __uint_as_float(r[j4 * 4 + 0]), __uint_as_float(r[j4 * 4 + 1]),
-                             __uint_as_float(r[j4 * 4 + 2]), __uint_as_float(r[j4 * 4 + 3]), id0 + j4 * 4);
+            st.wp = append4(st.wp, st.tau_f, __uint_as_float(r[j4 * 4 + 0]), __uint_as_float(r[j4 * 4 + 1]),
+                            __uint_as_float(r[j4 * 4 + 2]), __uint_as_float(r[j4 * 4 + 3]), id0 + j4 * 4);
     }
     }
 }
@@ -882,7 +877,7 @@ __global__ void __launch_bounds__(threads_for(ST), 1) rank_tc_kernel(const RankT
             const float invS = 1.f / us.S;
             const float eps2 = 2.f * eps;
             RowState st;
-            st.lsc = p.lists + ((size_t)(ut * EPI_WARPS + half * 4 + q) * 32 + lane) * (2 * CAP_T);
+            st.list = p.lists + ((size_t)(ut * EPI_WARPS + half * 4 + q) * 32 + lane) * CAP_T;
             st.ex = nullptr; st.n_ex = 0; st.ex_c = 0;
             st.ex_w0 = st.ex_w1 = st.ex_w2 = st.ex_w3 = 0x7fffffff;
             if (valid && p.excl_indptr) {
@@ -932,21 +927,37 @@ __global__ void __launch_bounds__(threads_for(ST), 1) rank_tc_kernel(const RankT
                     if (lane == 0) { if (CG == 2) mbar_arrive_remote(r_acc_empty + 8 * acc); else mbar_arrive(acc_empty + acc); }
                     continue;
                 }
-                tmem_ld32_issue(t0, r0);
-                tmem_ld_wait(r0);
-#pragma unroll
-                for (int c0 = 0; c0 < STRIP_N; c0 += 64) {
-                    tmem_ld32_issue(t0 + c0 + 32, r1);                        // in flight while r0 is processed
-                    epilogue_chunk<DUMP>(r0, st, CAP_T, item0 + c0, dump_row, valid, invS);
+                // The accumulator goes back to the tensor pipe as soon as this warp's columns are in REGISTERS -- before the
+                // screening of the last 64 of them, whose data-dependent appends then run off the MMA's critical path
+                // (with 64-column strips: all of the screening).
+                st.wp = st.list + st.cnt;
+                auto hand_back = [&]() {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) { if (CG == 2) mbar_arrive_remote(r_acc_empty + 8 * acc); else mbar_arrive(acc_empty + acc); }
+                };
+                if constexpr (STRIP_N == 64) {
+                    tmem_ld32_issue(t0, r0);
+                    tmem_ld32_issue(t0 + 32, r1);
+                    tmem_ld_wait(r0);
                     tmem_ld_wait(r1);
-                    if (c0 + 64 < STRIP_N) tmem_ld32_issue(t0 + c0 + 64, r0);
-                    epilogue_chunk<DUMP>(r1, st, CAP_T, item0 + c0 + 32, dump_row, valid, invS);
-                    if (c0 + 64 < STRIP_N) tmem_ld_wait(r0);
+                    hand_back();
+                    epilogue_chunk<DUMP>(r0, st, item0, dump_row, valid, invS);
+                    epilogue_chunk<DUMP>(r1, st, item0 + 32, dump_row, valid, invS);
+                } else {
+                    tmem_ld32_issue(t0, r0);
+                    tmem_ld_wait(r0);
+#pragma unroll
+                    for (int c0 = 0; c0 < STRIP_N; c0 += 64) {
+                        tmem_ld32_issue(t0 + c0 + 32, r1);                    // in flight while r0 is processed
+                        epilogue_chunk<DUMP>(r0, st, item0 + c0, dump_row, valid, invS);
+                        tmem_ld_wait(r1);
+                        if (c0 + 64 < STRIP_N) tmem_ld32_issue(t0 + c0 + 64, r0); else hand_back();
+                        epilogue_chunk<DUMP>(r1, st, item0 + c0 + 32, dump_row, valid, invS);
+                        if (c0 + 64 < STRIP_N) tmem_ld_wait(r0);
+                    }
                 }
-                // accumulator and stage are free again
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) { if (CG == 2) mbar_arrive_remote(r_acc_empty + 8 * acc); else mbar_arrive(acc_empty + acc); }
+                st.cnt = (int)(st.wp - st.list);
                 if (!DUMP) {
                     // Raise schedule: after stages 2, 4, 8, 16, ... for EVERY warp at once (a raise stalls the
                     // accumulator hand-off; doing it in all warps at the same stage costs one stall instead of
@@ -994,7 +1005,7 @@ struct FinishParams {
     const float* __restrict__ user_off;        // indexed by global query
     int64_t n_rows;
     int k, topk;
-    const float* __restrict__ lists;           // thread-private blocks [cap scores][cap ids] (see RankTcParams)
+    const unsigned long long* __restrict__ lists;   // thread-private lists of (score bits << 32 | id) entries (see RankTcParams)
     const int* __restrict__ row_cnt;
     const int* __restrict__ row_flag;
     const float* __restrict__ row_tau;         // final filter of each (row, strip), scaled units
@@ -1009,9 +1020,9 @@ struct FinishParams {
 };
 
 // list block of (user tile ut, row r of the tile, strip s)
-__device__ __forceinline__ const float* finish_list(const FinishParams& p, int64_t ut, int r, int s)
+__device__ __forceinline__ const unsigned long long* finish_list(const FinishParams& p, int64_t ut, int r, int s)
 {
-    return p.lists + ((size_t)(ut * (4 * p.strips) + s * 4 + (r >> 5)) * 32 + (r & 31)) * (size_t)(2 * p.cap);
+    return p.lists + ((size_t)(ut * (4 * p.strips) + s * 4 + (r >> 5)) * 32 + (r & 31)) * (size_t)p.cap;
 }
 
 // STAGED: the candidates' item rows are gathered warp-cooperatively (one coalesced 16-byte cp.async per lane
@@ -1074,12 +1085,12 @@ __global__ void __launch_bounds__(128) rank_tc_finish_kernel(const FinishParams 
         for (int f = tid; f < p.k; f += 128) su[f] = (double)__ldg(u + f);
         __syncthreads();
         for (int x = 0; x < p.strips; ++x) {
-            const float* lsc = finish_list(p, ut, r, x);
-            const int32_t* lid = reinterpret_cast<const int32_t*>(lsc + p.cap);
+            const unsigned long long* list = finish_list(p, ut, r, x);
             for (int e = tid; e < Ls[x]; e += 128) {
-                if (lsc[e] >= tau_f) {
+                const unsigned long long ent = list[e];
+                if (ent_score(ent) >= tau_f) {
                     const int pos = atomicAdd(&cand_n, 1);
-                    sort_buf[pos] = (unsigned long long)(uint32_t)lid[e];
+                    sort_buf[pos] = ent & 0xffffffffull;
                 }
             }
         }
@@ -1227,14 +1238,14 @@ __global__ void __launch_bounds__(32) rank_tc_finish_warp_kernel(const FinishPar
         // thread-private list blocks, order-preserving warp compaction
         int L = 0;
         for (int x = 0; x < p.strips; ++x) {
-            const float* lsc = finish_list(p, ut, r, x);
-            const int32_t* lid = reinterpret_cast<const int32_t*>(lsc + p.cap);
+            const unsigned long long* list = finish_list(p, ut, r, x);
             for (int e0 = 0; e0 < Ls[x]; e0 += 32) {
                 const int e = e0 + lane;
-                const bool keep = e < Ls[x] && lsc[e] >= tau_f;
+                const unsigned long long ent = e < Ls[x] ? list[e] : 0ull;
+                const bool keep = e < Ls[x] && ent_score(ent) >= tau_f;
                 const unsigned m = __ballot_sync(0xffffffffu, keep);
                 const int pos = L + __popc(m & ((1u << lane) - 1u));
-                if (keep && pos < FW_KEYS) keys[pos] = (unsigned long long)(uint32_t)lid[e];
+                if (keep && pos < FW_KEYS) keys[pos] = ent & 0xffffffffull;
                 L += __popc(m);
             }
         }
@@ -1450,9 +1461,11 @@ static int rank_strips(int k, int topk)
         if (e[0] == '4') return 4;
         if (e[0] == '2') return 2;
     }
-    // measured (profiles/r01_rank_tc_c5.md): 16 epilogue warps beat 8 by 11 % at k=64 / 100 K items; at k=128 / 1 M items
-    // they are +3 % on random factors but -7 % on a trained model (more list traffic per strip), so 8 stay there
-    return k <= 64 ? 4 : 2;
+    // 64-column strips: a warp holds its whole strip in registers, so the accumulator is handed back before any
+    // screening (the data-dependent appends leave the MMA's critical path), and four warps per scheduler hide the
+    // latency of the append path (measured: profiles/r02_rank_tc.md)
+    (void)k;
+    return 4;
 }
 
 }  // namespace tc
@@ -1555,7 +1568,7 @@ int rank_tc(const float* U, const int64_t* user_idx, int64_t n_q, const float* V
         p.excl_indptr = excl_indptr ? excl_indptr + q0 : nullptr;
         p.excl_indices = excl_indices;
         p.n_rows = rows; p.n_ut = (int)n_ut; p.n_it = (int)L.n_it; p.kp = L.kp; p.topk = topk;
-        p.lists = reinterpret_cast<float*>(ws + L.off_lists);
+        p.lists = reinterpret_cast<unsigned long long*>(ws + L.off_lists);
         p.row_cnt = reinterpret_cast<int*>(ws + L.off_cnt);
         p.row_flag = reinterpret_cast<int*>(ws + L.off_flag);
         p.row_tau = reinterpret_cast<float*>(ws + L.off_tau);
@@ -1660,7 +1673,7 @@ extern "C" int b200_rank_tc_debug_scores(const float* U, int64_t n_q, const floa
     p.scal = reinterpret_cast<const unsigned int*>(ws + L.off_scal);
     p.excl_indptr = nullptr; p.excl_indices = nullptr;
     p.n_rows = n_q; p.n_ut = (int)n_ut; p.n_it = (int)L.n_it; p.kp = L.kp; p.topk = 1;
-    p.lists = reinterpret_cast<float*>(ws + L.off_lists);
+    p.lists = reinterpret_cast<unsigned long long*>(ws + L.off_lists);
     p.row_cnt = reinterpret_cast<int*>(ws + L.off_cnt);
     p.row_flag = reinterpret_cast<int*>(ws + L.off_flag);
     p.row_tau = reinterpret_cast<float*>(ws + L.off_tau);

@@ -81,7 +81,7 @@ class BprData:
 
 
 def bpr_epoch(data, n_neg, U, V, B, lr, reg, use_bias, seed, epoch, stats, n_samples=None,
-              sample_base=0, atomic=True, exact_exp=False, unbounded=False, neg_weighted=False, hinge=False):
+              sample_base=0, atomic=True, exact_exp=False, unbounded=False, neg_weighted=False, hinge=False, blocked=False):
     """One Hogwild BPR epoch on the current stream; `stats` (int64[2] CUDA) accumulates
     (correct, skipped)."""
     L = require_cuda()
@@ -90,7 +90,7 @@ def bpr_epoch(data, n_neg, U, V, B, lr, reg, use_bias, seed, epoch, stats, n_sam
     _dev(stats, torch.int64, "stats")
     flags = ((_lib.SGD_ATOMIC if atomic else 0) | (_lib.SGD_EXACT_EXP if exact_exp else 0)
              | (_lib.SGD_UNBOUNDED if unbounded else 0) | (_lib.BPR_NEG_WEIGHTED if neg_weighted else 0)
-             | (_lib.BPR_LOSS_HINGE if hinge else 0))
+             | (_lib.BPR_LOSS_HINGE if hinge else 0) | (_lib.BPR_BLOCKED if blocked else 0))
     n = data.nnz if n_samples is None else int(n_samples)
     data.prepare()
     check(L.b200_bpr_epoch(ptr(data.pairs), ptr(data.table), data.table.numel(), data.nnz, data.n_users, int(n_neg), n,
@@ -99,13 +99,23 @@ def bpr_epoch(data, n_neg, U, V, B, lr, reg, use_bias, seed, epoch, stats, n_sam
                            current_stream()), "b200_bpr_epoch")
 
 
-def bpr_draw_host(seed, epoch, n, nnz, n_neg, sample_base=0):
-    """The (i_index, j_id) stream that bpr_epoch(seed, epoch) consumes, computed on the host."""
+def bpr_block_plan(n_users, n_neg, k):
+    """(windows of the interaction list, item blocks) of the cache-blocked sample order for this model size."""
+    import ctypes
+    L = _lib.load()
+    a, b = ctypes.c_uint32(), ctypes.c_uint32()
+    check(L.b200_bpr_block_plan(int(n_users), int(n_neg), int(k), ctypes.byref(a), ctypes.byref(b)), "b200_bpr_block_plan")
+    return a.value, b.value
+
+
+def bpr_draw_host(seed, epoch, n, nnz, n_neg, sample_base=0, plan=(1, 1)):
+    """The (i_index, j_id) stream that bpr_epoch(seed, epoch) consumes, computed on the host (plan = bpr_block_plan(...)
+    for an epoch run with blocked=True)."""
     L = _lib.load()
     ii = np.empty(n, dtype=np.int64)
     jj = np.empty(n, dtype=np.int32)
-    check(L.b200_bpr_draw_host(int(seed) & (2 ** 64 - 1), int(epoch), int(sample_base), int(n), int(nnz), int(n_neg),
-                               ii.ctypes.data, jj.ctypes.data), "b200_bpr_draw_host")
+    check(L.b200_bpr_draw_host2(int(seed) & (2 ** 64 - 1), int(epoch), int(sample_base), int(n), int(nnz), int(n_neg),
+                                int(plan[0]), int(plan[1]), ii.ctypes.data, jj.ctypes.data), "b200_bpr_draw_host")
     return ii, jj
 
 
@@ -432,6 +442,31 @@ def topk_metrics(ids, pos_indptr, pos_indices, kinds, ks, user_idx=None, topk=No
     check(L.b200_topk_metrics(ptr(ids), n_q, topk, stride, ptr(user_idx), ptr(pos_indptr), ptr(pos_indices), ptr(mk),
                               ptr(kk), len(kinds), ptr(out), current_stream()), "b200_topk_metrics")
     return out
+
+
+def rank_counts(scores, pos_indptr, pos_indices, user_idx=None, excl_indptr=None, excl_indices=None, less=None, pos_score=None):
+    """The counts behind AUC / MAP / MRR for a batch of score rows (b200_rank_counts).  `scores` f32 [n_q, n_items] CUDA is
+    MODIFIED (excluded entries become NaN).  pos_* = CSR of the test positives (int64 / int32 CUDA), row user_idx[q] for
+    score row q.  Returns (less int64 [len(pos_indices)], pos_score f32 [len(pos_indices)], n_cand int64 [n_q],
+    before_first int64 [n_q]); `less` / `pos_score` are filled only at the positions of the listed users' positives."""
+    L = require_cuda()
+    _dev(scores, torch.float32, "scores"), _dev(pos_indptr, torch.int64, "pos_indptr"), _dev(pos_indices, torch.int32, "pos_indices")
+    n_q, n_items = scores.shape
+    dev = scores.device
+    if less is None:
+        less = torch.zeros(max(pos_indices.numel(), 1), dtype=torch.int64, device=dev)
+    if pos_score is None:
+        pos_score = torch.zeros(max(pos_indices.numel(), 1), dtype=torch.float32, device=dev)
+    n_cand = torch.zeros(max(n_q, 1), dtype=torch.int64, device=dev)
+    before = torch.zeros(max(n_q, 1), dtype=torch.int64, device=dev)
+    if user_idx is not None:
+        _dev(user_idx, torch.int64, "user_idx")
+    if excl_indptr is not None:
+        _dev(excl_indptr, torch.int64, "excl_indptr"), _dev(excl_indices, torch.int32, "excl_indices")
+    check(L.b200_rank_counts(ptr(scores), n_q, n_items, ptr(excl_indptr), ptr(excl_indices), ptr(user_idx), ptr(pos_indptr),
+                             ptr(pos_indices), ptr(less), ptr(pos_score), ptr(n_cand), ptr(before), current_stream()),
+          "b200_rank_counts")
+    return less, pos_score, n_cand[:n_q], before[:n_q]
 
 
 def delta_make(x, snapshot, delta):

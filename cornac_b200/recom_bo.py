@@ -110,6 +110,9 @@ class BaselineOnly(DeviceScoringMixin, Recommender):
         return zu, zv, item_base, np.asarray(self.u_biases, dtype=DTYPE), self.num_items
 
     def rank(self, user_idx, item_indices=None, k=-1, **kwargs):
+        hit = self._b200_cached_rank(user_idx, item_indices, k) if self.knows_user(user_idx) else None
+        if hit is not None:
+            return hit
         known = torch.from_numpy(np.asarray(self.score(user_idx), dtype=DTYPE)).cuda()[None, :]
         if known.shape[1] != self.total_items:               # unknown items get the MIN score (recommender.py:507-511)
             allsc = torch.full((1, self.total_items), float(known.min().item()), dtype=torch.float32, device="cuda")

@@ -149,13 +149,17 @@ class BPR(DeviceScoringMixin, Recommender, ANNMixin):
     # reference: recom_bpr.pyx:272-297
     def score(self, user_idx, item_idx=None):
         if item_idx is None:
-            return self._b200_scores_dev([user_idx])[0].cpu().numpy()
+            cached = self._b200_cached_scores(user_idx)
+            return cached.copy() if cached is not None else self._b200_scores_dev([user_idx])[0].cpu().numpy()
         item_score = self.i_biases[item_idx]
         item_score += np.dot(self.u_factors[user_idx], self.i_factors[item_idx])
         return item_score
 
     # reference: recommender.py:476-530
     def rank(self, user_idx, item_indices=None, k=-1, **kwargs):
+        hit = self._b200_cached_rank(user_idx, item_indices, k)          # filled by transform() before an evaluation
+        if hit is not None:
+            return hit
         scores = self._b200_scores_dev([user_idx])          # [1, total_items]
         return self._b200_rank(scores, item_indices, k)
 

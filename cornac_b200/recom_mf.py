@@ -126,7 +126,8 @@ class MF(DeviceScoringMixin, Recommender, ANNMixin):
             raise ScoreException("Can't make score prediction for item %d" % item_idx)
         if item_idx is None:
             if self.knows_user(user_idx):
-                return self._b200_scores_dev([user_idx])[0].cpu().numpy()
+                cached = self._b200_cached_scores(user_idx)
+                return cached.copy() if cached is not None else self._b200_scores_dev([user_idx])[0].cpu().numpy()
             return self.global_mean + self.i_biases
         item_score = self.global_mean + self.i_biases[item_idx]
         if self.knows_user(user_idx):
@@ -136,6 +137,9 @@ class MF(DeviceScoringMixin, Recommender, ANNMixin):
 
     # reference: recommender.py:476-530
     def rank(self, user_idx, item_indices=None, k=-1, **kwargs):
+        hit = self._b200_cached_rank(user_idx, item_indices, k) if self.knows_user(user_idx) else None
+        if hit is not None:
+            return hit
         if not self.knows_user(user_idx):
             known = torch.from_numpy(np.asarray(self.global_mean + self.i_biases, dtype=DTYPE)).cuda()[None, :]
         else:

@@ -45,6 +45,9 @@ extern "C" {
 #define B200_BPR_NEG_WEIGHTED 8u /* WBPR (recom_wbpr.pyx:125-136): j = item of a uniformly drawn INTERACTION */
 #define B200_BPR_LOSS_HINGE 16u  /* MMMF (cornac/models/mmmf/recom_mmmf.pyx:129-154): hinge loss, biases always trained */
 #define B200_SGD_UNBOUNDED 4u /* do not cap the number of concurrently running samples (see b200_bpr_epoch) */
+#define B200_BPR_BLOCKED 32u /* cache-blocked sample ORDER (same per-epoch law, see b200_bpr_block_plan): the epoch visits the
+                              * interaction list window by window and the items block by block so that the rows in use stay in
+                              * the L2; a no-op for matrices whose factors already fit (plan 1 x 1) */
 
 B200_API const char* b200_last_error(void);
 B200_API int b200_abi_version(void);
@@ -88,12 +91,24 @@ B200_API int b200_bpr_epoch(const int32_t* pairs, const uint64_t* table, int64_t
                             uint64_t seed, uint64_t epoch, uint64_t sample_base,
                             unsigned flags, int64_t* stats, void* stream);
 
+/* The plan of the cache-blocked order for a factor matrix pair: windows of the interaction list (user side) and blocks
+ * of the items such that one window's user rows and one block's item rows stay L2-resident.  Sample s of an epoch
+ * (s = sample_base + local index) belongs to run (s / ceil(nnz / (windows * blocks))) mod (windows * blocks); run
+ * (w, b) draws i_index uniformly from the w-th window of [0, nnz) and j uniformly from item block (b + epoch) mod blocks:
+ * every interaction is still drawn once per epoch in expectation and every negative is uniform over the items,
+ * independently of the interaction (the law of recom_bpr.pyx:237-239); only the ORDER of the epoch's triplets changes. */
+B200_API int b200_bpr_block_plan(int64_t n_users, int64_t n_neg, int k, uint32_t* n_windows, uint32_t* n_blocks);
+
 /* The sample law of b200_bpr_epoch, evaluated on the HOST (no CUDA): writes, for
  * s = 0..n-1, the i_index and j_id that sample `sample_base + s` of `epoch` draws.  Lets a
  * caller replay / audit the exact stream the throughput kernel consumed.
  *   out_i_index host int64[n], out_j_id host int32[n]                                      */
 B200_API int b200_bpr_draw_host(uint64_t seed, uint64_t epoch, uint64_t sample_base, int64_t n,
                                 int64_t nnz, int64_t n_neg, int64_t* out_i_index, int32_t* out_j_id);
+/* the same for an epoch run with B200_BPR_BLOCKED under the plan (n_windows, n_blocks) of b200_bpr_block_plan */
+B200_API int b200_bpr_draw_host2(uint64_t seed, uint64_t epoch, uint64_t sample_base, int64_t n,
+                                 int64_t nnz, int64_t n_neg, uint32_t n_windows, uint32_t n_blocks,
+                                 int64_t* out_i_index, int32_t* out_j_id);
 
 /* BPR, parity mode.  Applies an explicit sample stream (i_index[s], j_id[s]),
  * s = 0..n_samples-1, with the SAME RESULT AS APPLYING IT SEQUENTIALLY in stream order,

@@ -285,3 +285,47 @@ def test_c4_mf_lr0_is_identity_and_loss_matches_at_target_shape(c3):
     for _ in range(2):
         engine.mf_epoch(rid, cid, val, U, V, Bu, Bi, 0.01, 0.02, 3.0, True, loss)
     assert float(loss.item()) < 0.995 * first
+
+
+def test_c3_cache_blocked_order_draws_the_same_law_and_trains_like_the_unblocked_epoch(c3):
+    """B200_BPR_BLOCKED at the target shape (plan 16 windows x 13 item blocks): (correct, skipped) of a slice that spans
+    several (window, block) runs equal the oracle's counts on the host-evaluated blocked stream (b200_bpr_draw_host2);
+    the slice's interactions / negatives really come from the windows / blocks of the plan; a blocked epoch conserves the
+    item mass like the unblocked one and reaches the same pairwise accuracy (+-0.01) from the same start."""
+    import torch
+    from cornac_b200 import engine
+    W, data = c3["W"], c3["data"]
+    plan = engine.bpr_block_plan(data.n_users, W["n_items"], W["k"])
+    assert plan[0] > 1 and plan[1] > 1
+    s_sub = -(-data.nnz // (plan[0] * plan[1]))
+    U, V, B = c3["U"].clone(), c3["V"].clone(), c3["B"].clone()
+    stats = torch.zeros(2, dtype=torch.int64, device=c3["dev"])
+    n, base = 1_500_000, 7 * s_sub - 400_000                       # crosses two run boundaries
+    engine.bpr_epoch(data, W["n_items"], U, V, B, 0.0, 0.01, True, 99, 3, stats, n_samples=n, sample_base=base, exact_exp=True,
+                     blocked=True)
+    c, s = stats.cpu().tolist()
+    assert torch.equal(U, c3["U"]) and torch.equal(V, c3["V"])
+    ii, jj = engine.bpr_draw_host(99, 3, n, data.nnz, W["n_items"], sample_base=base, plan=plan)
+    runs = (base + np.arange(n)) // s_sub
+    for r in np.unique(runs):
+        sel = runs == r
+        w, b = int(r) // plan[1], (int(r) % plan[1] + 3) % plan[1]
+        assert ii[sel].min() >= w * data.nnz // plan[0] - 1 and ii[sel].max() <= (w + 1) * data.nnz // plan[0] + 1
+        assert jj[sel].min() >= b * W["n_items"] // plan[1] - 1 and jj[sel].max() <= (b + 1) * W["n_items"] // plan[1] + 1
+    indptr, indices = c3["indptr"].cpu().numpy(), c3["indices"].cpu().numpy()
+    Uh, Vh, Bh = c3["U"].cpu().numpy(), c3["V"].cpu().numpy(), c3["B"].cpu().numpy()
+    c_ref, s_ref = O.bpr_replay(ii, jj, indptr, indices, Uh, Vh, Bh, 0.0, 0.01, True)
+    assert s == s_ref and abs(c - c_ref) <= max(3, int(2e-5 * n))
+    acc = {}
+    for blocked in (False, True):
+        U, V, B = c3["U"].clone(), c3["V"].clone(), c3["B"].clone()
+        col0 = V.double().sum(0)
+        for e in range(2):
+            stats.zero_()
+            engine.bpr_epoch(data, W["n_items"], U, V, B, 0.05, 0.0, True, 7, e, stats, blocked=blocked)
+        cc, ss = stats.cpu().tolist()
+        acc[blocked] = cc / (data.nnz - ss)
+        moved = (V.double() - c3["V"].double()).abs().sum().item()
+        assert (V.double().sum(0) - col0).abs().max().item() < 1e-5 * moved / W["k"] + 1e-3
+        assert abs(ss / data.nnz - 0.00023) < 0.0005
+    assert abs(acc[True] - acc[False]) < 0.01, acc

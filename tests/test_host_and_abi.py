@@ -127,3 +127,32 @@ def test_recommend_batch_host_logic_with_a_stubbed_device():
         m.recommend_batch(["a"], k=7)
     with pytest.raises(ValueError):
         m.recommend_batch(["a"], k=2, remove_seen=True)
+
+
+def test_cache_blocked_sample_order_keeps_the_per_epoch_law():
+    """b200_bpr_draw_host2 (the host twin of the B200_BPR_BLOCKED kernels): over one epoch every interaction is drawn once
+    in expectation, negatives are uniform over all items, every window of the interaction list meets every item block,
+    windows / blocks receive exactly their share; plan 1 x 1 is the unblocked stream bit for bit."""
+    from cornac_b200 import engine
+    nnz, n_neg = 120_007, 9_001
+    for epoch, plan in ((0, (5, 3)), (4, (7, 4)), (1, (1, 6)), (2, (9, 1))):
+        ii, jj = engine.bpr_draw_host(11, epoch, nnz, nnz, n_neg, plan=plan)
+        assert ii.min() >= 0 and ii.max() < nnz and jj.min() >= 0 and jj.max() < n_neg
+        wn, bn = plan
+        wb = np.array([w * (nnz // wn) + min(w, nnz % wn) for w in range(wn + 1)])
+        bb = np.array([b * (n_neg // bn) + min(b, n_neg % bn) for b in range(bn + 1)])
+        w_of, b_of = np.searchsorted(wb, ii, side="right") - 1, np.searchsorted(bb, jj, side="right") - 1
+        assert np.unique(w_of * bn + b_of).size == wn * bn                          # all (window, block) runs occur
+        share_w = np.bincount(w_of, minlength=wn) / nnz
+        assert np.allclose(share_w, np.diff(wb) / nnz, atol=2.0 / (wn * bn) * 0.51 + 1e-9)     # whole runs per window
+        # negatives: uniform over the items (chi-square-ish bound on the block shares, Poisson noise per item)
+        assert np.allclose(np.bincount(b_of, minlength=bn) / nnz, np.diff(bb) / n_neg, atol=0.02)
+        cnt = np.bincount(jj, minlength=n_neg)
+        assert abs(cnt.mean() - nnz / n_neg) < 1e-9 and cnt.std() < 1.5 * np.sqrt(nnz / n_neg)
+        # interactions: mean 1 draw each, Poisson-like spread
+        ci = np.bincount(ii, minlength=nnz)
+        assert abs(ci.mean() - 1.0) < 1e-9 and 0.9 < ci.var() < 1.1
+    a = engine.bpr_draw_host(5, 2, 5000, nnz, n_neg, sample_base=123)
+    b = engine.bpr_draw_host(5, 2, 5000, nnz, n_neg, sample_base=123, plan=(1, 1))
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert engine.bpr_block_plan(1000, 2000, 64) == (1, 1) and engine.bpr_block_plan(10_000_000, 1_000_000, 128) == (123, 13)

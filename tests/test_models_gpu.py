@@ -210,10 +210,10 @@ def test_batched_ranking_eval_equals_reference_loop():
             for ua, ub in zip(a_usr, b_usr):
                 assert list(ua.keys()) == list(ub.keys())
                 assert np.allclose(list(ua.values()), list(ub.values()), rtol=1e-12, atol=1e-15)
-    # metrics that need full score vectors are delegated to the reference implementation
+    # a metric that needs full score vectors (device counts, see test_device_auc_map_mrr_equal_the_reference_loop)
     a = ref_eval(mdl, [AUC()], train_set, test_set, rating_threshold=4.0)[0]
     b = b200_eval(mdl, [AUC()], train_set, test_set, rating_threshold=4.0)[0]
-    assert a == b
+    assert np.allclose(a, b, rtol=1e-12)
 
 
 @pytest.mark.parametrize("topk,n_items,n_q", [(10, 50, 300), (100, 2000, 500), (257, 600, 64), (4096, 5000, 9)])
@@ -320,3 +320,61 @@ def test_recommend_batch_on_the_gpu_equals_per_user_recommend():
         assert mdl.recommend_batch(users[:3], k=-1) == [list(mdl.recommend(u, k=-1)) for u in users[:3]]
         with pytest.raises(ValueError):
             mdl.recommend_batch(["no-such-user"], k=5)
+
+
+def test_transform_cache_serves_rank_and_score_without_device_work_and_identically():
+    """`transform(test_set)` (the hook BaseMethod.evaluate calls before the per-user loops, recommender.py:410-421)
+    precomputes scores + the global ranking head for all test users; `rank()` / `score()` then answer from host memory and
+    return exactly what the uncached device path returns -- for arbitrary candidate sets, k = -1, k larger than the
+    cached head, and users outside the cache (lazy per-user fallback: hyperopt never calls transform)."""
+    from cornac_b200 import BPR, MF, BaselineOnly
+    from cornac_b200 import engine
+    _, train_set, test_set, _, _ = _split_sets()
+    rng = np.random.RandomState(0)
+    for mdl in (BPR(k=16, max_iter=10, learning_rate=0.05), MF(k=16, max_iter=10), BaselineOnly(max_iter=5)):
+        mdl.fit(train_set)
+        users = sorted(set(test_set.uir_tuple[0]))[:40]
+        cold = {}
+        for u in users:
+            cand = np.sort(rng.choice(train_set.num_items, size=rng.randint(30, train_set.num_items), replace=False))
+            cold[u] = (cand, [mdl.rank(u, item_indices=cand, k=kk) for kk in (10, -1, 2000)], mdl.score(u))
+        mdl.transform(test_set)
+        assert mdl._b200_eval_cache is not None
+        launches = engine.require_cuda().b200_kernel_launches()
+        for u in users:
+            cand, ranked, sc = cold[u]
+            for kk, (r0, s0) in zip((10, -1, 2000), ranked):
+                r1, s1 = mdl.rank(u, item_indices=cand, k=kk)
+                assert np.array_equal(s0, s1)
+                top = len(cand) if (kk == -1 or kk >= len(cand)) else kk
+                assert np.array_equal(r0[:top], r1[:top]) and sorted(r0) == sorted(r1)
+            assert np.array_equal(mdl.score(u), sc)
+        assert engine.require_cuda().b200_kernel_launches() == launches            # no kernel ran for the cached users
+        r_all = mdl.rank(users[0], k=5)
+        assert len(r_all[0]) == train_set.num_items
+        mdl.fit(train_set)                                                         # new parameters: the cache is gone
+        assert mdl._b200_eval_cache is None
+
+
+def test_device_auc_map_mrr_equal_the_reference_loop():
+    """AUC / MAP (/ MRR without cut-off metrics) from device score rows + b200_rank_counts equal the reference loop's
+    values user by user (ranking.py:473-485, 522-525, 213-222), also next to @k metrics and with a validation set."""
+    from cornac.eval_methods.base_method import ranking_eval as ref_eval
+    from cornac.metrics import AUC, MAP, MRR, NDCG, Recall
+    from cornac_b200 import BPR, MF
+    from cornac_b200.evaluation import ranking_eval as b200_eval
+    _, train_set, test_set, _, _ = _split_sets()
+    for mdl in (BPR(k=10, max_iter=30, learning_rate=0.05, seed=123), MF(k=10, max_iter=20, seed=123)):
+        mdl.fit(train_set)
+        for metrics in ([AUC(), MAP(), NDCG(k=10), Recall(k=20)], [AUC(), MAP(), MRR()], [MAP()]):
+            for thr in (1.0, 4.0):
+                a_avg, a_usr = ref_eval(mdl, metrics, train_set, test_set, rating_threshold=thr, exclude_unknowns=True)
+                b_avg, b_usr = b200_eval(mdl, metrics, train_set, test_set, rating_threshold=thr, exclude_unknowns=True)
+                assert np.allclose(a_avg, b_avg, rtol=1e-12, atol=1e-15), (mdl.name, [m.name for m in metrics], thr, a_avg, b_avg)
+                for ua, ub in zip(a_usr, b_usr):
+                    assert list(ua.keys()) == list(ub.keys())
+                    assert np.allclose(list(ua.values()), list(ub.values()), rtol=1e-12, atol=1e-15)
+    # MRR next to a cut-off metric: the reference evaluates it on a partially sorted list -> delegated, identical by construction
+    a = ref_eval(mdl, [MRR(), NDCG(k=10)], train_set, test_set, rating_threshold=4.0)[0]
+    b = b200_eval(mdl, [MRR(), NDCG(k=10)], train_set, test_set, rating_threshold=4.0)[0]
+    assert a == b

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--nnz", type=int, default=0)
     ap.add_argument("--c3", type=int, default=0, help="1: block 0 of bench.py's configs[2] model (1.25M x 1M x 125M, k=128)")
     ap.add_argument("--epochs", type=int, default=3)
+    ap.add_argument("--blocked", type=int, default=0, help="1: cache-blocked sample order (B200_BPR_BLOCKED)")
     args = ap.parse_args()
     W = dict(bench.WORKLOADS["c2"])
     if args.c3:
@@ -62,16 +63,19 @@ def main():
     for name, tune, at in configs:
         os.environ["B200_BPR_TUNE"] = tune
         for e in range(2):
-            engine.bpr_epoch(data, W["n_items"], U, V, B, W["lr"], W["reg"], True, 1, e, stats, atomic=bool(at))
+            engine.bpr_epoch(data, W["n_items"], U, V, B, W["lr"], W["reg"], True, 1, e, stats, atomic=bool(at), blocked=bool(args.blocked))
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for e in range(args.epochs):
-            engine.bpr_epoch(data, W["n_items"], U, V, B, W["lr"], W["reg"], True, 1, 10 + e, stats, atomic=bool(at))
+            engine.bpr_epoch(data, W["n_items"], U, V, B, W["lr"], W["reg"], True, 1, 10 + e, stats, atomic=bool(at), blocked=bool(args.blocked))
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / args.epochs
-        print("k=%d %-32s %8.2f ms  %6.3f G samples/s" % (args.k, name, ms, data.nnz / ms / 1e6), flush=True)
+        c, sk = stats.cpu().tolist()
+        print("k=%d %-32s %8.2f ms  %6.3f G samples/s  blocked=%d plan=%s acc=%.4f" % (args.k, name, ms, data.nnz / ms / 1e6, args.blocked,
+              engine.bpr_block_plan(W["n_users"], W["n_items"], args.k), c / max(1, (2 + args.epochs) * data.nnz - sk)), flush=True)
+        stats.zero_()
 
 
 if __name__ == "__main__":
