@@ -359,6 +359,9 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS),
                     help="c3 = BASELINE configs[2] (default, the north_star target); c2 = configs[1]")
     ap.add_argument("--atomic", type=int, default=1, help="1: red.global.add scatter (default), 0: plain racy stores")
+    ap.add_argument("--blocked", type=int, default=1, help="1: cache-blocked sample order (default, what fit() uses), 0: i.i.d. order")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="item-replica exchange at N > 1: p2p = one fused NVLink kernel per tensor, nccl = delta kernels + all-reduce")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-rank", action="store_true")
@@ -398,7 +401,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     from cornac_b200 import engine
     from cornac_b200._lib import load
-    from cornac_b200.parallel import ItemReplicaSync
+    from cornac_b200.parallel import make_item_sync
     L = load()
 
     # ---- data: this rank's user blocks of the ONE model; items shared
@@ -417,13 +420,14 @@ def main():
     torch.cuda.synchronize()
     log("[bench] rank %d/%d data ready in %.1fs: blocks %s = %d users x %d items x %d nnz (%.1f GB allocated)"
         % (rank, world, time.time() - t0, blocks, n_local, W["n_items"], nnz, torch.cuda.memory_allocated() / 1e9))
-    sync = ItemReplicaSync([V, B]) if world > 1 else None
+    sync = make_item_sync([V, B], kind=args.exchange) if world > 1 else None
+    exchange_kind = type(sync).__name__ if sync is not None else None
     stats = torch.zeros(2, dtype=torch.int64, device=dev)
     key = 0xB200
 
     def epoch(e):
         engine.bpr_epoch(data, W["n_items"], U, V, B, W["lr"], W["reg"], W["use_bias"], key + rank, e, stats,
-                         atomic=bool(args.atomic))
+                         atomic=bool(args.atomic), blocked=bool(args.blocked))
 
     def barrier():
         if world > 1:
@@ -479,7 +483,8 @@ def main():
     # ---- roofline of the dominant kernel, per rank (every rank launches the same kernel on nnz / N samples)
     peak, peak_src = measured_peaks()
     g_lanes = min(32, max(4, k // 4))
-    kernel_name = "bpr_hogwild_chunk_kernel<G=%d,NPL=1,VEC,%s>" % (g_lanes, "ATOMIC" if args.atomic else "PLAIN")
+    kernel_name = ("bpr_hogwild_stream_kernel<G=%d,%s,D=2>" if (k % 4 == 0 and g_lanes >= 32) else "bpr_hogwild_chunk_kernel<G=%d,NPL=1,VEC,%s>") \
+        % (g_lanes, "ATOMIC" if args.atomic else "PLAIN")
     fracs = []
     for r in range(world):
         upd_r, skp_r = allr[r, 1] / args.steps, allr[r, 2] / args.steps
@@ -501,8 +506,10 @@ def main():
                 "exchange_ms_mean": [round(float(x), 3) for x in allr[:, 4]],
                 "kernel_ms_min_med_max_over_ranks": [round(float(np.min(allr[:, 3])), 3), round(float(np.median(allr[:, 3])), 3),
                                                      round(float(np.max(allr[:, 3])), 3)],
-                "exchange": ("delta_make -> NCCL all-reduce(%d MB) -> delta_apply" % ((W["n_items"] * (k + 1) * 4) // 1000000))
-                            if world > 1 else "none (single GPU)"}
+                "exchange": ("none (single GPU)" if world == 1 else
+                             ("%s: one fused NVLink peer-memory kernel per tensor (reduce-scatter + apply + all-gather of %d MB)"
+                              if exchange_kind == "PeerItemExchange" else
+                              "%s: delta_make -> NCCL all-reduce(%d MB) -> delta_apply") % (exchange_kind, (W["n_items"] * (k + 1) * 4) // 1000000))}
 
     def over_ranks(ms):
         if world == 1:
@@ -513,6 +520,10 @@ def main():
 
     # the pair store / membership table are only needed by the epochs
     data.pairs = data.table = None
+    if sync is not None and hasattr(sync, "failed") and sync.failed():
+        raise SystemExit("bench.py: a peer did not arrive in the NVLink item exchange (bounded wait expired)")
+    if sync is not None and hasattr(sync, "close"):
+        sync.close()
     sync = None
     torch.cuda.empty_cache()
 
@@ -531,7 +542,7 @@ def main():
     # ---- configs[3]: MF on the same rating list, all ranks
     mf_metric = None
     if not args.no_mf:
-        mf_metric = run_mf(W, engine, data, dev, world, over_ranks)
+        mf_metric = run_mf(W, engine, data, dev, world, over_ranks, exchange=args.exchange)
 
     # ---- CPU baseline on rank 0, N = 1 only
     cpu_baseline = None
@@ -555,7 +566,10 @@ def main():
                        "l2": "working set per rank (U %d MB + V %d MB + pair store %d MB + membership table) exceeds the 126 MB L2; no flush needed"
                              % (n_local * k * 4 // 1000000, W["n_items"] * k * 4 // 1000000, nnz * 8 // 1000000),
                        "parallelism": "users sharded x%d by interaction count, items replicated, 1 all-reduce of item deltas per epoch" % world,
-                       "scatter": "red.global.add.v4.f32" if args.atomic else "st.global.cg.v4.f32 (Hogwild)"},
+                       "scatter": "red.global.add.v4.f32" if args.atomic else "st.global.cg.v4.f32 (Hogwild)",
+                       "sample_order": ("cache-blocked: %d windows of the interaction list x %d item blocks per rank (b200_bpr_block_plan); "
+                                        "same per-epoch law as the i.i.d. order" % engine.bpr_block_plan(n_local, W["n_items"], k))
+                                       if args.blocked else "i.i.d. (Philox counter order)"},
             "samples_per_s": round((W["nnz"] * args.steps) / (ms_total * 1e-3), 1),
             "skipped_frac": round(skipped_all / (W["nnz"] * args.steps), 5),
             "timed_region_s": round(ms_total * 1e-3, 3),
@@ -592,7 +606,8 @@ def run_e2e(args, W, engine, indptr, indices, blocks, dev, world, rank):
     def one(e):
         hist, _ = engine.bpr_train_host(h_indptr.numpy(), h_indices.numpy(), W["n_items"], hU.numpy(), hV.numpy(),
                                         hB.numpy(), W["lr"], W["reg"], W["use_bias"], 1, key=77 + e + rank,
-                                        atomic=bool(args.atomic), on_epoch=lambda *a: None, replica_sync=world > 1)
+                                        atomic=bool(args.atomic), on_epoch=lambda *a: None, replica_sync=world > 1,
+                                        blocked=bool(args.blocked))
         return hist[0]
 
     one(0)                                             # warm-up (allocator, pinned staging)
@@ -751,13 +766,13 @@ def reference_mf_ratings_per_s(rid, cid, val, n_users, n_items, k, budget_s=8.0)
     return epochs * len(val32) / secs, threads, epochs, secs
 
 
-def run_mf(W, engine, data, dev, world=1, over_ranks=lambda ms: ms):
+def run_mf(W, engine, data, dev, world=1, over_ranks=lambda ms: ms, exchange="auto"):
     """BASELINE.json configs[3]: MF ratings/s (b200_mf_epoch, Hogwild + atomic scatter), k = 128, on the rating list made
     of the model's interactions with synthetic ratings in {1..5}, stored by user (CSR order); every rank trains its
     shard, V / Bi are replicated and all-reduced once per epoch like BPR's."""
     import torch
     import torch.distributed as dist
-    from cornac_b200.parallel import ItemReplicaSync
+    from cornac_b200.parallel import make_item_sync
     k = 128
     g = torch.Generator(device=dev)
     g.manual_seed(5)
@@ -771,7 +786,7 @@ def run_mf(W, engine, data, dev, world=1, over_ranks=lambda ms: ms):
     V = torch.randn((W["n_items"], k), generator=gv, device=dev) * 0.01
     Bu, Bi = torch.zeros(data.n_users, device=dev), torch.zeros(W["n_items"], device=dev)
     loss = torch.zeros(1, device=dev)
-    sync = ItemReplicaSync([V, Bi]) if world > 1 else None
+    sync = make_item_sync([V, Bi], kind=exchange) if world > 1 else None
 
     def step():
         engine.mf_epoch(rid, cid, val, U, V, Bu, Bi, 0.01, 0.02, 3.0, True, loss)
@@ -799,6 +814,9 @@ def run_mf(W, engine, data, dev, world=1, over_ranks=lambda ms: ms):
     kms = over_ranks(float(np.mean([a.elapsed_time(b) for a, b in ev])))
     peak, _ = measured_peaks()
     gbs = n * (16 * k + 28) / (kms * 1e-3) / 1e9
+    if sync is not None and hasattr(sync, "close"):
+        torch.cuda.synchronize()
+        sync.close()
     cpu = None
     if world == 1:
         try:                                                # a reported baseline, never a reason for the bench line to fail

@@ -34,6 +34,8 @@ SIGNATURES = {
     "b200_bpr_block_plan": (_int, [_i64, _i64, _int, _vp, _vp]),
     "b200_bpr_epoch_replay": (_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _int, _f32, _f32, _int,
                                      _c.c_uint, _vp, _vp]),
+    "b200_bpr_epoch_replay2": (_int, [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _int, _f32, _f32, _int,
+                                      _c.c_uint, _vp, _vp]),
     "b200_mt_sampler_create": (_vp, [_u32]),
     "b200_mt_sampler_destroy": (None, [_vp]),
     "b200_mt_sampler_fill_i64": (_int, [_vp, _i64, _i64, _vp]),
@@ -56,6 +58,11 @@ SIGNATURES = {
     "b200_rank_counts": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200_delta_make": (_int, [_vp, _vp, _vp, _i64, _vp]),
     "b200_delta_apply": (_int, [_vp, _vp, _vp, _i64, _vp]),
+    "b200_ipc_export": (_int, [_vp, _vp, _vp]),
+    "b200_ipc_open": (_int, [_vp, _i64, _vp]),
+    "b200_ipc_close": (_int, [_vp, _i64]),
+    "b200_item_exchange_slice": (_int, [_int, _int, _i64, _vp, _vp]),
+    "b200_item_exchange": (_int, [_int, _int, _vp, _vp, _vp, _i64, _u32, _vp]),
 }
 
 SGD_ATOMIC = 1

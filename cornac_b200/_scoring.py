@@ -44,6 +44,8 @@ class DeviceScoringMixin:
         (then, and for callers that never call transform -- hyperopt, cornac/hyperopt.py:162 -- rank() falls back to the
         per-user device path); it is dropped whenever the parameters change (fit)."""
         self._b200_eval_cache = None
+        if self._B200_EVAL_CACHE_BYTES <= 0:
+            return
         try:
             users = np.unique(np.asarray(test_set.uir_tuple[0], dtype=np.int64))
         except Exception:

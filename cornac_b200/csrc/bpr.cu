@@ -832,6 +832,165 @@ __global__ void __launch_bounds__(1024) bpr_replay_window_kernel(const ReplayPar
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Parity mode, scheduled: one CTA of 32 warps, dependencies resolved over whole PHASES of 1024 samples.
+// The windowed kernel above only looks 32 samples ahead; the stream's own critical path is 3-4x shorter than what
+// 32-sample windows allow (tools/replay_levels.py).  Here every thread owns one sample of the phase and, round by round,
+//   (A) every pending sample puts its index into the slots of its three rows in two direct-mapped "earliest pending
+//       toucher" tables (atomicMin; user rows and item rows apart);
+//   (B) a sample that holds all three of its slots has no earlier pending sample on any of its rows: it is READY.  Hash
+//       collisions only make a sample wait (the earliest pending sample of the phase always wins its slots: progress);
+//   (C) the ready samples are compacted into a queue and executed, one per warp at a time, in parallel -- they touch
+//       pairwise-disjoint rows, and every earlier sample that shares a row with one of them has already been applied,
+//       so the result is the serial one BIT FOR BIT (same per-sample arithmetic as bpr_replay_kernel).
+// SMEM_MODEL: U, V and B are loaded into shared memory for the whole epoch when they fit (ML-100K sized problems: the
+// case the seeded mode exists for), so a sample's rows cost ~30 cycles instead of an L2 round trip.
+struct SchedShared {
+    int m_u[1024], m_i[1024], m_j[1024];
+    unsigned int tab_u[4096], tab_i[4096];
+    unsigned short queue[1024];
+    unsigned char pending[1024];
+    int q_n;
+};
+
+__device__ __forceinline__ unsigned int sched_slot(int row) { return ((unsigned int)row * 2654435761u) >> 20; }
+
+template <bool SMEM_MODEL>
+__global__ void __launch_bounds__(1024) bpr_replay_sched_kernel(const ReplayParams p, int64_t n_users, int64_t n_items)
+{
+    extern __shared__ __align__(16) unsigned char sched_dyn[];
+    SchedShared& sh = *reinterpret_cast<SchedShared*>(sched_dyn);
+    float* sU = reinterpret_cast<float*>(sched_dyn + ((sizeof(SchedShared) + 15) & ~(size_t)15));
+    float* sV = sU + (SMEM_MODEL ? n_users * p.k : 0);
+    float* sB = sV + (SMEM_MODEL ? n_items * p.k : 0);
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    const size_t k = (size_t)p.k;
+    if (SMEM_MODEL) {
+        for (int64_t x = tid; x < n_users * p.k; x += 1024) sU[x] = __ldcg(p.U + x);
+        for (int64_t x = tid; x < n_items * p.k; x += 1024) sV[x] = __ldcg(p.V + x);
+        for (int64_t x = tid; x < n_items; x += 1024) sB[x] = __ldcg(p.B + x);
+    }
+    for (int x = tid; x < 4096; x += 1024) { sh.tab_u[x] = 0xffffffffu; sh.tab_i[x] = 0xffffffffu; }
+    if (tid == 0) sh.q_n = 0;
+    __syncthreads();
+    float* const Ub = SMEM_MODEL ? sU : p.U;
+    float* const Vb = SMEM_MODEL ? sV : p.V;
+    float* const Bb = SMEM_MODEL ? sB : p.B;
+    auto ld = [&](const float* a) { return SMEM_MODEL ? *a : __ldcg(a); };
+    auto st = [&](float* a, float v) { if (SMEM_MODEL) *a = v; else __stcg(a, v); };
+    unsigned long long n_correct = 0, n_skipped = 0;
+    for (int64_t base0 = 0; base0 < p.n_samples; base0 += 1024) {
+        // ---- resolve the phase's samples, one per thread (read-only inputs: order-free)
+        const int64_t s = base0 + tid;
+        int32_t mu = 0, mi = 0, mj = 0;
+        bool pend = false;
+        if (s < p.n_samples) {
+            const int64_t ii = p.i_index[s];
+            mj = p.j_id[s];
+            mu = __ldg(p.coo_row + ii);
+            mi = __ldg(p.indices + ii);
+            pend = !row_contains(p.indices, __ldg(p.indptr + mu), __ldg(p.indptr + mu + 1), mj);
+            if (!pend) ++n_skipped;
+        }
+        sh.m_u[tid] = mu; sh.m_i[tid] = mi; sh.m_j[tid] = mj;
+        const unsigned int hu = sched_slot(mu), hi = sched_slot(mi), hj = sched_slot(mj);
+        for (;;) {
+            if (!__syncthreads_or(pend)) break;                  // also orders the previous round's row writes
+            // (A) earliest pending toucher of every row slot
+            if (pend) {
+                atomicMin(&sh.tab_u[hu], (unsigned int)tid);
+                atomicMin(&sh.tab_i[hi], (unsigned int)tid);
+                atomicMin(&sh.tab_i[hj], (unsigned int)tid);
+            }
+            __syncthreads();
+            // (B) ready = holds all its slots
+            const bool ready = pend && sh.tab_u[hu] == (unsigned int)tid && sh.tab_i[hi] == (unsigned int)tid
+                               && sh.tab_i[hj] == (unsigned int)tid;
+            const unsigned int bal = __ballot_sync(0xffffffffu, ready);
+            int wbase = 0;
+            if (lane == 0 && bal) wbase = atomicAdd(&sh.q_n, __popc(bal));
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            __syncthreads();                                       // every table read is done: slots may be reset
+            if (pend) { sh.tab_u[hu] = 0xffffffffu; sh.tab_i[hi] = 0xffffffffu; sh.tab_i[hj] = 0xffffffffu; }
+            if (ready) {
+                sh.queue[wbase + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)tid;
+                pend = false;
+            }
+            __syncthreads();
+            // (C) execute the ready samples, one per warp at a time (any order: they share no row)
+            const int n_ready = sh.q_n;
+            for (int q = w; q < n_ready; q += 32) {
+                const int t = sh.queue[q];
+                const int32_t u = sh.m_u[t], i = sh.m_i[t], j = sh.m_j[t];
+                float* pu = Ub + (size_t)u * k;
+                float* pi = Vb + (size_t)i * k;
+                float* pj = Vb + (size_t)j * k;
+                const float bi = ld(Bb + i), bj = ld(Bb + j);
+                constexpr int RC = 4;                              // k <= 128: rows stay in registers between dot and update
+                float ru[RC], ri[RC], rj[RC];
+                float part = 0.f;
+#pragma unroll
+                for (int x = 0; x < RC; ++x) {
+                    const int f = lane + 32 * x;
+                    ru[x] = ri[x] = rj[x] = 0.f;
+                    if (f < p.k) { ru[x] = ld(pu + f); ri[x] = ld(pi + f); rj[x] = ld(pj + f); }
+                }
+#pragma unroll
+                for (int x = 0; x < RC; ++x)
+                    if (lane + 32 * x < p.k) part = __fadd_rn(part, __fmul_rn(ru[x], __fsub_rn(ri[x], rj[x])));
+                for (int f = lane + 32 * RC; f < p.k; f += 32)
+                    part = __fadd_rn(part, __fmul_rn(ld(pu + f), __fsub_rn(ld(pi + f), ld(pj + f))));
+                const float score = __fadd_rn(__fsub_rn(bi, bj), group_sum<32>(part));
+                float z = 1.f;
+                bool update = true;
+                if (p.hinge) {                                     // recom_mmmf.pyx:137-139
+                    if (score > 0.f) { ++n_correct; update = false; }
+                } else {
+                    z = (float)(1.0 / (1.0 + exp((double)score)));
+                    n_correct += (z < .5f);
+                }
+                if (update) {
+                    const float lr = p.lr, reg = p.reg;
+#pragma unroll
+                    for (int x = 0; x < RC; ++x) {
+                        const int f = lane + 32 * x;
+                        if (f < p.k) {
+                            const float uf = ru[x], vi = ri[x], vj = rj[x];
+                            st(pu + f, __fadd_rn(uf, __fmul_rn(lr, __fsub_rn(__fmul_rn(z, __fsub_rn(vi, vj)), __fmul_rn(reg, uf)))));
+                            st(pi + f, __fadd_rn(vi, __fmul_rn(lr, __fsub_rn(__fmul_rn(z, uf), __fmul_rn(reg, vi)))));
+                            st(pj + f, __fadd_rn(vj, __fmul_rn(lr, __fsub_rn(__fmul_rn(-z, uf), __fmul_rn(reg, vj)))));
+                        }
+                    }
+                    for (int f = lane + 32 * RC; f < p.k; f += 32) {
+                        const float uf = ld(pu + f), vi = ld(pi + f), vj = ld(pj + f);
+                        st(pu + f, __fadd_rn(uf, __fmul_rn(lr, __fsub_rn(__fmul_rn(z, __fsub_rn(vi, vj)), __fmul_rn(reg, uf)))));
+                        st(pi + f, __fadd_rn(vi, __fmul_rn(lr, __fsub_rn(__fmul_rn(z, uf), __fmul_rn(reg, vi)))));
+                        st(pj + f, __fadd_rn(vj, __fmul_rn(lr, __fsub_rn(__fmul_rn(-z, uf), __fmul_rn(reg, vj)))));
+                    }
+                    if (p.use_bias && lane == 0) {
+                        st(Bb + i, __fadd_rn(bi, __fmul_rn(lr, __fsub_rn(z, __fmul_rn(reg, bi)))));
+                        st(Bb + j, __fadd_rn(bj, __fmul_rn(lr, __fsub_rn(-z, __fmul_rn(reg, bj)))));
+                    }
+                }
+            }
+            __syncthreads();                                       // queue consumed
+            if (tid == 0) sh.q_n = 0;
+        }
+    }
+    __syncthreads();
+    if (SMEM_MODEL) {
+        for (int64_t x = tid; x < n_users * p.k; x += 1024) p.U[x] = sU[x];
+        for (int64_t x = tid; x < n_items * p.k; x += 1024) p.V[x] = sV[x];
+        for (int64_t x = tid; x < n_items; x += 1024) p.B[x] = sB[x];
+    }
+    // correct: one count per warp (lane 0 counted for the whole warp); skipped: one count per resolving thread
+    const unsigned long long sk = __reduce_add_sync(0xffffffffu, (unsigned)n_skipped);
+    if (lane == 0) {
+        atomicAdd(p.stats + 0, n_correct);
+        atomicAdd(p.stats + 1, sk);
+    }
+}
+
 template <int G, int NPL, bool VEC, bool ATOMIC, int S, int MINB>
 static int launch_hogwild_s(const BprParams& p, cudaStream_t st, const HogwildTune& tune)
 {
@@ -1054,11 +1213,34 @@ extern "C" int b200_bpr_epoch(const int32_t* pairs, const uint64_t* table, int64
     return B200_OK;
 }
 
-extern "C" int b200_bpr_epoch_replay(const int64_t* i_index, const int32_t* j_id, int64_t n_samples,
-                                     const int32_t* indptr, const int32_t* indices, const int32_t* coo_row,
-                                     float* U, float* V, float* B, int k,
-                                     float lr, float reg, int use_bias, unsigned flags,
-                                     int64_t* stats, void* stream)
+static int bpr_replay_launch(ReplayParams& p, int64_t n_users, int64_t n_items, cudaStream_t st)
+{
+    const char* mode = getenv("B200_REPLAY_SERIAL");          // dev knob: 1 = strictly serial warp, 2 = 32-sample windows
+    ::b200::count_launch();
+    if (mode && mode[0] == '1') { bpr_replay_kernel<<<1, 32, 0, st>>>(p); B200_CUDA(cudaGetLastError()); return B200_OK; }
+    if (mode && mode[0] == '2') { bpr_replay_window_kernel<<<1, 1024, 0, st>>>(p); B200_CUDA(cudaGetLastError()); return B200_OK; }
+    const size_t fixed = (sizeof(SchedShared) + 15) & ~(size_t)15;
+    size_t model = 0;
+    if (n_users > 0 && n_items > 0) model = ((size_t)(n_users + n_items) * p.k + (size_t)n_items) * sizeof(float);
+    const size_t limit = 227 * 1024 - 1024;
+    if (model > 0 && fixed + model <= limit && !(mode && mode[0] == '3')) {      // 3 = scheduled kernel on the global factors
+        const size_t smem = fixed + model;
+        B200_CUDA(cudaFuncSetAttribute(bpr_replay_sched_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        bpr_replay_sched_kernel<true><<<1, 1024, smem, st>>>(p, n_users, n_items);
+    } else {
+        B200_CUDA(cudaFuncSetAttribute(bpr_replay_sched_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fixed));
+        bpr_replay_sched_kernel<false><<<1, 1024, fixed, st>>>(p, 0, 0);
+    }
+    B200_CUDA(cudaGetLastError());
+    return B200_OK;
+}
+
+extern "C" int b200_bpr_epoch_replay2(const int64_t* i_index, const int32_t* j_id, int64_t n_samples,
+                                      const int32_t* indptr, const int32_t* indices, const int32_t* coo_row,
+                                      int64_t n_users, int64_t n_items,
+                                      float* U, float* V, float* B, int k,
+                                      float lr, float reg, int use_bias, unsigned flags,
+                                      int64_t* stats, void* stream)
 {
     B200_REQUIRE(i_index && j_id && indptr && indices && coo_row && U && V && B && stats,
                  "b200_bpr_epoch_replay: null pointer argument");
@@ -1071,10 +1253,15 @@ extern "C" int b200_bpr_epoch_replay(const int64_t* i_index, const int32_t* j_id
     p.hinge = (flags & B200_BPR_LOSS_HINGE) ? 1 : 0;
     if (p.hinge) p.use_bias = 1;
     p.stats = reinterpret_cast<unsigned long long*>(stats);
-    const char* serial = getenv("B200_REPLAY_SERIAL");
-    ::b200::count_launch();
-    if (serial && serial[0] == '1') bpr_replay_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(p);
-    else bpr_replay_window_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(p);
-    B200_CUDA(cudaGetLastError());
-    return B200_OK;
+    return bpr_replay_launch(p, n_users, n_items, (cudaStream_t)stream);
+}
+
+extern "C" int b200_bpr_epoch_replay(const int64_t* i_index, const int32_t* j_id, int64_t n_samples,
+                                     const int32_t* indptr, const int32_t* indices, const int32_t* coo_row,
+                                     float* U, float* V, float* B, int k,
+                                     float lr, float reg, int use_bias, unsigned flags,
+                                     int64_t* stats, void* stream)
+{
+    return b200_bpr_epoch_replay2(i_index, j_id, n_samples, indptr, indices, coo_row, 0, 0, U, V, B, k, lr, reg, use_bias,
+                                  flags, stats, stream);
 }

@@ -443,7 +443,7 @@ struct RankTcParams {
     const int32_t* __restrict__ excl_indices;
     int64_t n_rows;                        // valid rows in this chunk
     int n_ut, n_it, kp, topk;
-    unsigned long long* __restrict__ lists;    // [n_ut * 4 ST warps][32 lanes][cap] thread-private lists: (score bits << 32) | item id
+    unsigned long long* __restrict__ lists;    // [n_ut * 4 ST warps][cap][32 lanes] interleaved lists: (score bits << 32) | item id
     int* __restrict__ row_cnt;             // [n_ut * TM][MAX_ST strips]
     int* __restrict__ row_flag;            // [n_ut * TM][MAX_ST] 1 = list overflow -> exact path
     float* __restrict__ row_tau;           // [n_ut * TM][MAX_ST] final filter tau - 2 eps of the strip (scaled units): the finish drops entries below the row's largest
@@ -453,9 +453,9 @@ struct RankTcParams {
                                            // 4 = raise schedule with ratio 1.41 instead of 2 (results stay exact)
 };
 
-// Per-thread epilogue state: one thread owns one (user row, column strip) and its candidate list -- a private,
-// contiguous block of `cap` 8-byte entries (score bits << 32 | item id) in global memory, appended to with one store and
-// a pointer bump.  Items reach a list in increasing id order and every in-place compaction keeps that order; the user's
+// Per-thread epilogue state: one thread owns one (user row, column strip) and its candidate list of up to `cap` 8-byte
+// entries (score bits << 32 | item id) in global memory, interleaved with the lists of the other 31 lanes of its warp
+// (entry e at list[e * 32]) and appended to with one store and a pointer bump.  Items reach a list in increasing id order and every in-place compaction keeps that order; the user's
 // exclusion list (sorted too) is merged against the NEW tail of the list whenever the threshold is raised, and once
 // more in the finish kernel -- the hot loop never branches on it.  Entries that fall below a later threshold are NOT
 // removed eagerly: the finish kernel drops everything below the row's final filter, and a list is compacted in place
@@ -475,23 +475,21 @@ struct RowState {
 
 __device__ __forceinline__ float ent_score(unsigned long long e) { return __uint_as_float((unsigned)(e >> 32)); }
 
-// sequential scan of a list: eight 16-byte loads (16 entries) in flight per thread
+// sequential scan of a list with 16 independent loads in flight.  The 32 lists of a warp are INTERLEAVED in memory
+// (entry e of lane l at list[e * 32 + l]), so the lock-step scans of a raise are fully coalesced: one 256-byte request
+// per warp and entry (thread-private contiguous lists cost 32 sectors per request -- measured 3x slower raises).
 template <typename F>
-__device__ __forceinline__ void scan_list(const unsigned long long* __restrict__ list, int L, F f)
+__device__ __forceinline__ void scan_list(const unsigned long long* list, int L, F f)
 {
     int e = 0;
     for (; e + 16 <= L; e += 16) {
-        ulonglong2 v[8];
+        unsigned long long v[16];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const ulonglong2*>(list + e + 2 * i);
+        for (int i = 0; i < 16; ++i) v[i] = list[(size_t)(e + i) * 32];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { f(v[i].x); f(v[i].y); }
+        for (int i = 0; i < 16; ++i) f(v[i]);
     }
-    for (; e + 2 <= L; e += 2) {
-        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(list + e);
-        f(v.x); f(v.y);
-    }
-    if (e < L) f(list[e]);
+    for (; e < L; ++e) f(list[(size_t)e * 32]);
 }
 
 // named barrier of the ST epilogue warps that own the column strips of the same 32 user rows
@@ -546,7 +544,7 @@ __device__ __forceinline__ void raise_threshold(RowState& st, int K, float eps2,
             unsigned long long v[8];                              // a batch is read before it is written (w <= e0)
             const int nb = st.cnt - e0 < 8 ? st.cnt - e0 : 8;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = i < nb ? list[e0 + i] : 0ull;
+            for (int i = 0; i < 8; ++i) v[i] = i < nb ? list[(size_t)(e0 + i) * 32] : 0ull;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 if (i < nb) {
@@ -563,7 +561,7 @@ __device__ __forceinline__ void raise_threshold(RowState& st, int K, float eps2,
                         }
                     }
                     if (st.ex_w0 != id) {
-                        if (w != e0 + i) list[w] = v[i];
+                        if (w != e0 + i) list[(size_t)w * 32] = v[i];
                         ++w;
                     }
                 }
@@ -652,7 +650,8 @@ __device__ __forceinline__ void raise_threshold(RowState& st, int K, float eps2,
         jf = jf < 0 ? 0 : (jf > NB - 1 ? NB - 1 : jf);
 #pragma unroll 4
         for (int j = NB - 1; j >= 0; --j) alive += (j >= jf) ? (int)hist_mine[j * TM] : 0;
-        want = !JOINT || (L > 2 * alive + 32);
+        want = true;                            // lists stay short: the finish reads them with a 256-byte stride
+        (void)alive;
     }
     // ---- (3) compaction (order-preserving), when at least half of the list is dead weight (always after a solo raise).
     //      Joint raises decide per warp (the lanes run in lock step anyway); no lane has left the function before this
@@ -662,7 +661,7 @@ __device__ __forceinline__ void raise_threshold(RowState& st, int K, float eps2,
     if (go) {
         int w = 0;          // writes trail the reads (w <= e); each batch of 16 is read before it is written
         scan_list(list, L, [&](unsigned long long ent) {
-            if (ent_score(ent) >= st.tau_f) { list[w] = ent; ++w; }
+            if (ent_score(ent) >= st.tau_f) { list[(size_t)w * 32] = ent; ++w; }
         });
         st.cnt = w;
         st.checked = w;
@@ -681,10 +680,10 @@ __device__ __forceinline__ float fmax3(float a, float b, float c)
 __device__ __noinline__ unsigned long long* append4(unsigned long long* wp, float tau_f, float s0, float s1, float s2,
                                                     float s3, int32_t id)
 {
-    if (s0 > tau_f) { *wp = ((unsigned long long)__float_as_uint(s0) << 32) | (uint32_t)id; ++wp; }
-    if (s1 > tau_f) { *wp = ((unsigned long long)__float_as_uint(s1) << 32) | (uint32_t)(id + 1); ++wp; }
-    if (s2 > tau_f) { *wp = ((unsigned long long)__float_as_uint(s2) << 32) | (uint32_t)(id + 2); ++wp; }
-    if (s3 > tau_f) { *wp = ((unsigned long long)__float_as_uint(s3) << 32) | (uint32_t)(id + 3); ++wp; }
+    if (s0 > tau_f) { *wp = ((unsigned long long)__float_as_uint(s0) << 32) | (uint32_t)id; wp += 32; }
+    if (s1 > tau_f) { *wp = ((unsigned long long)__float_as_uint(s1) << 32) | (uint32_t)(id + 1); wp += 32; }
+    if (s2 > tau_f) { *wp = ((unsigned long long)__float_as_uint(s2) << 32) | (uint32_t)(id + 2); wp += 32; }
+    if (s3 > tau_f) { *wp = ((unsigned long long)__float_as_uint(s3) << 32) | (uint32_t)(id + 3); wp += 32; }
     return wp;
 }
 
@@ -877,7 +876,7 @@ __global__ void __launch_bounds__(threads_for(ST), 1) rank_tc_kernel(const RankT
             const float invS = 1.f / us.S;
             const float eps2 = 2.f * eps;
             RowState st;
-            st.list = p.lists + ((size_t)(ut * EPI_WARPS + half * 4 + q) * 32 + lane) * CAP_T;
+            st.list = p.lists + ((size_t)(ut * EPI_WARPS + half * 4 + q) * CAP_T) * 32 + lane;
             st.ex = nullptr; st.n_ex = 0; st.ex_c = 0;
             st.ex_w0 = st.ex_w1 = st.ex_w2 = st.ex_w3 = 0x7fffffff;
             if (valid && p.excl_indptr) {
@@ -930,7 +929,7 @@ __global__ void __launch_bounds__(threads_for(ST), 1) rank_tc_kernel(const RankT
                 // The accumulator goes back to the tensor pipe as soon as this warp's columns are in REGISTERS -- before the
                 // screening of the last 64 of them, whose data-dependent appends then run off the MMA's critical path
                 // (with 64-column strips: all of the screening).
-                st.wp = st.list + st.cnt;
+                st.wp = st.list + (size_t)st.cnt * 32;
                 auto hand_back = [&]() {
                     tc_fence_before();
                     __syncwarp();
@@ -957,7 +956,7 @@ __global__ void __launch_bounds__(threads_for(ST), 1) rank_tc_kernel(const RankT
                         if (c0 + 64 < STRIP_N) tmem_ld_wait(r0);
                     }
                 }
-                st.cnt = (int)(st.wp - st.list);
+                st.cnt = (int)((st.wp - st.list) >> 5);
                 if (!DUMP) {
                     // Raise schedule: after stages 2, 4, 8, 16, ... for EVERY warp at once (a raise stalls the
                     // accumulator hand-off; doing it in all warps at the same stage costs one stall instead of
@@ -1022,7 +1021,7 @@ struct FinishParams {
 // list block of (user tile ut, row r of the tile, strip s)
 __device__ __forceinline__ const unsigned long long* finish_list(const FinishParams& p, int64_t ut, int r, int s)
 {
-    return p.lists + ((size_t)(ut * (4 * p.strips) + s * 4 + (r >> 5)) * 32 + (r & 31)) * (size_t)p.cap;
+    return p.lists + ((size_t)(ut * (4 * p.strips) + s * 4 + (r >> 5)) * p.cap) * 32 + (r & 31);      // entry e at [e * 32]
 }
 
 // STAGED: the candidates' item rows are gathered warp-cooperatively (one coalesced 16-byte cp.async per lane
@@ -1087,7 +1086,7 @@ __global__ void __launch_bounds__(128) rank_tc_finish_kernel(const FinishParams 
         for (int x = 0; x < p.strips; ++x) {
             const unsigned long long* list = finish_list(p, ut, r, x);
             for (int e = tid; e < Ls[x]; e += 128) {
-                const unsigned long long ent = list[e];
+                const unsigned long long ent = list[(size_t)e * 32];
                 if (ent_score(ent) >= tau_f) {
                     const int pos = atomicAdd(&cand_n, 1);
                     sort_buf[pos] = ent & 0xffffffffull;
@@ -1241,7 +1240,7 @@ __global__ void __launch_bounds__(32) rank_tc_finish_warp_kernel(const FinishPar
             const unsigned long long* list = finish_list(p, ut, r, x);
             for (int e0 = 0; e0 < Ls[x]; e0 += 32) {
                 const int e = e0 + lane;
-                const unsigned long long ent = e < Ls[x] ? list[e] : 0ull;
+                const unsigned long long ent = e < Ls[x] ? list[(size_t)e * 32] : 0ull;
                 const bool keep = e < Ls[x] && ent_score(ent) >= tau_f;
                 const unsigned m = __ballot_sync(0xffffffffu, keep);
                 const int pos = L + __popc(m & ((1u << lane) - 1u));

@@ -124,16 +124,16 @@ def bpr_epoch_replay(data, i_index, j_id, U, V, B, lr, reg, use_bias, stats, hin
     L = require_cuda()
     _dev(i_index, torch.int64, "i_index"), _dev(j_id, torch.int32, "j_id")
     _dev(U, torch.float32, "U"), _dev(V, torch.float32, "V"), _dev(B, torch.float32, "B")
-    check(L.b200_bpr_epoch_replay(ptr(i_index), ptr(j_id), i_index.numel(), ptr(data.indptr), ptr(data.indices),
-                                  ptr(data.coo_row), ptr(U), ptr(V), ptr(B), int(U.shape[1]), float(lr), float(reg),
-                                  int(bool(use_bias)), _lib.BPR_LOSS_HINGE if hinge else 0,
-                                  ptr(_dev(stats, torch.int64, "stats")), current_stream()),
+    check(L.b200_bpr_epoch_replay2(ptr(i_index), ptr(j_id), i_index.numel(), ptr(data.indptr), ptr(data.indices),
+                                   ptr(data.coo_row), int(U.shape[0]), int(V.shape[0]), ptr(U), ptr(V), ptr(B), int(U.shape[1]),
+                                   float(lr), float(reg), int(bool(use_bias)), _lib.BPR_LOSS_HINGE if hinge else 0,
+                                   ptr(_dev(stats, torch.int64, "stats")), current_stream()),
           "b200_bpr_epoch_replay")
 
 
 def bpr_train_host(indptr, indices, n_neg, U, V, B, lr, reg, use_bias, max_iter, key=0, replay_seeds=None,
                    atomic=True, on_epoch=None, keep_device=False, replica_sync=False, weighted_seed=None,
-                   neg_weighted=False, hinge=False):
+                   neg_weighted=False, hinge=False, blocked=True):
     """Host-buffer entry of BPR training (what BPR.fit calls): uploads the CSR matrix and the
     factors, runs `max_iter` epochs, writes the trained factors back INTO the given numpy
     arrays U, V, B (pinned staging both ways).
@@ -163,8 +163,8 @@ def bpr_train_host(indptr, indices, n_neg, U, V, B, lr, reg, use_bias, max_iter,
     history = []
     sync = None
     if replica_sync:
-        from .parallel import ItemReplicaSync
-        sync = ItemReplicaSync([dV, dB])
+        from .parallel import make_item_sync
+        sync = make_item_sync([dV, dB])
     if weighted_seed is not None:
         # WBPR, deterministic: ONE mt19937 stream, each sample takes (pos draw, neg draw) from it and
         # the negative is the item of the drawn interaction (recom_wbpr.pyx:125-136)
@@ -200,12 +200,15 @@ def bpr_train_host(indptr, indices, n_neg, U, V, B, lr, reg, use_bias, max_iter,
         for epoch in range(max_iter):
             stats.zero_()
             bpr_epoch(data, n_neg, dU, dV, dB, lr, reg, use_bias, key, epoch, stats, atomic=atomic,
-                      neg_weighted=neg_weighted, hinge=hinge)
+                      neg_weighted=neg_weighted, hinge=hinge, blocked=blocked)
             if sync is not None:
                 sync.exchange()
             if on_epoch:
                 history.append(tuple(stats.cpu().tolist()))
                 on_epoch(epoch, *history[-1])
+    if sync is not None and hasattr(sync, "close"):
+        torch.cuda.synchronize()
+        sync.close()
     for host, dev in ((U, dU), (V, dV), (B, dB)):
         _to_host_into(host, dev)
     return history, ((dU, dV, dB) if keep_device else None)

@@ -152,7 +152,14 @@ def ranking_eval(model, metrics, train_set, test_set, val_set=None, rating_thres
         _full_vector_metrics(model, [metrics[i] for i in full_idx], users, test_pos, excl, n_items, pos_ptr, pos_idx,
                              per_metric, full_idx)
 
-    user_results = [dict(zip(users.tolist(), vals.tolist())) for vals in per_metric]
+    # per-user values carry the dtype the reference's metric returns (MAP: the dtype of scipy's rankdata, float32 here),
+    # so that the reference's own averaging expression `sum(values) / len(values)` rounds the same way
+    user_results = []
+    for m, vals in zip(metrics, per_metric):
+        if type(m) is MAP and _MAP_DTYPE != np.float64:
+            user_results.append(dict(zip(users.tolist(), list(vals.astype(_MAP_DTYPE)))))
+        else:
+            user_results.append(dict(zip(users.tolist(), vals.tolist())))
     avg_results = [sum(r.values()) / len(r) for r in user_results]
     return avg_results, user_results
 

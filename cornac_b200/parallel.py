@@ -75,6 +75,94 @@ class ItemReplicaSync:
             self.ops.apply(t, s, d)
 
 
+class PeerItemExchange:
+    """ItemReplicaSync's exchange as ONE kernel per tensor over NVLink peer memory (b200_item_exchange, csrc/p2p.cu):
+    the ranks map each other's replicas with CUDA IPC at construction (handles travel through torch.distributed); every
+    exchange() then launches, per tensor, a kernel in which this rank reduces and rewrites its slice of every replica.
+    No NCCL collective and no delta buffers on the data path; the result is V <- V_start + sum_r (V_r - V_start), summed in
+    rank order, bit-equal on all ranks.  One process per GPU, all GPUs of one NVLink domain."""
+
+    def __init__(self, tensors, group=None):
+        import ctypes
+        import torch
+        import torch.distributed as dist
+        from . import _lib
+        self._L = _lib.load()
+        self._check = _lib.check
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        if self.world > 8:
+            raise _lib.B200Error("PeerItemExchange supports up to 8 ranks (one NVLink domain)")
+        self.tensors = list(tensors)
+        self.seq = 0
+        self._state = []
+        self._opened = {}                               # (peer rank, IPC handle) -> mapped base: an allocation is opened once
+        for t in self.tensors:
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                raise _lib.B200Error("PeerItemExchange needs contiguous float32 CUDA tensors")
+            flags = torch.zeros(32, dtype=torch.int32, device=t.device)
+            lo, hi = ctypes.c_int64(), ctypes.c_int64()
+            self._check(self._L.b200_item_exchange_slice(self.rank, self.world, t.numel(), ctypes.byref(lo), ctypes.byref(hi)),
+                        "b200_item_exchange_slice")
+            snap = t.view(-1)[lo.value:hi.value].clone() if hi.value > lo.value else torch.zeros(4, device=t.device)
+            mine = []
+            for buf in (t, flags):
+                h = (ctypes.c_ubyte * 64)()
+                off = ctypes.c_int64()
+                self._check(self._L.b200_ipc_export(buf.data_ptr(), h, ctypes.byref(off)), "b200_ipc_export")
+                mine.append((bytes(h), off.value))
+            everyone = [None] * self.world
+            dist.all_gather_object(everyone, mine, group=group)
+            x_ptrs, f_ptrs = (ctypes.c_void_p * self.world)(), (ctypes.c_void_p * self.world)()
+            for r in range(self.world):
+                if r == self.rank:
+                    x_ptrs[r], f_ptrs[r] = t.data_ptr(), flags.data_ptr()
+                    continue
+                for slot, (h, off) in zip((x_ptrs, f_ptrs), everyone[r]):
+                    if (r, h) not in self._opened:
+                        out = ctypes.c_void_p()
+                        self._check(self._L.b200_ipc_open(h, 0, ctypes.byref(out)), "b200_ipc_open")
+                        self._opened[(r, h)] = out.value
+                    slot[r] = self._opened[(r, h)] + off
+            self._state.append(dict(t=t, flags=flags, snap=snap, x_ptrs=x_ptrs, f_ptrs=f_ptrs))
+        torch.cuda.synchronize()
+        dist.barrier(group=group)                       # every flag buffer is zeroed and mapped before the first exchange
+
+    def exchange(self):
+        from ._lib import current_stream
+        self.seq += 1
+        for st in self._state:
+            self._check(self._L.b200_item_exchange(self.rank, self.world, st["x_ptrs"], st["f_ptrs"], st["snap"].data_ptr(),
+                                                   st["t"].numel(), self.seq, current_stream()), "b200_item_exchange")
+
+    def failed(self):
+        """True when a peer did not show up in some exchange (bounded wait expired); synchronises."""
+        return any(int(st["flags"][17].item()) != 0 for st in self._state)
+
+    def close(self):
+        """Unmap the peers' allocations (after the last exchange has completed on every rank)."""
+        import torch.distributed as dist
+        if self._opened:
+            dist.barrier(group=self.group)
+            for base in self._opened.values():
+                self._L.b200_ipc_close(base, 0)
+            self._opened = {}
+
+
+def make_item_sync(tensors, group=None, kind="auto"):
+    """The per-epoch item exchange for `tensors` ([V, B]): 'p2p' = PeerItemExchange (one fused NVLink kernel per tensor),
+    'nccl' = ItemReplicaSync (delta kernels around a torch.distributed all-reduce; also the gloo / CPU test seam),
+    'auto' = p2p on CUDA tensors with the NCCL backend, else nccl."""
+    import torch.distributed as dist
+    if kind == "auto":
+        on_gpu = all(getattr(t, "is_cuda", False) for t in tensors)
+        kind = "p2p" if (on_gpu and dist.is_initialized() and dist.get_backend(group) == "nccl") else "nccl"
+    if kind == "p2p":
+        return PeerItemExchange(tensors, group=group)
+    return ItemReplicaSync(tensors, group=group)
+
+
 def bpr_fit_sharded(indptr, indices, n_items, U, V, B, lr, reg, use_bias, max_iter, key=0, atomic=True):
     """Multi-GPU BPR training of ONE model: call from every rank (one process per GPU, process
     group initialised, torch.cuda.set_device done) with the FULL host CSR matrix and factor arrays.
@@ -164,7 +252,7 @@ def mf_fit_sharded(rid, cid, val, U, V, Bu, Bi, lr, reg, mu, use_bias, max_iter,
     d_rid, d_cid, d_val = dev.ids(r_s), dev.ids(c_s), dev.f32(v_s)
     dU, dBu = dev.f32(U[lo:hi]), dev.f32(Bu[lo:hi])
     dV, dBi = dev.f32(V), dev.f32(Bi)
-    sync = ItemReplicaSync([dV, dBi], ops=dev.ops) if world > 1 else None
+    sync = (ItemReplicaSync([dV, dBi], ops=dev.ops) if dev.ops is not None else make_item_sync([dV, dBi])) if world > 1 else None
     loss_dev = dev.zeros1()
     lr32, reg32 = float(np.float32(lr)), float(np.float32(reg))
     losses, loss = [], np.float32(0)

@@ -21,6 +21,10 @@ DTYPE = np.float32
 
 
 class BaselineOnly(DeviceScoringMixin, Recommender):
+    # score() is three host additions (recom_bo.pyx:183-197, in the arrays' own precision): nothing to precompute in
+    # transform(); a cache of device-computed float32 rows would differ from it in the last bit
+    _B200_EVAL_CACHE_BYTES = 0
+
     def __init__(self, name="BaselineOnly", max_iter=20, learning_rate=0.01, lambda_reg=0.02, early_stop=False,
                  num_threads=0, trainable=True, verbose=False, init_params=None, seed=None, mode="auto",
                  atomic_updates=True):

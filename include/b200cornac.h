@@ -121,6 +121,15 @@ B200_API int b200_bpr_epoch_replay(const int64_t* i_index, const int32_t* j_id, 
                                    float lr, float reg, int use_bias, unsigned flags,
                                    int64_t* stats, void* stream);
 
+/* The same with the row counts of U and V given (n_users x k, n_items x k, B n_items): when the whole model fits the
+ * shared memory of one SM (ML-100K sized problems) the epoch runs on an on-chip copy of the factors.  Same result. */
+B200_API int b200_bpr_epoch_replay2(const int64_t* i_index, const int32_t* j_id, int64_t n_samples,
+                                    const int32_t* indptr, const int32_t* indices, const int32_t* coo_row,
+                                    int64_t n_users, int64_t n_items,
+                                    float* U, float* V, float* B, int k,
+                                    float lr, float reg, int use_bias, unsigned flags,
+                                    int64_t* stats, void* stream);
+
 /* Host-side restatement of RNGVector (recom_bpr.pyx:54-62): boost::random::mt19937 seeded
  * with `seed` + boost::random::uniform_int_distribution<long>(0, hi).  Pure host code, no
  * CUDA.  `fill` writes n consecutive draws from [0, hi] INCLUSIVE into host memory.        */
@@ -273,6 +282,26 @@ B200_API int b200_rank_counts(float* scores, int64_t n_q, int64_t n_items,
  * so every replica ends the epoch with x_start + sum over ranks of the local changes.     */
 B200_API int b200_delta_make(const float* x, const float* snapshot, float* delta, int64_t n, void* stream);
 B200_API int b200_delta_apply(float* x, float* snapshot, const float* delta, int64_t n, void* stream);
+
+/* The same exchange as ONE kernel over NVLink peer memory (one process per GPU, replicas mapped into each other with
+ * CUDA IPC): rank r owns the slice b200_item_exchange_slice(r, world, n) of the vector, reads that slice of EVERY
+ * replica over NVLink, forms  snapshot + sum_r (x_r - snapshot)  in rank order (deterministic, bit-equal everywhere) and
+ * stores it into every replica and into its snapshot -- delta, reduce-scatter, apply and all-gather fused; each byte
+ * crosses NVLink once per direction and there is no delta buffer.
+ *   b200_ipc_export   (host) 64-byte CUDA IPC handle of the allocation containing dev_ptr + the pointer's offset in it
+ *   b200_ipc_open     (host) map a peer's exported allocation; returns the peer pointer (peer access enabled lazily)
+ *   x_peers / flag_peers  host arrays of `world` DEVICE pointers: every rank's replica (f32[n]) and flag buffer
+ *                     (u32[32], zeroed once by its owner before the first exchange), own pointers at [rank]
+ *   snapshot_slice    device f32[hi - lo]: the epoch-start values of the owned slice (= the replica's after each exchange)
+ *   seq               1, 2, 3, ... : the same value on every rank for the same exchange
+ * Every rank must call it once per exchange; the kernel returns when all peers have finished writing this rank's
+ * replica.  A peer that never arrives sets flag word [17] after ~4 s instead of hanging the GPU. */
+B200_API int b200_ipc_export(const void* dev_ptr, void* handle64_out, int64_t* offset_out);
+B200_API int b200_ipc_open(const void* handle64, int64_t offset, void** mapped_out);
+B200_API int b200_ipc_close(void* mapped, int64_t offset);
+B200_API int b200_item_exchange_slice(int rank, int world, int64_t n, int64_t* lo_out, int64_t* hi_out);
+B200_API int b200_item_exchange(int rank, int world, void* const* x_peers, void* const* flag_peers, float* snapshot_slice,
+                                int64_t n, uint32_t seq, void* stream);
 
 #ifdef __cplusplus
 }

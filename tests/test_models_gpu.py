@@ -331,7 +331,10 @@ def test_transform_cache_serves_rank_and_score_without_device_work_and_identical
     from cornac_b200 import engine
     _, train_set, test_set, _, _ = _split_sets()
     rng = np.random.RandomState(0)
-    for mdl in (BPR(k=16, max_iter=10, learning_rate=0.05), MF(k=16, max_iter=10), BaselineOnly(max_iter=5)):
+    bo = BaselineOnly(max_iter=5).fit(train_set)
+    bo.transform(test_set)
+    assert bo._b200_eval_cache is None                       # host-only score(): nothing to cache
+    for mdl in (BPR(k=16, max_iter=10, learning_rate=0.05), MF(k=16, max_iter=10)):
         mdl.fit(train_set)
         users = sorted(set(test_set.uir_tuple[0]))[:40]
         cold = {}

@@ -38,10 +38,56 @@ def mf_check(rank, world):
     return ok
 
 
+def exchange_check(rank, world):
+    """PeerItemExchange (one fused NVLink kernel) against ItemReplicaSync (delta kernels + NCCL all-reduce) on the same
+    local changes: every replica ends at start + sum of all ranks' changes; the p2p result is bit-equal on all ranks."""
+    ok = True
+    for n, reps in ((1_000_003, 3), (128 * 50_000, 2), (7, 2)):
+        g = torch.Generator(device="cuda").manual_seed(100 + n)          # same start on every rank
+        start = torch.randn(n, generator=g, device="cuda")
+        xa, xb = start.clone(), start.clone()
+        pa = parallel.PeerItemExchange([xa])
+        pb = parallel.ItemReplicaSync([xb])
+        want = start.double().clone()
+        for it in range(reps):
+            gl = torch.Generator(device="cuda").manual_seed(7 * n + 31 * it)
+            deltas = [torch.randn(n, generator=gl, device="cuda") * 0.01 * (r + 1) for r in range(world)]     # known on every rank
+            xa += deltas[rank]
+            xb += deltas[rank]
+            pa.exchange()
+            pb.exchange()
+            for d in deltas:
+                want += d.double()
+        torch.cuda.synchronize()
+        err_a = float((xa.double() - want).abs().max())
+        err_b = float((xb.double() - want).abs().max())
+        gathered = [torch.empty_like(xa) for _ in range(world)]
+        dist.all_gather(gathered, xa)
+        same = all(torch.equal(gathered[0], t) for t in gathered)
+        good = err_a < 1e-4 and err_b < 1e-4 and same and not pa.failed()
+        # timing of one exchange of this size (both ways), after the correctness rounds
+        ts = []
+        for sync in (pa, pb):
+            torch.cuda.synchronize(); dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                sync.exchange()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) / 5)
+        pa.close()
+        print("rank %d/%d exchange n=%d: p2p err %.2e, nccl err %.2e, replicas bit-equal=%s, p2p %.3f ms vs nccl path %.3f ms -> %s"
+              % (rank, world, n, err_a, err_b, same, ts[0], ts[1], "OK" if good else "FAIL"), flush=True)
+        ok = ok and good
+    return ok
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ok_x = exchange_check(rank, world)
     rng = np.random.RandomState(4)                      # same data on every rank
     n_users, n_items, k = 20000, 3000, 32
     cu, ci = rng.randint(8, size=n_users), rng.randint(8, size=n_items)
@@ -74,7 +120,7 @@ def main():
     ok = same and untouched and moved and acc > 0.9 and auc_like > 1.0
     print("rank %d/%d users [%d,%d): replicas_equal=%s untouched=%s moved=%s acc=%.3f sep=%.2f -> %s"
           % (rank, world, lo, hi, same, untouched, moved, acc, auc_like, "OK" if ok else "FAIL"), flush=True)
-    ok = mf_check(rank, world) and ok
+    ok = mf_check(rank, world) and ok and ok_x
     flag = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(flag)
     dist.destroy_process_group()
