@@ -394,8 +394,10 @@ def test_edge_cases_empty_rows_tiny_shapes_zero_samples():
 
 @pytest.mark.parametrize("hot", [False, True])
 def test_windowed_replay_is_bit_identical_to_serial_replay(hot, monkeypatch):
-    """bpr_replay_window_kernel (dependency-ordered, 32 warps) == bpr_replay_kernel (one warp, strictly serial),
-    bit for bit, including on a matrix so small that almost every window is one long conflict chain."""
+    """the parallel replay kernels == bpr_replay_kernel (one warp, strictly serial), bit for bit, including on a matrix so
+    small that almost every window is one long conflict chain: the phase-scheduled kernel on an on-chip copy of the
+    factors (default when the model fits shared memory: the `hot` case), the same kernel on the global factors (3), and
+    the 32-sample-window kernel (2)."""
     import torch
     from cornac_b200 import engine
     n_users, n_items, nnz = (40, 12, 300) if hot else (5000, 3000, 60000)
@@ -409,16 +411,17 @@ def test_windowed_replay_is_bit_identical_to_serial_replay(hot, monkeypatch):
     ii = rng.randint(nnz, size=30011).astype(np.int64)
     jj = rng.randint(n_items, size=30011).astype(np.int32)
     outs = []
-    for serial in ("1", "0"):
+    for serial in ("1", "0", "3", "2"):
         monkeypatch.setenv("B200_REPLAY_SERIAL", serial)
         data = _data(indptr, indices)
         U, V, B = _dev(U0), _dev(V0), _dev(B0)
         stats = torch.zeros(2, dtype=torch.int64, device="cuda")
         engine.bpr_epoch_replay(data, _dev(ii), _dev(jj), U, V, B, 0.05, 0.01, True, stats)
         outs.append((U.cpu().numpy(), V.cpu().numpy(), B.cpu().numpy(), stats.cpu().tolist()))
-    for a, b in zip(outs[0][:3], outs[1][:3]):
-        assert np.array_equal(a, b)
-    assert outs[0][3] == outs[1][3]
+    for other in outs[1:]:
+        for a, b in zip(outs[0][:3], other[:3]):
+            assert np.array_equal(a, b)
+        assert outs[0][3] == other[3]
     Ur, Vr, Br = U0.copy(), V0.copy(), B0.copy()
     c_ref, s_ref = O.bpr_replay(ii, jj, indptr, indices, Ur, Vr, Br, 0.05, 0.01, True)
     assert outs[1][3][1] == s_ref and rel_err(outs[1][0], Ur) < 1e-5 and rel_err(outs[1][1], Vr) < 1e-5

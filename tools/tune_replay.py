@@ -26,7 +26,7 @@ for (n_users, n_items, nnz, k) in ((943, 1682, 80000, 10), (100_000, 20_000, 5_0
     data = engine.BprData.from_host(indptr, indices)
     di, dj = torch.from_numpy(ii).cuda(), torch.from_numpy(jj).cuda()
     res = {}
-    for serial in ("1", "0"):
+    for serial in ("1", "2", "3", "0"):
         os.environ["B200_REPLAY_SERIAL"] = serial
         U, V, B = (torch.from_numpy(x.copy()).cuda() for x in (U0, V0, B0))
         stats = torch.zeros(2, dtype=torch.int64, device="cuda")
@@ -40,5 +40,6 @@ for (n_users, n_items, nnz, k) in ((943, 1682, 80000, 10), (100_000, 20_000, 5_0
     t0 = time.perf_counter()
     O.bpr_replay(ii, jj, indptr, indices, Ur, Vr, Br, 0.05, 0.01, True)
     cpu = n / (time.perf_counter() - t0)
-    print("%d x %d x %d k=%d: windowed %.2f M/s, serial-warp %.2f M/s, oracle 1 thread %.2f M samples/s"
-          % (n_users, n_items, nnz, k, res["0"] / 1e6, res["1"] / 1e6, cpu / 1e6), flush=True)
+    print("%d x %d x %d k=%d: scheduled (default; on-chip model when it fits) %.2f M/s, scheduled on global factors %.2f M/s, "
+          "32-sample windows %.2f M/s, serial-warp %.2f M/s, oracle 1 thread %.2f M samples/s"
+          % (n_users, n_items, nnz, k, res["0"] / 1e6, res["3"] / 1e6, res["2"] / 1e6, res["1"] / 1e6, cpu / 1e6), flush=True)
