@@ -181,6 +181,15 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr)
 {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// The accumulator hand-back of the follower's (and the leader's) epilogue warps.  A release at cluster scope compiles to
+// MEMBAR.ALL.GPU + ERRBAR, which waits for every outstanding global store of the warp -- the candidate appends: 31 % of
+// all stall samples of the pair kernel (profiles/r02_rank_tc_pair_membar.md).  Nothing written to MEMORY is handed over
+// here: the consumer (the MMA issuer) only needs the TMEM reads of this warp to have completed, which tcgen05.wait::ld +
+// tcgen05.fence::before_thread_sync order before the arrive; so the arrive itself is relaxed.
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t cluster_addr)
+{
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 // wait on a barrier that threads of the PEER CTA arrive on (cluster-scope acquire), with back-off
 __device__ __forceinline__ void mbar_wait_cluster_backoff(uint64_t* bar, uint32_t parity)
 {
@@ -518,13 +527,13 @@ __device__ __forceinline__ float bin_edge(float a, float step, int j) { return f
 // bin j of strip s at hist[(s * NB + j) * TM]; `tau_row` likewise at tau_row[s * TM].
 template <bool JOINT, int ST>
 __device__ __forceinline__ void raise_threshold(RowState& st, int K, float eps2, uint32_t tile, int strip, int cap,
-                                                unsigned long long* tau_row, int* share, unsigned short* hist, int bar_id)
+                                                unsigned long long* tau_row, int* share, unsigned short* hist, int bar_id,
+                                                bool dbg_nocompact = false)
 {
     unsigned long long* my_tau = tau_row + strip * TM;
     int* pair_mine = share + strip * (TM * 4);
     unsigned short* hist_mine = hist + (size_t)strip * NB * TM;
     unsigned long long* __restrict__ list = st.list;
-    (void)cap;
     // The other column strips of this row publish their own lower bound of the row's k-th best score; any such bound
     // (even an old one) is valid for the whole row, so take the largest.  The tag rejects a value the sibling warp left
     // behind from the previous user tile.
@@ -658,6 +667,7 @@ __device__ __forceinline__ void raise_threshold(RowState& st, int K, float eps2,
     //      vote.  A solo raise decides per lane: lanes that could not raise returned above.
     bool go = want;
     if (JOINT) go = __any_sync(0xffffffffu, want);
+    if (dbg_nocompact && L < cap / 2) go = false;      // timing experiment (debug bit 16): compact only lists that are half full
     if (go) {
         int w = 0;          // writes trail the reads (w <= e); each batch of 16 is read before it is written
         scan_list(list, L, [&](unsigned long long ent) {
@@ -909,7 +919,7 @@ __global__ void __launch_bounds__(threads_for(ST), 1) rank_tc_kernel(const RankT
                 if (p.debug & 1) {                 // timing experiment: MMA / TMA feed rate without the screening
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) { if (CG == 2) mbar_arrive_remote(r_acc_empty + 8 * acc); else mbar_arrive(acc_empty + acc); }
+                    if (lane == 0) { if (CG == 2) mbar_arrive_remote_relaxed(r_acc_empty + 8 * acc); else mbar_arrive(acc_empty + acc); }
                     continue;
                 }
                 if (p.debug & 2) {                 // timing experiment: TMEM drain rate (tcgen05.ld only, no screening)
@@ -923,7 +933,7 @@ __global__ void __launch_bounds__(threads_for(ST), 1) rank_tc_kernel(const RankT
                     if (acc_or == 0x12345u) flag = 1;          // keep the loads alive
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) { if (CG == 2) mbar_arrive_remote(r_acc_empty + 8 * acc); else mbar_arrive(acc_empty + acc); }
+                    if (lane == 0) { if (CG == 2) mbar_arrive_remote_relaxed(r_acc_empty + 8 * acc); else mbar_arrive(acc_empty + acc); }
                     continue;
                 }
                 // The accumulator goes back to the tensor pipe as soon as this warp's columns are in REGISTERS -- before the
@@ -933,7 +943,7 @@ __global__ void __launch_bounds__(threads_for(ST), 1) rank_tc_kernel(const RankT
                 auto hand_back = [&]() {
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) { if (CG == 2) mbar_arrive_remote(r_acc_empty + 8 * acc); else mbar_arrive(acc_empty + acc); }
+                    if (lane == 0) { if (CG == 2) mbar_arrive_remote_relaxed(r_acc_empty + 8 * acc); else mbar_arrive(acc_empty + acc); }
                 };
                 if constexpr (STRIP_N == 64) {
                     tmem_ld32_issue(t0, r0);
@@ -973,7 +983,7 @@ __global__ void __launch_bounds__(threads_for(ST), 1) rank_tc_kernel(const RankT
                     unsigned short* hist = hist_share + q * 32 + lane;
                     unsigned long long* tau_row = tau_share + q * 32 + lane;
                     if (scheduled)
-                        raise_threshold<true, ST>(st, p.topk, eps2, (uint32_t)ut, half, CAP_T, tau_row, share, hist, 1 + q);
+                        raise_threshold<true, ST>(st, p.topk, eps2, (uint32_t)ut, half, CAP_T, tau_row, share, hist, 1 + q, (p.debug & 16) != 0);
                     else if (__any_sync(0xffffffffu, st.cnt >= TRIGGER))
                         raise_threshold<false, ST>(st, p.topk, eps2, (uint32_t)ut, half, CAP_T, tau_row, share, hist, 1 + q);
                     if (st.cnt > CAP_T - STRIP_N) { flag = 1; st.cnt = 0; st.checked = 0; st.tau_f = INFINITY; }

@@ -21,6 +21,15 @@ def require_cuda():
     return _lib.load()
 
 
+def warmup():
+    """Create the CUDA context and load libb200cornac.so now instead of inside the first fit()/rank() (a fresh process
+    pays seconds for the context; an experiment that times its models should not charge that to whichever runs first)."""
+    L = require_cuda()
+    torch.zeros(1, device="cuda")
+    torch.cuda.synchronize()
+    return L
+
+
 def _dev(t, dtype, name):
     if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == dtype and t.is_contiguous()):
         raise B200Error("%s must be a contiguous CUDA tensor of dtype %s" % (name, dtype))
@@ -165,37 +174,44 @@ def bpr_train_host(indptr, indices, n_neg, U, V, B, lr, reg, use_bias, max_iter,
     if replica_sync:
         from .parallel import make_item_sync
         sync = make_item_sync([dV, dB])
-    if weighted_seed is not None:
-        # WBPR, deterministic: ONE mt19937 stream, each sample takes (pos draw, neg draw) from it and
-        # the negative is the item of the drawn interaction (recom_wbpr.pyx:125-136)
-        g = MTSampler(weighted_seed)
-        h_ij = np.empty(2 * nnz, dtype=np.int64)
-        h_i = torch.empty(nnz, dtype=torch.int64).pin_memory()
-        h_j = torch.empty(nnz, dtype=torch.int32).pin_memory()
-        host_indices = np.asarray(indices)
+    if weighted_seed is not None or replay_seeds is not None:
+        # Deterministic mode.  BPR: the two mt19937 streams of the reference's RNGVector (recom_bpr.pyx:54-62).  WBPR:
+        # ONE stream, each sample takes (pos draw, neg draw) from it and the negative is the item of the drawn
+        # interaction (recom_wbpr.pyx:125-136).  The epochs are PIPELINED: the host draws epoch e + 1 while the GPU
+        # applies epoch e (three pinned staging sets, fenced by events; per-epoch stats stay on the device and come
+        # back once at the end), unless a per-epoch callback needs the numbers right away.
+        n_sets = 3 if nnz <= (1 << 24) else 2
+        if weighted_seed is not None:
+            g = MTSampler(weighted_seed)
+            h_ij = np.empty(2 * nnz, dtype=np.int64)
+            host_indices = np.asarray(indices)
+        else:
+            g_pos, g_neg = MTSampler(replay_seeds[0]), MTSampler(replay_seeds[1])
+        h_i = [torch.empty(nnz, dtype=torch.int64).pin_memory() for _ in range(n_sets)]
+        h_j = [torch.empty(nnz, dtype=torch.int32).pin_memory() for _ in range(n_sets)]
+        d_i = [torch.empty(nnz, dtype=torch.int64, device="cuda") for _ in range(n_sets)]
+        d_j = [torch.empty(nnz, dtype=torch.int32, device="cuda") for _ in range(n_sets)]
+        fence = [None] * n_sets
+        stats_all = torch.zeros((max_iter, 2), dtype=torch.int64, device="cuda")
         for epoch in range(max_iter):
-            g.fill(nnz - 1, 2 * nnz, out=h_ij)
-            h_i.numpy()[:] = h_ij[0::2]
-            h_j.numpy()[:] = host_indices[h_ij[1::2]]
-            d_i, d_j = h_i.cuda(non_blocking=True), h_j.cuda(non_blocking=True)
-            stats.zero_()
-            bpr_epoch_replay(data, d_i, d_j, dU, dV, dB, lr, reg, use_bias, stats, hinge=hinge)
-            history.append(tuple(stats.cpu().tolist()))
+            b = epoch % n_sets
+            if fence[b] is not None:
+                fence[b].synchronize()          # the upload of the epoch that last used this staging set has finished
+            if weighted_seed is not None:
+                g.fill(nnz - 1, 2 * nnz, out=h_ij)
+                h_i[b].numpy()[:] = h_ij[0::2]
+                h_j[b].numpy()[:] = host_indices[h_ij[1::2]]
+            else:
+                g_pos.fill(nnz - 1, nnz, out=h_i[b].numpy())
+                g_neg.fill(int(n_neg) - 1, nnz, out=h_j[b].numpy())
+            d_i[b].copy_(h_i[b], non_blocking=True)
+            d_j[b].copy_(h_j[b], non_blocking=True)
+            fence[b] = torch.cuda.Event()
+            fence[b].record()
+            bpr_epoch_replay(data, d_i[b], d_j[b], dU, dV, dB, lr, reg, use_bias, stats_all[epoch], hinge=hinge)
             if on_epoch:
-                on_epoch(epoch, *history[-1])
-    elif replay_seeds is not None:
-        g_pos, g_neg = MTSampler(replay_seeds[0]), MTSampler(replay_seeds[1])
-        h_i = torch.empty(nnz, dtype=torch.int64).pin_memory()
-        h_j = torch.empty(nnz, dtype=torch.int32).pin_memory()
-        for epoch in range(max_iter):
-            g_pos.fill(nnz - 1, nnz, out=h_i.numpy())
-            g_neg.fill(int(n_neg) - 1, nnz, out=h_j.numpy())
-            d_i, d_j = h_i.cuda(non_blocking=True), h_j.cuda(non_blocking=True)
-            stats.zero_()
-            bpr_epoch_replay(data, d_i, d_j, dU, dV, dB, lr, reg, use_bias, stats, hinge=hinge)
-            history.append(tuple(stats.cpu().tolist()))      # also fences the staging buffers
-            if on_epoch:
-                on_epoch(epoch, *history[-1])
+                on_epoch(epoch, *stats_all[epoch].cpu().tolist())
+        history = [tuple(r) for r in stats_all.cpu().tolist()]
     else:
         for epoch in range(max_iter):
             stats.zero_()

@@ -137,7 +137,7 @@ class BPR(DeviceScoringMixin, Recommender, ANNMixin):
             self.learning_rate, self.lambda_reg, self.use_bias, self.max_iter,
             key=(int(s_pos) << 31) | int(s_neg), replay_seeds=replay_seeds, atomic=self.atomic_updates,
             hinge=self._b200_hinge,
-            on_epoch=on_epoch if (self.verbose or replay) else None, keep_device=True)
+            on_epoch=on_epoch if self.verbose else None, keep_device=True)
         self._b200_adopt_device(dev[0], dev[1], dev[2], None, self.total_items)
         if self.verbose:
             print("Optimization finished!")
@@ -219,7 +219,7 @@ class WBPR(BPR):
             X.indptr, X.indices, train_set.num_items, self.u_factors, self.i_factors, self.i_biases,
             self.learning_rate, self.lambda_reg, self.use_bias, self.max_iter, key=int(s_vec),
             weighted_seed=get_rng(s_vec).randint(2 ** 31) if replay else None, neg_weighted=True,
-            atomic=self.atomic_updates, on_epoch=(lambda *a: None) if replay else None, keep_device=True)
+            atomic=self.atomic_updates, keep_device=True)
         self._b200_adopt_device(dev[0], dev[1], dev[2], None, self.total_items)
         return self
 

@@ -46,6 +46,8 @@ def ml100k_like(seed=123):
 
 
 if __name__ == "__main__":
+    # CUDA context + library load happen here, not inside the first B200 model's fit(): Train (s) then compares training
+    cornac_b200.engine.warmup()
     rs = RatioSplit(data=ml100k_like(), test_size=0.2, rating_threshold=4.0, exclude_unknowns=True, seed=123, verbose=True)
     models = [
         cornac.models.BPR(k=10, max_iter=200, learning_rate=0.001, lambda_reg=0.01, seed=123, name="BPR (reference, seeded)"),

@@ -57,7 +57,7 @@ if __name__ == "__main__":
     tc = os.environ.get("B200_RANK_TC", "1")
     print("B200_RANK_TC =", tc, " B200_RANK_DEBUG =", os.environ.get("B200_RANK_DEBUG"))
     if os.environ.get("TUNE_ONLY") == "c5":
-        run(1_000_000, 1_000_000, 128, 18944, 100, 100)
+        run(1_000_000, 1_000_000, 128, 18944, int(os.environ.get("TUNE_TOPK", "100")), int(os.environ.get("TUNE_EXCL", "100")))
         sys.exit(0)
     run(1_000_000, 100_000, 64, 4096, 100, 100)
     run(1_000_000, 100_000, 64, 18944, 100, 100)
