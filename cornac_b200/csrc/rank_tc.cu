@@ -487,18 +487,20 @@ __device__ __forceinline__ float ent_score(unsigned long long e) { return __uint
 // sequential scan of a list with 16 independent loads in flight.  The 32 lists of a warp are INTERLEAVED in memory
 // (entry e of lane l at list[e * 32 + l]), so the lock-step scans of a raise are fully coalesced: one 256-byte request
 // per warp and entry (thread-private contiguous lists cost 32 sectors per request -- measured 3x slower raises).
-template <typename F>
+template <int B, typename F>
 __device__ __forceinline__ void scan_list(const unsigned long long* list, int L, F f)
 {
-    int e = 0;
-    for (; e + 16 <= L; e += 16) {
-        unsigned long long v[16];
+    // Every batch -- the last, partial one too -- is ONE round trip of B predicated independent loads: a list lives in L2
+    // (~1 us away under load) and a raise is nothing but such trips in sequence.  (An element-by-element tail loop cost one
+    // trip per entry: 60 us per raise on short lists, 13 % of the epilogue warps' time, profiles/r02_rank_tc.md.)
+    for (int e = 0; e < L; e += B) {
+        unsigned long long v[B];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = list[(size_t)(e + i) * 32];
+        for (int i = 0; i < B; ++i) v[i] = (e + i < L) ? list[(size_t)(e + i) * 32] : 0ull;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) f(v[i]);
+        for (int i = 0; i < B; ++i)
+            if (e + i < L) f(v[i]);
     }
-    for (; e < L; ++e) f(list[(size_t)e * 32]);
 }
 
 // named barrier of the ST epilogue warps that own the column strips of the same 32 user rows
@@ -530,6 +532,7 @@ __device__ __forceinline__ void raise_threshold(RowState& st, int K, float eps2,
                                                 unsigned long long* tau_row, int* share, unsigned short* hist, int bar_id,
                                                 bool dbg_nocompact = false)
 {
+    constexpr int SCAN_B = ST == 2 ? 32 : 16;      // loads in flight per scan batch (the chunk registers are dead during a raise)
     unsigned long long* my_tau = tau_row + strip * TM;
     int* pair_mine = share + strip * (TM * 4);
     unsigned short* hist_mine = hist + (size_t)strip * NB * TM;
@@ -549,13 +552,13 @@ __device__ __forceinline__ void raise_threshold(RowState& st, int K, float eps2,
     //      per round trip (independent loads) into a register window.  Entries are moved only after the first hit.
     if (st.n_ex > 0 && st.checked < st.cnt) {
         int w = st.checked;
-        for (int e0 = st.checked; e0 < st.cnt; e0 += 8) {       // 8 independent id loads per round trip;
-            unsigned long long v[8];                              // a batch is read before it is written (w <= e0)
-            const int nb = st.cnt - e0 < 8 ? st.cnt - e0 : 8;
+        for (int e0 = st.checked; e0 < st.cnt; e0 += 16) {      // 16 independent id loads per round trip;
+            unsigned long long v[16];                             // a batch is read before it is written (w <= e0)
+            const int nb = st.cnt - e0 < 16 ? st.cnt - e0 : 16;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = i < nb ? list[(size_t)(e0 + i) * 32] : 0ull;
+            for (int i = 0; i < 16; ++i) v[i] = i < nb ? list[(size_t)(e0 + i) * 32] : 0ull;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < 16; ++i) {
                 if (i < nb) {
                     const int32_t id = (int32_t)(v[i] & 0xffffffffull);
                     while (st.ex_w0 < id) {                       // advance the window past ids below `id`
@@ -585,7 +588,7 @@ __device__ __forceinline__ void raise_threshold(RowState& st, int K, float eps2,
     if (L == 0) { lo = INFINITY; hi = -INFINITY; }
     else if (!(hi > -INFINITY) || !(lo > -1.0e37f)) {  // this list's score range is not known yet
         lo = INFINITY; hi = -INFINITY;
-        scan_list(list, L, [&](unsigned long long ent) {
+        scan_list<SCAN_B>(list, L, [&](unsigned long long ent) {
             const float sc = ent_score(ent);
             lo = fminf(lo, sc);
             hi = fmaxf(hi, sc);
@@ -616,7 +619,7 @@ __device__ __forceinline__ void raise_threshold(RowState& st, int K, float eps2,
     float new_hi = -INFINITY;
     if (ok) {
         const float inv = 1.f / step;
-        scan_list(list, L, [&](unsigned long long ent) {
+        scan_list<SCAN_B>(list, L, [&](unsigned long long ent) {
             const float sc = ent_score(ent);
             new_hi = fmaxf(new_hi, sc);
             if (sc >= a) {
@@ -670,7 +673,7 @@ __device__ __forceinline__ void raise_threshold(RowState& st, int K, float eps2,
     if (dbg_nocompact && L < cap / 2) go = false;      // timing experiment (debug bit 16): compact only lists that are half full
     if (go) {
         int w = 0;          // writes trail the reads (w <= e); each batch of 16 is read before it is written
-        scan_list(list, L, [&](unsigned long long ent) {
+        scan_list<SCAN_B>(list, L, [&](unsigned long long ent) {
             if (ent_score(ent) >= st.tau_f) { list[(size_t)w * 32] = ent; ++w; }
         });
         st.cnt = w;
@@ -906,6 +909,12 @@ __global__ void __launch_bounds__(threads_for(ST), 1) rank_tc_kernel(const RankT
             tau_share[half * TM + q * 32 + lane] = ((unsigned long long)(uint32_t)ut << 32) | 0xff800000u;   // -inf
             st.tau_f = valid ? -1.0e38f : INFINITY;       // padding items score -inf: never above the filter
             if (p.debug & 8) st.tau_f = INFINITY;         // timing experiment: screening only (nothing is ever listed)
+            if ((p.debug & 32) && valid) {                // timing experiment: start from the PREVIOUS call's final filters (perfect thresholds)
+                float t = -INFINITY;
+#pragma unroll
+                for (int x = 0; x < ST; ++x) t = fmaxf(t, p.row_tau[row * MAX_ST + x]);
+                st.tau_f = t; st.tau = t + eps2;
+            }
             int flag = 0;
             float* dump_row = DUMP ? p.dump + (size_t)(valid ? row : 0) * ((size_t)p.n_it * TN) : nullptr;
             int next_sched = 2;
@@ -974,7 +983,10 @@ __global__ void __launch_bounds__(threads_for(ST), 1) rank_tc_kernel(const RankT
                     // ~K ln 2 entries, so the lists stay short.  A list grows by at most HALF_N entries per
                     // stage: keep cnt <= CAP - HALF_N.
                     const int done = it + 1;
-                    const bool scheduled = done == next_sched;
+                    // ... and once more after the LAST stage: the lists then hold ~K ln(n_it / last raise) entries above a
+                    // stale threshold, every one of which the finish kernel would re-score exactly (a 512-byte gather from V
+                    // per candidate: the finish is HBM-bound on those gathers)
+                    const bool scheduled = (done == next_sched && !(p.debug & 64)) || done == p.n_it;      // bit 64: timing experiment, final raise only
                     if (scheduled) {               // geometric schedule, ratio 2 (or ~1.41 with debug bit 4)
                         const int grown = (p.debug & 4) ? (done * 181) >> 7 : done * 2;
                         next_sched = grown > done ? grown : done + 1;

@@ -262,6 +262,223 @@ ORA_API void ora_bpr_replay(const int64_t *i_index, const int32_t *j_ids, int64_
     *skipped = sk;
 }
 
+/* ------------------------------------------------------------------------- */
+/* f3: VEBPR (cornac/models/bpr/recom_vebpr.pyx).  One sample of the prange loop of
+ * VEBPR._fit_sgd_viewloss (:239-335); v_id < 0 = the user has no viewed item (the BPR fall-back
+ * branch, :246-275).  The expressions are the .pyx expressions with the .pyx types: `floating` = float,
+ * the literals 1.0 / 50.0 are doubles, so (1.0 - alpha) * ... is evaluated in double like in the
+ * generated C.  No item biases.  Returns 1 when skipped.                                         */
+static inline float ora_clip50(float x)
+{
+    if (x > 50.0) x = 50.0; else if (x < -50.0) x = -50.0;        /* :258-261, :296-309 */
+    return x;
+}
+
+static int ora_vebpr_one(const int32_t *indptr, const int32_t *indices,
+                         const int32_t *view_indptr, const int32_t *view_indices,
+                         int64_t u, int32_t i_id, int32_t v_id, int32_t j_id,
+                         float *U, float *V, int k, float lr, float reg, float alpha, int64_t *correct)
+{
+    float *user = U + (size_t)u * k, *item_i = V + (size_t)i_id * k, *item_j = V + (size_t)j_id * k;
+    if (v_id < 0) {                                                 /* :246-275 */
+        if (ora_has_non_zero(indptr, indices, u, j_id)) return 1;
+        float x_uij = 0.0;
+        for (int f = 0; f < k; ++f) x_uij = x_uij + user[f] * (item_i[f] - item_j[f]);
+        x_uij = ora_clip50(x_uij);
+        float delta_ij = 1.0 / (1.0 + exp(x_uij));
+        if (delta_ij < 0.5) ++*correct;
+        for (int f = 0; f < k; ++f) {
+            float u_old = user[f], i_old = item_i[f], j_old = item_j[f];
+            user[f] -= lr * (-delta_ij * (i_old - j_old) + reg * u_old);
+            item_i[f] -= lr * (-delta_ij * u_old + reg * i_old);
+            item_j[f] -= lr * (delta_ij * u_old + reg * j_old);
+        }
+        return 0;
+    }
+    if (ora_has_non_zero(indptr, indices, u, j_id) || ora_has_non_zero(view_indptr, view_indices, u, j_id))
+        return 1;                                                   /* :281-285 */
+    float *item_v = V + (size_t)v_id * k;
+    float x_uij = 0.0, x_uiv = 0.0, x_uvj = 0.0;
+    for (int f = 0; f < k; ++f) {                                   /* :292-295 */
+        x_uij = x_uij + user[f] * (item_i[f] - item_j[f]);
+        x_uiv = x_uiv + user[f] * (item_i[f] - item_v[f]);
+        x_uvj = x_uvj + user[f] * (item_v[f] - item_j[f]);
+    }
+    x_uij = ora_clip50(x_uij); x_uiv = ora_clip50(x_uiv); x_uvj = ora_clip50(x_uvj);
+    float delta_ij = 1.0 / (1.0 + exp(x_uij));                      /* :312-314 */
+    float delta_iv = 1.0 / (1.0 + exp(x_uiv));
+    float delta_vj = 1.0 / (1.0 + exp(x_uvj));
+    if (delta_ij < 0.5 && delta_iv < 0.5 && delta_vj < 0.5) ++*correct;
+    for (int f = 0; f < k; ++f) {                                   /* :321-335 */
+        float u_old = user[f], i_old = item_i[f], v_old = item_v[f], j_old = item_j[f];
+        user[f] -= lr * (-delta_ij * (i_old - j_old) - alpha * delta_iv * (i_old - v_old)
+                         - (1.0 - alpha) * delta_vj * (v_old - j_old) + reg * u_old);
+        item_i[f] -= lr * (-delta_ij * u_old - alpha * delta_iv * u_old + reg * i_old);
+        item_v[f] -= lr * (alpha * delta_iv * u_old - (1.0 - alpha) * delta_vj * u_old + reg * v_old);
+        item_j[f] -= lr * (delta_ij * u_old + (1.0 - alpha) * delta_vj * u_old + reg * j_old);
+    }
+    return 0;
+}
+
+/* One epoch of VEBPR._fit_sgd_viewloss with num_threads = 1: three mt19937 streams (pos in [0, nnz-1], view and
+ * neg in [0, n_items-1], :198-200); the view stream is consumed only for users WITH viewed items, the neg
+ * stream always (:240-280).  trace_* (optional, length nnz) record (i_index, v_id or -1, j_id).            */
+ORA_API void ora_vebpr_fit_sgd(ora_mt19937 *rng_pos, ora_mt19937 *rng_view, ora_mt19937 *rng_neg,
+                               int64_t nnz, int64_t n_items,
+                               const int32_t *user_ids, const int32_t *item_ids, const int32_t *indptr,
+                               const int32_t *view_item_ids, const int32_t *view_indptr,
+                               float *U, float *V, int k, float lr, float reg, float alpha,
+                               int64_t *correct, int64_t *skipped,
+                               int64_t *trace_i, int32_t *trace_v, int32_t *trace_j)
+{
+    int64_t c = 0, sk = 0;
+    for (int64_t s = 0; s < nnz; ++s) {
+        int64_t i_index = (int64_t)(ora_boost_uniform_u64(rng_pos, (uint64_t)(nnz - 1)) % (uint64_t)nnz);   /* :240 */
+        int64_t u = user_ids[i_index];
+        int32_t num_view = view_indptr[u + 1] - view_indptr[u];      /* view_count, :196 */
+        int32_t v_id = -1;
+        if (num_view > 0) {                                         /* :277-278 */
+            int64_t v_index = view_indptr[u] + (int64_t)(ora_boost_uniform_u64(rng_view, (uint64_t)(n_items - 1)) % (uint64_t)num_view);
+            v_id = view_item_ids[v_index];
+        }
+        int32_t j_id = (int32_t)ora_boost_uniform_u64(rng_neg, (uint64_t)(n_items - 1));      /* :250 / :279 */
+        if (trace_i) trace_i[s] = i_index;
+        if (trace_v) trace_v[s] = v_id;
+        if (trace_j) trace_j[s] = j_id;
+        sk += ora_vebpr_one(indptr, item_ids, view_indptr, view_item_ids, u, item_ids[i_index], v_id, j_id,
+                            U, V, k, lr, reg, alpha, &c);
+    }
+    *correct = c;
+    *skipped = sk;
+}
+
+ORA_API void ora_vebpr_replay(const int64_t *i_index, const int32_t *v_ids, const int32_t *j_ids, int64_t n,
+                              const int32_t *user_ids, const int32_t *item_ids, const int32_t *indptr,
+                              const int32_t *view_item_ids, const int32_t *view_indptr,
+                              float *U, float *V, int k, float lr, float reg, float alpha,
+                              int64_t *correct, int64_t *skipped)
+{
+    int64_t c = 0, sk = 0;
+    for (int64_t s = 0; s < n; ++s) {
+        int64_t ii = i_index[s];
+        sk += ora_vebpr_one(indptr, item_ids, view_indptr, view_item_ids, user_ids[ii], item_ids[ii], v_ids[s], j_ids[s],
+                            U, V, k, lr, reg, alpha, &c);
+    }
+    *correct = c;
+    *skipped = sk;
+}
+
+/* ------------------------------------------------------------------------- */
+/* f3: SBPR (cornac/models/sbpr/recom_sbpr.pyx).  One sample of SBPR._fit_sgd (:225-298).
+ * k_index = the sampled position in the user's social-item list (social_indptr[u] + floor(k_rand * n_social));
+ * k_id = social_item_ids[k_index] is read even when the user has NO social item (:231-233) -- then it is some
+ * other user's entry (or, past the end of the array, undefined in the reference: here -1 = never equal to j).
+ * Returns 1 when skipped (:238-240).                                                                  */
+static int ora_sbpr_one(const int32_t *indptr, const int32_t *indices, int64_t u, int32_t i_id, int32_t j_id,
+                        int64_t k_index, int32_t n_social, const int32_t *social_item_ids,
+                        const int32_t *social_item_counts, int64_t n_social_total,
+                        float *U, float *V, float *B, int k, float lr, float lbd_u, float lbd_v, float lbd_b, int use_bias)
+{
+    int32_t k_id = (k_index >= 0 && k_index < n_social_total) ? social_item_ids[k_index] : -1;
+    if (ora_has_non_zero(indptr, indices, u, j_id) || j_id == k_id) return 1;
+    float *user = U + (size_t)u * k, *item_i = V + (size_t)i_id * k, *item_j = V + (size_t)j_id * k;
+    if (n_social == 0) {                                            /* :247-265: BPR, biases always trained */
+        float score = B[i_id] - B[j_id];
+        for (int f = 0; f < k; ++f) score = score + user[f] * (item_i[f] - item_j[f]);
+        float z = 1.0 / (1.0 + exp(score));
+        for (int f = 0; f < k; ++f) {
+            float u_temp = user[f];
+            user[f] += lr * (z * (item_i[f] - item_j[f]) - lbd_u * user[f]);
+            item_i[f] += lr * (z * u_temp - lbd_v * item_i[f]);
+            item_j[f] += lr * (-z * u_temp - lbd_v * item_j[f]);
+        }
+        B[i_id] += lr * (z - lbd_b * B[i_id]);
+        B[j_id] += lr * (-z - lbd_b * B[j_id]);
+        return 0;
+    }
+    float *item_k = V + (size_t)k_id * k;                           /* :269-297: SBPR-2 */
+    float score_ik = B[i_id] - B[k_id];
+    float score_kj = B[k_id] - B[j_id];
+    for (int f = 0; f < k; ++f) {
+        score_ik = score_ik + user[f] * (item_i[f] - item_k[f]);
+        score_kj = score_kj + user[f] * (item_k[f] - item_j[f]);
+    }
+    float s_uk = 1.0 / (1.0 + social_item_counts[k_index]);
+    float z_ik = 1.0 / (1.0 + exp(score_ik * s_uk));
+    float z_kj = 1.0 / (1.0 + exp(score_kj));
+    for (int f = 0; f < k; ++f) {
+        float u_temp = user[f];
+        user[f] += lr * (z_ik * (item_i[f] - item_k[f]) * s_uk + z_kj * (item_k[f] - item_j[f]) - lbd_u * user[f]);
+        item_i[f] += lr * (z_ik * u_temp * s_uk - lbd_v * item_i[f]);
+        item_j[f] += lr * (-z_kj * u_temp - lbd_v * item_j[f]);
+        item_k[f] += lr * (z_kj * u_temp - z_ik * u_temp * s_uk - lbd_v * item_k[f]);
+    }
+    if (use_bias) {
+        B[i_id] += lr * (z_ik * s_uk - lbd_b * B[i_id]);
+        B[j_id] += lr * (-z_kj - lbd_b * B[j_id]);
+        B[k_id] += lr * (z_kj - z_ik * s_uk - lbd_b * B[k_id]);
+    }
+    return 0;
+}
+
+/* position of the sampled social item: social_indptr[u] + (int)floor(k_rand * n_social), k_rand = (float)draw / (float)num_items
+ * (recom_sbpr.pyx:229-232; float product, libm floor on its promotion to double).  The reference is BUILT with -O3 -ffast-math
+ * (setup.py:130-137): gcc hoists the loop-invariant 1 / (float)num_items out of the sample loop and MULTIPLIES, which rounds
+ * differently from the division for about one draw in four (e.g. 20 / 100 * 5 -> 1, 20 * (1/100) * 5 -> 0).  The fixture
+ * tests/golden/sbpr_mid_k16.npz (compiled reference) is reproduced by the reciprocal form only (checked both), so that is
+ * what the oracle -- and the product -- compute.                                                                        */
+static inline int64_t ora_sbpr_k_index(const int32_t *social_indptr, int64_t u, uint64_t draw, int64_t num_items)
+{
+    int32_t n_social = social_indptr[u + 1] - social_indptr[u];
+    volatile float inv_items = 1.0f / ((float)num_items);
+    float k_rand = ((float)(long)draw) * inv_items;
+    return (int64_t)social_indptr[u] + (int)floor(k_rand * n_social);
+}
+
+/* One epoch of SBPR._fit_sgd with num_threads = 1: i_index from rng_pos in [0, nnz-1]; j_id, then the draw behind
+ * k_rand, both from rng_neg in [0, num_items-1] (:225-230).  trace_k records k_index.                           */
+ORA_API void ora_sbpr_fit_sgd(ora_mt19937 *rng_pos, ora_mt19937 *rng_neg, int64_t nnz, int64_t num_items,
+                              const int32_t *user_ids, const int32_t *item_ids, const int32_t *indptr,
+                              const int32_t *social_item_ids, const int32_t *social_item_counts,
+                              const int32_t *social_indptr, int64_t n_social_total,
+                              float *U, float *V, float *B, int k,
+                              float lr, float lbd_u, float lbd_v, float lbd_b, int use_bias,
+                              int64_t *skipped, int64_t *trace_i, int32_t *trace_j, int64_t *trace_k)
+{
+    int64_t sk = 0;
+    for (int64_t s = 0; s < nnz; ++s) {
+        int64_t i_index = (int64_t)ora_boost_uniform_u64(rng_pos, (uint64_t)(nnz - 1));
+        int64_t u = user_ids[i_index];
+        int32_t j_id = (int32_t)ora_boost_uniform_u64(rng_neg, (uint64_t)(num_items - 1));
+        uint64_t kd = ora_boost_uniform_u64(rng_neg, (uint64_t)(num_items - 1));
+        int64_t k_index = ora_sbpr_k_index(social_indptr, u, kd, num_items);
+        if (trace_i) trace_i[s] = i_index;
+        if (trace_j) trace_j[s] = j_id;
+        if (trace_k) trace_k[s] = k_index;
+        sk += ora_sbpr_one(indptr, item_ids, u, item_ids[i_index], j_id, k_index,
+                           social_indptr[u + 1] - social_indptr[u], social_item_ids, social_item_counts, n_social_total,
+                           U, V, B, k, lr, lbd_u, lbd_v, lbd_b, use_bias);
+    }
+    *skipped = sk;
+}
+
+ORA_API void ora_sbpr_replay(const int64_t *i_index, const int32_t *j_ids, const int64_t *k_index, int64_t n,
+                             const int32_t *user_ids, const int32_t *item_ids, const int32_t *indptr,
+                             const int32_t *social_item_ids, const int32_t *social_item_counts,
+                             const int32_t *social_indptr, int64_t n_social_total,
+                             float *U, float *V, float *B, int k,
+                             float lr, float lbd_u, float lbd_v, float lbd_b, int use_bias, int64_t *skipped)
+{
+    int64_t sk = 0;
+    for (int64_t s = 0; s < n; ++s) {
+        int64_t ii = i_index[s], u = user_ids[ii];
+        sk += ora_sbpr_one(indptr, item_ids, u, item_ids[ii], j_ids[s], k_index[s],
+                           social_indptr[u + 1] - social_indptr[u], social_item_ids, social_item_counts, n_social_total,
+                           U, V, B, k, lr, lbd_u, lbd_v, lbd_b, use_bias);
+    }
+    *skipped = sk;
+}
+
 /* Multi-threaded Hogwild port of the same epoch (`prange(schedule='guided')`
  * with one mt19937 pair per thread, recom_bpr.pyx:54-62,231-234).  Only used
  * as the "port" CPU baseline when baseline/_ref is unavailable; racy by design. */

@@ -178,8 +178,92 @@ def eval_case(name, n_users, n_items, nnz, dseed):
     )
 
 
+def vebpr_case(name, n_users, n_items, nnz, n_view, k, max_iter, lr, reg, alpha, seed, dseed):
+    """VEBPR (cornac/models/bpr/recom_vebpr.pyx) on a PurchaseViewDataset: ~30 % of the users have no viewed item
+    (the BPR fall-back branch of the loop, :246-275)."""
+    from cornac.data import PurchaseViewDataset
+    from cornac.models.bpr.recom_vebpr import VEBPR
+    u, i, r = synth_uir(n_users, n_items, nnz, dseed)
+    ds = dataset_from(u, i, r)
+    rng = np.random.RandomState(dseed + 100)
+    viewers = rng.permutation(n_users)[: int(0.7 * n_users)]
+    views = sorted(set(zip(rng.choice(viewers, size=n_view).tolist(), rng.randint(n_items, size=n_view).tolist())))
+    pv = PurchaseViewDataset.attach_view(ds, [(str(a), str(b), 1.0) for a, b in views])
+    m = VEBPR(k=k, max_iter=max_iter, learning_rate=lr, lambda_reg=reg, alpha=alpha, seed=seed).fit(pv)
+    X, W = pv.matrix, pv.view_matrix
+    np.savez_compressed(
+        os.path.join(HERE, name + ".npz"),
+        indptr=X.indptr.astype(np.int32), indices=X.indices.astype(np.int32), data=X.data.astype(np.float32),
+        view_indptr=W.indptr.astype(np.int32), view_indices=W.indices.astype(np.int32),
+        num_users=pv.num_users, num_items=pv.num_items, total_users=m.total_users, total_items=m.total_items,
+        k=k, max_iter=max_iter, lr=lr, reg=reg, alpha=alpha, seed=seed, U=m.u_factor, V=m.i_factor)
+    print(name, "ok")
+
+
+def sbpr_case(name, n_users, n_items, nnz, k, max_iter, lr, lbd_u, lbd_v, lbd_b, use_bias, seed, dseed):
+    """SBPR (cornac/models/sbpr/recom_sbpr.pyx).  The reference's SBPR.fit cannot run as written (it calls
+    self._prepare_data() / self._prepare_social_data() without the train_set argument, :168-169 -> TypeError), so the
+    fixture drives the pieces fit() names, in its order: Recommender.fit, _init, _prepare_data, _prepare_social_data,
+    the two RNGVectors (:173-174) and max_iter calls of the compiled _fit_sgd (:193-300)."""
+    from cornac.data import GraphModality
+    from cornac.models import Recommender
+    from cornac.models.bpr.recom_bpr import RNGVector
+    from cornac.models.sbpr.recom_sbpr import SBPR
+    from scipy.sparse import csr_matrix
+    u, i, r = synth_uir(n_users, n_items, nnz, dseed)
+    ds = dataset_from(u, i, r)
+    rng = np.random.RandomState(dseed + 200)
+    edges = set()
+    for a in range(n_users):
+        if rng.rand() < 0.7:                      # ~30 % of the users have no friend: the plain-BPR branch (:247-265)
+            for b in rng.randint(n_users, size=rng.randint(1, 5)):
+                if a != int(b):
+                    edges.add((a, int(b)))
+    # k_id = social_item_ids[social_indptr[u] + ...] is read even for users WITHOUT social items (:231-233); for such users
+    # at the END of the user range that index is one past the array (undefined behaviour in the reference).  The LAST train
+    # user therefore gets friends, so that every index the kernel reads exists and the fixture is reproducible.
+    last = max(ds.uid_map.values())
+    inv = {v: int(k_) for k_, v in ds.uid_map.items()}
+    edges.update((inv[last], inv[b]) for b in range(3))
+    gm = GraphModality(data=[(str(a), str(b), 1.0) for a, b in sorted(edges)])
+    gm.build(id_map=ds.uid_map)
+    ds.add_modalities(user_graph=gm)
+    m = SBPR(k=k, max_iter=max_iter, learning_rate=lr, lambda_u=lbd_u, lambda_v=lbd_v, lambda_b=lbd_b, use_bias=use_bias, seed=seed)
+    try:
+        m.fit(ds)
+        raise SystemExit("the reference's SBPR.fit ran: regenerate this fixture through fit()")
+    except TypeError:
+        pass
+    m = SBPR(k=k, max_iter=max_iter, learning_rate=lr, lambda_u=lbd_u, lambda_v=lbd_v, lambda_b=lbd_b, use_bias=use_bias, seed=seed)
+    Recommender.fit(m, ds)
+    m._init()
+    X, _, user_ids = m._prepare_data(ds)
+    s_ids, s_cnts, s_ptr = m._prepare_social_data(ds)
+    assert s_ptr[-1] > s_ptr[-2], "the last user must have social items (see above)"
+    rp = RNGVector(1, len(user_ids) - 1, m.rng.randint(2 ** 31))
+    rn = RNGVector(1, ds.num_items - 1, m.rng.randint(2 ** 31))
+    skipped = [m._fit_sgd(rp, rn, 1, user_ids, X.indices, X.indptr, s_ids, s_cnts, s_ptr, m.u_factors, m.i_factors, m.i_biases)
+               for _ in range(max_iter)]
+    train_users = set(ds.uir_tuple[0])
+    rid, cid, val = ds.user_graph.get_train_triplet(train_users, train_users)
+    Y = csr_matrix((val, (rid, cid)), shape=(ds.num_users, ds.num_users))
+    Y.sort_indices()
+    np.savez_compressed(
+        os.path.join(HERE, name + ".npz"),
+        indptr=X.indptr.astype(np.int32), indices=X.indices.astype(np.int32), data=X.data.astype(np.float32),
+        graph_indptr=Y.indptr.astype(np.int32), graph_indices=Y.indices.astype(np.int32),
+        social_item_ids=s_ids.astype(np.int32), social_item_counts=s_cnts.astype(np.int32), social_indptr=s_ptr.astype(np.int32),
+        num_users=ds.num_users, num_items=ds.num_items, total_users=m.total_users, total_items=m.total_items,
+        k=k, max_iter=max_iter, lr=lr, lbd_u=lbd_u, lbd_v=lbd_v, lbd_b=lbd_b, use_bias=use_bias, seed=seed,
+        skipped=np.array(skipped, np.int64), U=m.u_factors, V=m.i_factors, B=m.i_biases)
+    print(name, "ok")
+
+
 if __name__ == "__main__":
     print("cornac", cornac.__version__)
+    if len(sys.argv) > 1 and sys.argv[1] == "sbpr":          # regenerate one fixture
+        sbpr_case("sbpr_mid_k16", 150, 100, 2000, k=16, max_iter=8, lr=0.05, lbd_u=0.02, lbd_v=0.03, lbd_b=0.04, use_bias=True, seed=19, dseed=10)
+        sys.exit(0)
     bpr_case("bpr_small_k10", 60, 40, 600, k=10, max_iter=30, lr=0.05, reg=0.01, use_bias=True, seed=123, dseed=1)
     bpr_case("bpr_mid_k32", 300, 200, 5700, k=32, max_iter=5, lr=0.05, reg=0.01, use_bias=True, seed=7, dseed=2)
     bpr_case("bpr_nobias_k16", 120, 90, 1500, k=16, max_iter=8, lr=0.02, reg=0.001, use_bias=False, seed=42, dseed=3)
@@ -190,3 +274,5 @@ if __name__ == "__main__":
     wbpr_case("wbpr_mid_k16", 150, 100, 2000, k=16, max_iter=10, lr=0.05, reg=0.01, seed=11, dseed=6)
     bo_case("bo_mid", 150, 100, 2000, max_iter=15, lr=0.01, reg=0.02, seed=5, dseed=8)
     mmmf_case("mmmf_mid_k16", 150, 100, 2000, k=16, max_iter=10, lr=0.02, reg=0.01, seed=13, dseed=7)
+    vebpr_case("vebpr_mid_k16", 150, 100, 2000, n_view=1500, k=16, max_iter=8, lr=0.05, reg=0.01, alpha=0.3, seed=17, dseed=9)
+    sbpr_case("sbpr_mid_k16", 150, 100, 2000, k=16, max_iter=8, lr=0.05, lbd_u=0.02, lbd_v=0.03, lbd_b=0.04, use_bias=True, seed=19, dseed=10)

@@ -129,6 +129,45 @@ def test_mmmf_fit_matches_compiled_reference():
     assert rel_err(r["U"], g["U"]) < TOL and rel_err(r["V"], g["V"]) < TOL and rel_err(r["B"], g["B"]) < TOL
 
 
+def test_vebpr_fit_matches_compiled_reference():
+    """VEBPR (recom_vebpr.pyx:214-337): three RNG streams, the view stream consumed only for users with viewed items."""
+    g = golden("vebpr_mid_k16")
+    r = O.vebpr_fit(g["indptr"], g["indices"], g["view_indptr"], g["view_indices"], int(g["num_items"]), int(g["total_users"]),
+                    int(g["total_items"]), int(g["k"]), int(g["max_iter"]), float(g["lr"]), float(g["reg"]), float(g["alpha"]),
+                    int(g["seed"]), trace=True)
+    assert rel_err(r["U"], g["U"]) < TOL and rel_err(r["V"], g["V"]) < TOL
+    # both branches of the loop are exercised, and replaying the traced stream reproduces the fit
+    v0 = r["v_id"][0]
+    assert (v0 < 0).any() and (v0 >= 0).any()
+    _, U, V, _ = O.bpr_init(int(g["seed"]), int(g["total_users"]), int(g["total_items"]), int(g["k"]))
+    for e in range(int(g["max_iter"])):
+        c, sk = O.vebpr_replay(r["i_index"][e], r["v_id"][e], r["j_id"][e], g["indptr"], g["indices"], g["view_indptr"],
+                               g["view_indices"], U, V, float(g["lr"]), float(g["reg"]), float(g["alpha"]))
+        assert (c, sk) == r["stats"][e]
+    assert np.array_equal(U, r["U"]) and np.array_equal(V, r["V"])
+
+
+def test_sbpr_fit_matches_compiled_reference():
+    """SBPR._fit_sgd (recom_sbpr.pyx:193-300) and _prepare_social_data (:119-145), driven as SBPR.fit names them."""
+    g = golden("sbpr_mid_k16")
+    ids, cnts, ptr = O.sbpr_social_items(g["indptr"], g["indices"], g["graph_indptr"], g["graph_indices"])
+    assert np.array_equal(ids, g["social_item_ids"]) and np.array_equal(cnts, g["social_item_counts"])
+    assert np.array_equal(ptr, g["social_indptr"])
+    r = O.sbpr_fit(g["indptr"], g["indices"], ids, cnts, ptr, int(g["num_items"]), int(g["total_users"]), int(g["total_items"]),
+                   int(g["k"]), int(g["max_iter"]), float(g["lr"]), float(g["lbd_u"]), float(g["lbd_v"]), float(g["lbd_b"]),
+                   bool(g["use_bias"]), int(g["seed"]), trace=True)
+    assert r["stats"] == g["skipped"].tolist()
+    assert rel_err(r["U"], g["U"]) < TOL and rel_err(r["V"], g["V"]) < TOL and rel_err(r["B"], g["B"]) < TOL
+    n_soc = np.diff(ptr)
+    assert (n_soc == 0).any() and (n_soc > 0).any()           # both loop bodies (plain BPR / SBPR-2) are exercised
+    _, U, V, B = O.bpr_init(int(g["seed"]), int(g["total_users"]), int(g["total_items"]), int(g["k"]))
+    for e in range(int(g["max_iter"])):
+        sk = O.sbpr_replay(r["i_index"][e], r["j_id"][e], r["k_index"][e], g["indptr"], g["indices"], ids, cnts, ptr, U, V, B,
+                           float(g["lr"]), float(g["lbd_u"]), float(g["lbd_v"]), float(g["lbd_b"]), bool(g["use_bias"]))
+        assert sk == r["stats"][e]
+    assert np.array_equal(U, r["U"]) and np.array_equal(V, r["V"]) and np.array_equal(B, r["B"])
+
+
 # ---------------------------------------------------------------------------------------------
 # WMF (SURVEY 8(f)4) -- the reference's TensorFlow graph cannot run here: PARITY UNPINNED.  The restatement in
 # oracle/wmf_oracle.py is only checked for internal consistency.

@@ -42,6 +42,8 @@ def run(n_users, n_items, k, n_q, topk, n_excl, reps=3):
         assert rc == 0, L.b200_last_error()
     go()
     torch.cuda.synchronize()
+    if os.environ.get("TUNE_DEBUG_AFTER_WARMUP"):      # e.g. 32: the timed calls start from the warm-up call's final thresholds
+        os.environ["B200_RANK_DEBUG"] = os.environ["TUNE_DEBUG_AFTER_WARMUP"]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
