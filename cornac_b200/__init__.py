@@ -8,7 +8,7 @@ Layers:  include/b200cornac.h (C ABI)  <-  cornac_b200/csrc (CUDA)  <-  cornac_b
 plug-ins).  The plug-in classes need the `cornac` package importable (they subclass its
 Recommender so that cornac.Experiment accepts them); the engine does not.
 """
-__all__ = ["BPR", "WBPR", "MMMF", "MF", "WMF", "BaselineOnly", "engine", "B200Error"]
+__all__ = ["BPR", "WBPR", "MMMF", "VEBPR", "SBPR", "MF", "WMF", "BaselineOnly", "engine", "B200Error"]
 
 from ._lib import B200Error  # noqa: F401
 
@@ -23,6 +23,12 @@ def __getattr__(name):
     if name == "MMMF":
         from .recom_bpr import MMMF
         return MMMF
+    if name == "VEBPR":
+        from .recom_bprx import VEBPR
+        return VEBPR
+    if name == "SBPR":
+        from .recom_bprx import SBPR
+        return SBPR
     if name == "MF":
         from .recom_mf import MF
         return MF

@@ -40,6 +40,15 @@ SIGNATURES = {
     "b200_mt_sampler_destroy": (None, [_vp]),
     "b200_mt_sampler_fill_i64": (_int, [_vp, _i64, _i64, _vp]),
     "b200_mt_sampler_fill_i32": (_int, [_vp, _i64, _i64, _vp]),
+    "b200_vebpr_epoch": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _int, _f32, _f32, _f32, _u64, _u64, _i64,
+                                _vp, _vp]),
+    "b200_vebpr_epoch_replay": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _f32, _f32, _f32, _vp, _vp]),
+    "b200_vebpr_draw_host": (_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "b200_sbpr_epoch": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _int, _f32, _f32, _f32, _f32,
+                               _int, _u64, _u64, _i64, _vp, _vp]),
+    "b200_sbpr_epoch_replay": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _int,
+                                      _f32, _f32, _f32, _f32, _int, _vp, _vp]),
+    "b200_sbpr_draw_host": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _vp, _vp]),
     "b200_mf_epoch": (_int, [_vp, _vp, _vp, _i64, _int, _i64, _i64, _vp, _vp, _vp, _vp, _int, _f32, _f32, _f32, _int, _int,
                              _c.c_uint, _vp, _vp]),
     "b200_wmf_step": (_int, [_vp, _vp, _vp, _vp, _int, _i64, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp,

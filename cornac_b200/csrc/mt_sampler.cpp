@@ -137,3 +137,58 @@ extern "C" int b200_mt_sampler_fill_i32(b200_mt_sampler* s, int64_t hi, int64_t 
     for (int64_t t = 0; t < n; ++t) out[t] = (int32_t)s->draw((uint64_t)hi);
     return B200_OK;
 }
+
+// ---------------------------------------------------------------------------------------
+// Seeded sample streams of the BPR siblings whose draws depend on the data (so they cannot be produced by three
+// independent fill calls): the streams are drawn here, sample by sample, in the reference's order.
+
+// VEBPR._fit_sgd_viewloss (cornac/models/bpr/recom_vebpr.pyx:240-280): per sample  i_index <- pos % nnz;  then, ONLY when
+// the user has viewed items,  v <- view_indices[view_indptr[u] + view_draw % num_view]  (else v = -1);  then  j <- neg.
+extern "C" int b200_vebpr_draw_host(b200_mt_sampler* pos, b200_mt_sampler* view, b200_mt_sampler* neg, int64_t nnz, int64_t n_items,
+                                    const int32_t* coo_row, const int32_t* view_indptr, const int32_t* view_indices,
+                                    int64_t n_samples, int64_t* i_index_out, int32_t* v_id_out, int32_t* j_id_out)
+{
+    if (!pos || !view || !neg || nnz < 1 || n_items < 1 || n_items > 0x7fffffffLL || n_samples < 0 || !coo_row || !view_indptr ||
+        (n_samples > 0 && (!i_index_out || !v_id_out || !j_id_out))) {
+        b200::set_error("b200_vebpr_draw_host: bad argument");
+        return B200_ERR_INVALID;
+    }
+    for (int64_t s = 0; s < n_samples; ++s) {
+        const int64_t ii = (int64_t)(pos->draw((uint64_t)(nnz - 1)) % (uint64_t)nnz);
+        const int32_t u = coo_row[ii];
+        const int32_t num_view = view_indptr[u + 1] - view_indptr[u];
+        int32_t v = -1;
+        if (num_view > 0) v = view_indices[view_indptr[u] + (int64_t)(view->draw((uint64_t)(n_items - 1)) % (uint64_t)num_view)];
+        i_index_out[s] = ii;
+        v_id_out[s] = v;
+        j_id_out[s] = (int32_t)neg->draw((uint64_t)(n_items - 1));
+    }
+    return B200_OK;
+}
+
+// SBPR._fit_sgd (cornac/models/sbpr/recom_sbpr.pyx:225-232): per sample  i_index <- pos;  j <- neg;  k_rand <- neg (second draw
+// of the same stream) / num_items;  k_index = social_indptr[u] + (int)floor(k_rand * n_social).  k_rand is the float
+// product draw * (1 / num_items): the reference's build (-O3 -ffast-math) hoists the reciprocal out of the loop, and only
+// this form reproduces the compiled reference's samples (fixture tests/golden/sbpr_mid_k16.npz; the division does not).
+extern "C" int b200_sbpr_draw_host(b200_mt_sampler* pos, b200_mt_sampler* neg, int64_t nnz, int64_t n_items,
+                                   const int32_t* coo_row, const int32_t* social_indptr, int64_t n_samples,
+                                   int64_t* i_index_out, int32_t* j_id_out, int64_t* k_index_out)
+{
+    if (!pos || !neg || nnz < 1 || n_items < 1 || n_items > 0x7fffffffLL || n_samples < 0 || !coo_row || !social_indptr ||
+        (n_samples > 0 && (!i_index_out || !j_id_out || !k_index_out))) {
+        b200::set_error("b200_sbpr_draw_host: bad argument");
+        return B200_ERR_INVALID;
+    }
+    volatile float inv_items = 1.0f / (float)n_items;
+    for (int64_t s = 0; s < n_samples; ++s) {
+        const int64_t ii = (int64_t)pos->draw((uint64_t)(nnz - 1));
+        const int32_t u = coo_row[ii];
+        const int32_t j = (int32_t)neg->draw((uint64_t)(n_items - 1));
+        const float k_rand = (float)(long)neg->draw((uint64_t)(n_items - 1)) * inv_items;
+        const int32_t n_social = social_indptr[u + 1] - social_indptr[u];
+        i_index_out[s] = ii;
+        j_id_out[s] = j;
+        k_index_out[s] = (int64_t)social_indptr[u] + (int)__builtin_floor((double)(k_rand * (float)n_social));
+    }
+    return B200_OK;
+}

@@ -230,6 +230,97 @@ def bpr_train_host(indptr, indices, n_neg, U, V, B, lr, reg, use_bias, max_iter,
     return history, ((dU, dV, dB) if keep_device else None)
 
 
+def tri_train_host(kind, indptr, indices, aux, n_items, U, V, B, hyper, max_iter, key=0, replay_seeds=None, on_epoch=None,
+                   keep_device=False):
+    """Host-buffer entry of the BPR siblings with a third item per sample (csrc/bprx.cu), what VEBPR.fit / SBPR.fit call.
+
+    kind "vebpr": aux = (view_indptr, view_indices) of the viewed-not-purchased CSR, hyper = dict(lr, reg, alpha), B = None,
+                  replay_seeds = (pos, view, neg) mt19937 seeds of the three RNGVectors (recom_vebpr.pyx:198-200);
+    kind "sbpr":  aux = (social_indptr, social_item_ids, social_item_counts), hyper = dict(lr, lambda_u, lambda_v, lambda_b,
+                  use_bias), replay_seeds = (pos, neg) (recom_sbpr.pyx:173-174).
+    replay_seeds given -> the seeded streams are drawn on the host in the reference's order (b200_*_draw_host) and applied
+    by the serial-equivalent replay kernel, the host drawing epoch e + 1 while the GPU applies epoch e; else Hogwild epochs
+    with on-device Philox sampling keyed by `key`.  Trained factors are written back INTO U, V (, B).
+    Returns (per-epoch (correct, skipped) list, device tensors (U, V, B or None) if keep_device)."""
+    L = require_cuda()
+    assert kind in ("vebpr", "sbpr")
+    data = BprData.from_host(indptr, indices)
+    nnz = data.nnz
+    coo = data.coo_row
+    aux_dev = [to_device(np.ascontiguousarray(a, dtype=np.int32), torch.int32) if len(a) else
+               torch.zeros(1, dtype=torch.int32, device="cuda") for a in aux]
+    dU, dV = to_device(U, torch.float32), to_device(V, torch.float32)
+    dB = to_device(B, torch.float32) if B is not None else None
+    n_users, k = int(dU.shape[0]), int(dU.shape[1])
+    max_iter = int(max_iter)
+    stats_all = torch.zeros((max(max_iter, 1), 2), dtype=torch.int64, device="cuda")
+    f32 = lambda x: float(np.float32(x))          # noqa: E731
+    st = current_stream
+
+    def hogwild(epoch):
+        if kind == "vebpr":
+            check(L.b200_vebpr_epoch(ptr(data.indptr), ptr(data.indices), ptr(coo), n_users, int(n_items), nnz,
+                                     ptr(aux_dev[0]), ptr(aux_dev[1]), ptr(dU), ptr(dV), k, f32(hyper["lr"]), f32(hyper["reg"]),
+                                     f32(hyper["alpha"]), int(key) & ((1 << 64) - 1), epoch, nnz, ptr(stats_all[epoch]), st()),
+                  "b200_vebpr_epoch")
+        else:
+            check(L.b200_sbpr_epoch(ptr(data.indptr), ptr(data.indices), ptr(coo), n_users, int(n_items), nnz,
+                                    ptr(aux_dev[0]), ptr(aux_dev[1]), ptr(aux_dev[2]), len(aux[1]), ptr(dU), ptr(dV), ptr(dB), k,
+                                    f32(hyper["lr"]), f32(hyper["lambda_u"]), f32(hyper["lambda_v"]), f32(hyper["lambda_b"]),
+                                    int(bool(hyper["use_bias"])), int(key) & ((1 << 64) - 1), epoch, nnz, ptr(stats_all[epoch]), st()),
+                  "b200_sbpr_epoch")
+
+    if replay_seeds is None:
+        for epoch in range(max_iter):
+            hogwild(epoch)
+            if on_epoch:
+                on_epoch(epoch, *stats_all[epoch].cpu().tolist())
+    else:
+        gens = [MTSampler(s_) for s_ in replay_seeds]
+        h_coo = np.repeat(np.arange(len(indptr) - 1, dtype=np.int32), np.diff(np.asarray(indptr)).astype(np.int64))
+        h_aux = [np.ascontiguousarray(a, dtype=np.int32) for a in aux]
+        third = torch.int32 if kind == "vebpr" else torch.int64
+        n_sets = 2
+        h_i = [torch.empty(nnz, dtype=torch.int64).pin_memory() for _ in range(n_sets)]
+        h_j = [torch.empty(nnz, dtype=torch.int32).pin_memory() for _ in range(n_sets)]
+        h_t = [torch.empty(nnz, dtype=third).pin_memory() for _ in range(n_sets)]
+        d_i = [torch.empty(nnz, dtype=torch.int64, device="cuda") for _ in range(n_sets)]
+        d_j = [torch.empty(nnz, dtype=torch.int32, device="cuda") for _ in range(n_sets)]
+        d_t = [torch.empty(nnz, dtype=third, device="cuda") for _ in range(n_sets)]
+        fence = [None] * n_sets
+        for epoch in range(max_iter):
+            b = epoch % n_sets
+            if fence[b] is not None:
+                fence[b].synchronize()
+            if kind == "vebpr":
+                check(L.b200_vebpr_draw_host(gens[0]._h, gens[1]._h, gens[2]._h, nnz, int(n_items), h_coo.ctypes.data,
+                                             h_aux[0].ctypes.data, h_aux[1].ctypes.data, nnz, h_i[b].data_ptr(), h_t[b].data_ptr(),
+                                             h_j[b].data_ptr()), "b200_vebpr_draw_host")
+            else:
+                check(L.b200_sbpr_draw_host(gens[0]._h, gens[1]._h, nnz, int(n_items), h_coo.ctypes.data, h_aux[0].ctypes.data, nnz,
+                                            h_i[b].data_ptr(), h_j[b].data_ptr(), h_t[b].data_ptr()), "b200_sbpr_draw_host")
+            d_i[b].copy_(h_i[b], non_blocking=True), d_j[b].copy_(h_j[b], non_blocking=True), d_t[b].copy_(h_t[b], non_blocking=True)
+            fence[b] = torch.cuda.Event()
+            fence[b].record()
+            if kind == "vebpr":
+                check(L.b200_vebpr_epoch_replay(ptr(d_i[b]), ptr(d_t[b]), ptr(d_j[b]), nnz, ptr(data.indptr), ptr(data.indices), ptr(coo),
+                                                ptr(aux_dev[0]), ptr(aux_dev[1]), ptr(dU), ptr(dV), k, f32(hyper["lr"]), f32(hyper["reg"]),
+                                                f32(hyper["alpha"]), ptr(stats_all[epoch]), st()), "b200_vebpr_epoch_replay")
+            else:
+                check(L.b200_sbpr_epoch_replay(ptr(d_i[b]), ptr(d_j[b]), ptr(d_t[b]), nnz, ptr(data.indptr), ptr(data.indices), ptr(coo),
+                                               ptr(aux_dev[0]), ptr(aux_dev[1]), ptr(aux_dev[2]), len(aux[1]), ptr(dU), ptr(dV), ptr(dB), k,
+                                               f32(hyper["lr"]), f32(hyper["lambda_u"]), f32(hyper["lambda_v"]), f32(hyper["lambda_b"]),
+                                               int(bool(hyper["use_bias"])), ptr(stats_all[epoch]), st()), "b200_sbpr_epoch_replay")
+            if on_epoch:
+                on_epoch(epoch, *stats_all[epoch].cpu().tolist())
+    history = [tuple(r) for r in stats_all[:max_iter].cpu().tolist()]
+    _to_host_into(U, dU)
+    _to_host_into(V, dV)
+    if B is not None:
+        _to_host_into(B, dB)
+    return history, ((dU, dV, dB) if keep_device else None)
+
+
 _COPY_STREAMS = {}
 
 

@@ -140,6 +140,53 @@ B200_API int b200_mt_sampler_fill_i64(b200_mt_sampler* s, int64_t hi, int64_t n,
 B200_API int b200_mt_sampler_fill_i32(b200_mt_sampler* s, int64_t hi, int64_t n, int32_t* out_host);
 
 /* ------------------------------------------------------------------------------------
+ * BPR siblings with a third item per sample, csrc/bprx.cu.  Common arguments:
+ *   indptr / indices  device int32 CSR of the (purchase) interactions, rows sorted;  coo_row device int32[nnz] = row of
+ *                     every interaction (BPR._prepare_data, recom_bpr.pyx:154-161)
+ *   stats             device int64[2], accumulated: [0] correct (VEBPR only), [1] skipped
+ *   *_epoch           one Hogwild epoch of n_samples samples drawn on the device (Philox keyed by seed, epoch) in the
+ *                     reference's law; scatter with red.global.add
+ *   *_epoch_replay    an explicit sample stream (device arrays, from *_draw_host) applied with the SERIAL result, arithmetic
+ *                     in the reference's operation order and types: trained factors match the seeded single-thread
+ *                     reference within 1e-4
+ *   *_draw_host       (host, no CUDA) the seeded streams in the reference's RNG order; all pointers are HOST pointers
+ *
+ * VEBPR: replaces VEBPR._fit_sgd_viewloss (bpr/recom_vebpr.pyx:214-337).  view_indptr / view_indices = CSR of the
+ * "viewed but not purchased" matrix (PurchaseViewDataset.view_matrix, sorted rows, same shape as the purchase matrix);
+ * v_id = the sampled viewed item, -1 for a user without viewed items (BPR fall-back branch).  No item biases.        */
+B200_API int b200_vebpr_epoch(const int32_t* indptr, const int32_t* indices, const int32_t* coo_row, int64_t n_users,
+                              int64_t n_items, int64_t nnz, const int32_t* view_indptr, const int32_t* view_indices,
+                              float* U, float* V, int k, float lr, float reg, float alpha, uint64_t seed, uint64_t epoch,
+                              int64_t n_samples, int64_t* stats, void* stream);
+B200_API int b200_vebpr_epoch_replay(const int64_t* i_index, const int32_t* v_id, const int32_t* j_id, int64_t n_samples,
+                                     const int32_t* indptr, const int32_t* indices, const int32_t* coo_row,
+                                     const int32_t* view_indptr, const int32_t* view_indices,
+                                     float* U, float* V, int k, float lr, float reg, float alpha, int64_t* stats, void* stream);
+B200_API int b200_vebpr_draw_host(b200_mt_sampler* pos, b200_mt_sampler* view, b200_mt_sampler* neg, int64_t nnz, int64_t n_items,
+                                  const int32_t* coo_row, const int32_t* view_indptr, const int32_t* view_indices,
+                                  int64_t n_samples, int64_t* i_index_out, int32_t* v_id_out, int32_t* j_id_out);
+/* SBPR: replaces SBPR._fit_sgd (sbpr/recom_sbpr.pyx:193-300).  social_indptr / social_item_ids / social_item_counts =
+ * the output of SBPR._prepare_social_data (:119-145): per user the items her friends have and she has not, and how many
+ * friends have each; n_social = len(social_item_ids).  k_index = the sampled POSITION in social_item_ids (the entry is
+ * read, and compared with j, also for users without social items, as in the reference; positions past the end compare
+ * unequal).  lambda_u / lambda_v / lambda_b regularise users / items / biases; use_bias gates the bias updates of the
+ * SBPR-2 branch only (the BPR fall-back branch always trains them, :263-264).                                        */
+B200_API int b200_sbpr_epoch(const int32_t* indptr, const int32_t* indices, const int32_t* coo_row, int64_t n_users,
+                             int64_t n_items, int64_t nnz, const int32_t* social_indptr, const int32_t* social_item_ids,
+                             const int32_t* social_item_counts, int64_t n_social,
+                             float* U, float* V, float* B, int k, float lr, float lambda_u, float lambda_v, float lambda_b,
+                             int use_bias, uint64_t seed, uint64_t epoch, int64_t n_samples, int64_t* stats, void* stream);
+B200_API int b200_sbpr_epoch_replay(const int64_t* i_index, const int32_t* j_id, const int64_t* k_index, int64_t n_samples,
+                                    const int32_t* indptr, const int32_t* indices, const int32_t* coo_row,
+                                    const int32_t* social_indptr, const int32_t* social_item_ids,
+                                    const int32_t* social_item_counts, int64_t n_social,
+                                    float* U, float* V, float* B, int k, float lr, float lambda_u, float lambda_v, float lambda_b,
+                                    int use_bias, int64_t* stats, void* stream);
+B200_API int b200_sbpr_draw_host(b200_mt_sampler* pos, b200_mt_sampler* neg, int64_t nnz, int64_t n_items,
+                                 const int32_t* coo_row, const int32_t* social_indptr, int64_t n_samples,
+                                 int64_t* i_index_out, int32_t* j_id_out, int64_t* k_index_out);
+
+/* ------------------------------------------------------------------------------------
  * MF.  Replaces one epoch of backend_cpu.fit_sgd (mf/backend_cpu.pyx:58-83).
  *   rid, cid device int64[n] (the reference's INT64_t layout) or int32[n] when ids_are_i32
  *   val device f32[n]; U f32[n_users,k]; V f32[n_items,k]; Bu f32[n_users], Bi f32[n_items]

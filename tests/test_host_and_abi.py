@@ -6,7 +6,7 @@ import re
 import numpy as np
 import pytest
 
-from conftest import ROOT
+from conftest import ROOT, golden
 from oracle import oracle as O
 
 
@@ -156,3 +156,37 @@ def test_cache_blocked_sample_order_keeps_the_per_epoch_law():
     b = engine.bpr_draw_host(5, 2, 5000, nnz, n_neg, sample_base=123, plan=(1, 1))
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
     assert engine.bpr_block_plan(1000, 2000, 64) == (1, 1) and engine.bpr_block_plan(10_000_000, 1_000_000, 128) == (123, 13)
+
+
+def test_host_samplers_reproduce_the_oracle_streams():
+    """b200_vebpr_draw_host / b200_sbpr_draw_host == the streams the oracle traces (RNG order of the reference)."""
+    from cornac_b200 import _lib, engine
+    from oracle import oracle as O
+    L = _lib.load()
+    g = golden("vebpr_mid_k16")
+    r = O.vebpr_fit(g["indptr"], g["indices"], g["view_indptr"], g["view_indices"], int(g["num_items"]), int(g["total_users"]),
+                    int(g["total_items"]), int(g["k"]), 2, float(g["lr"]), float(g["reg"]), float(g["alpha"]), int(g["seed"]), trace=True)
+    rng, _, _, _ = O.bpr_init(int(g["seed"]), int(g["total_users"]), int(g["total_items"]), int(g["k"]))
+    gens = [engine.MTSampler(O.rngvector_seed(rng.randint(2 ** 31))) for _ in range(3)]
+    nnz = len(g["indices"])
+    coo = O.coo_rows(g["indptr"])
+    vp, vi = np.ascontiguousarray(g["view_indptr"]), np.ascontiguousarray(g["view_indices"])
+    for e in range(2):
+        oi, ov, oj = np.empty(nnz, np.int64), np.empty(nnz, np.int32), np.empty(nnz, np.int32)
+        assert L.b200_vebpr_draw_host(gens[0]._h, gens[1]._h, gens[2]._h, nnz, int(g["num_items"]), coo.ctypes.data, vp.ctypes.data,
+                                      vi.ctypes.data, nnz, oi.ctypes.data, ov.ctypes.data, oj.ctypes.data) == 0
+        assert np.array_equal(oi, r["i_index"][e]) and np.array_equal(ov, r["v_id"][e]) and np.array_equal(oj, r["j_id"][e])
+    g = golden("sbpr_mid_k16")
+    r = O.sbpr_fit(g["indptr"], g["indices"], g["social_item_ids"], g["social_item_counts"], g["social_indptr"], int(g["num_items"]),
+                   int(g["total_users"]), int(g["total_items"]), int(g["k"]), 2, float(g["lr"]), float(g["lbd_u"]), float(g["lbd_v"]),
+                   float(g["lbd_b"]), True, int(g["seed"]), trace=True)
+    rng, _, _, _ = O.bpr_init(int(g["seed"]), int(g["total_users"]), int(g["total_items"]), int(g["k"]))
+    gens = [engine.MTSampler(O.rngvector_seed(rng.randint(2 ** 31))) for _ in range(2)]
+    nnz = len(g["indices"])
+    coo = O.coo_rows(g["indptr"])
+    sp_ = np.ascontiguousarray(g["social_indptr"])
+    for e in range(2):
+        oi, oj, ok = np.empty(nnz, np.int64), np.empty(nnz, np.int32), np.empty(nnz, np.int64)
+        assert L.b200_sbpr_draw_host(gens[0]._h, gens[1]._h, nnz, int(g["num_items"]), coo.ctypes.data, sp_.ctypes.data, nnz,
+                                     oi.ctypes.data, oj.ctypes.data, ok.ctypes.data) == 0
+        assert np.array_equal(oi, r["i_index"][e]) and np.array_equal(oj, r["j_id"][e]) and np.array_equal(ok, r["k_index"][e])
