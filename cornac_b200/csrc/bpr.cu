@@ -1133,7 +1133,11 @@ extern "C" int b200_bpr_prepare(const int32_t* indptr, const int32_t* indices, i
 extern "C" int b200_bpr_block_plan(int64_t n_users, int64_t n_neg, int k, uint32_t* n_windows, uint32_t* n_blocks)
 {
     B200_REQUIRE(n_users >= 1 && n_neg >= 1 && k >= 1 && n_windows && n_blocks, "b200_bpr_block_plan: bad argument");
-    const double part = 40.0 * 1024 * 1024;
+    double part = 40.0 * 1024 * 1024;
+    if (const char* e = getenv("B200_BPR_PART_MB")) {          // dev knob: bytes of rows per window / item block
+        const double mb = atof(e);
+        if (mb >= 1.0 && mb <= 4096.0) part = mb * 1024 * 1024;
+    }
     const double ub = (double)n_users * k * 4, vb = (double)n_neg * k * 4;
     uint32_t wn = 1, bn = 1;
     if (ub + vb > 2 * part) {

@@ -23,7 +23,8 @@ constexpr int SC_Q = 8;           // queries per block pass
 __global__ void __launch_bounds__(SC_THREADS) score_batch_kernel(
     const float* __restrict__ U, const int64_t* __restrict__ user_idx, int64_t n_q,
     const float* __restrict__ V, int64_t n_items, int k,
-    const float* __restrict__ item_base, const float* __restrict__ user_off, float* __restrict__ out)
+    const float* __restrict__ item_base, const float* __restrict__ user_off, float* __restrict__ out,
+    float user_off_all = 0.f)
 {
     __shared__ float Vs[SC_ITEMS][SC_KC + 1];
     __shared__ double Us[SC_Q][SC_KC];
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(SC_THREADS) score_batch_kernel(
                 for (int q = 0; q < SC_Q; ++q) {
                     const int64_t gq = q0 + q;
                     if (gq < n_q) {
-                        const float uo = user_off ? __ldg(user_off + gq) : 0.f;
+                        const float uo = user_off ? __ldg(user_off + gq) : user_off_all;
                         const double a = h ? acc1[q] : acc0[q];
                         out[(size_t)gq * n_items + gi] = __fadd_rn(__fadd_rn(base, uo), __double2float_rn(a));
                     }
@@ -281,6 +282,23 @@ extern "C" int b200_score_batch(const float* U, const int64_t* user_idx, int64_t
     const int64_t n_qt = (n_q + SC_Q - 1) / SC_Q;
     dim3 grid((unsigned)n_it, (unsigned)(n_qt < 65535 ? n_qt : 65535));
     score_batch_kernel<<<grid, SC_THREADS, 0, (cudaStream_t)stream>>>(U, user_idx, n_q, V, n_items, k, item_base, user_off, out); ::b200::count_launch();
+    B200_CUDA(cudaGetLastError());
+    return B200_OK;
+}
+
+// The single-user form of SURVEY 8(b): out = (item_base + user_off) + fast_dot(U[user_idx], V)  -- what one call of
+// BPR.score / MF.score computes (recom_bpr.pyx:290-293, mf/recom_mf.py:272-278: user_off = mu + Bu[u]).
+extern "C" int b200_score(const float* U, int64_t user_idx, const float* V, int64_t n_items, int k,
+                          const float* item_base, float user_off, float* out, void* stream)
+{
+    B200_REQUIRE(U && V && out, "b200_score: null pointer argument");
+    B200_REQUIRE(user_idx >= 0 && n_items >= 0 && k >= 1, "b200_score: bad arguments user_idx=%lld n_items=%lld k=%d",
+                 (long long)user_idx, (long long)n_items, k);
+    if (n_items == 0) return B200_OK;
+    const int64_t n_it = (n_items + SC_ITEMS - 1) / SC_ITEMS;
+    dim3 grid((unsigned)n_it, 1u);
+    score_batch_kernel<<<grid, SC_THREADS, 0, (cudaStream_t)stream>>>(U + (size_t)user_idx * k, nullptr, 1, V, n_items, k, item_base, nullptr,
+                                                                     out, user_off); ::b200::count_launch();
     B200_CUDA(cudaGetLastError());
     return B200_OK;
 }

@@ -234,6 +234,11 @@ B200_API int b200_score_batch(const float* U, const int64_t* user_idx, int64_t n
                               const float* item_base, const float* user_off,
                               float* out, void* stream);
 
+/* One user: out[i] = (item_base[i] + user_off) + dot(U[user_idx], V[i]) -- one call of fast_dot as BPR.score / MF.score
+ * make it (fast_dot.pyx:25-43; user_off = mu + Bu[u] for MF, 0 for BPR).  Same arithmetic as b200_score_batch.          */
+B200_API int b200_score(const float* U, int64_t user_idx, const float* V, int64_t n_items, int k,
+                        const float* item_base, float user_off, float* out, void* stream);
+
 /* Top-k of precomputed score rows.  Replaces the argpartition/argsort of
  * Recommender.rank (recommender.py:521-528) with a TOTAL order (score desc, id asc).
  *   scores device f32[n_q, n_items]; excl_indptr device int64[n_q+1] / excl_indices device

@@ -32,6 +32,27 @@ def test_score_batch_bit_exact(k, n_items, n_q):
     assert np.array_equal(got.cpu().numpy(), want)
 
 
+def test_single_user_score_entry_equals_the_batched_one():
+    """b200_score (one user, scalar offset: the fast_dot call of BPR.score / MF.score) == row of b200_score_batch, bit for bit."""
+    import torch
+    from cornac_b200 import _lib, engine
+    from cornac_b200._lib import check, current_stream, ptr
+    L = _lib.load()
+    rng = np.random.RandomState(3)
+    k, n_items = 48, 3001
+    U = rng.normal(0, 0.3, (20, k)).astype(np.float32)
+    V = rng.normal(0, 0.3, (n_items, k)).astype(np.float32)
+    base = rng.normal(0, 0.3, n_items).astype(np.float32)
+    dU, dV, dB = _dev(U), _dev(V), _dev(base)
+    out = torch.empty(n_items, dtype=torch.float32, device="cuda")
+    for u, off in ((0, 0.0), (7, 0.25), (19, -1.5)):
+        check(L.b200_score(ptr(dU), u, ptr(dV), n_items, k, ptr(dB), off, ptr(out), current_stream()), "b200_score")
+        want = O.score_batch(U[u:u + 1], V, base, np.array([off], np.float32))[0]
+        assert np.array_equal(out.cpu().numpy(), want)
+    check(L.b200_score(ptr(dU), 3, ptr(dV), n_items, k, None, 0.0, ptr(out), current_stream()), "b200_score")
+    assert np.array_equal(out.cpu().numpy(), O.score_batch(U[3:4], V)[0])
+
+
 def test_fast_dot_known_answers_on_device():
     # reference: tests/cornac/utils/test_fastdot.py:26-37
     from cornac_b200 import engine
