@@ -748,9 +748,12 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t (&r)[32], RowState& st, 
 //   pair_full[s], pair_u leader's, 2 arrivals: each CTA's relay thread (warp 3) forwards "my half / my U tile landed"
 //   empty[s], u_empty, acc_full[a]   local in BOTH CTAs, signalled by the leader's tcgen05.commit (multicast)
 //   acc_empty[a]         leader's, 2 x EPI_WARPS arrivals: the follower's epilogue warps arrive remotely
-template <bool DUMP, int ST, int CG>
+// DBG: the timing-experiment switches (B200_RANK_DEBUG) are compiled into a separate instantiation; the production kernel
+// carries none of their branches (the stage loop is sensitive to every instruction and register, profiles/r02_rank_tc.md).
+template <bool DUMP, int ST, int CG, bool DBG = false>
 __global__ void __launch_bounds__(threads_for(ST), 1) rank_tc_kernel(const RankTcParams p)
 {
+    const int dbg = DBG ? p.debug : 0;
     constexpr int EPI_WARPS = 4 * ST;
     constexpr int STRIP_N = TN / ST;
     constexpr int CAP_T = cap_for(ST);
@@ -908,8 +911,8 @@ __global__ void __launch_bounds__(threads_for(ST), 1) rank_tc_kernel(const RankT
             st.tau = -INFINITY; st.hi = -INFINITY;
             tau_share[half * TM + q * 32 + lane] = ((unsigned long long)(uint32_t)ut << 32) | 0xff800000u;   // -inf
             st.tau_f = valid ? -1.0e38f : INFINITY;       // padding items score -inf: never above the filter
-            if (p.debug & 8) st.tau_f = INFINITY;         // timing experiment: screening only (nothing is ever listed)
-            if ((p.debug & 32) && valid) {                // timing experiment: start from the PREVIOUS call's final filters (perfect thresholds)
+            if (dbg & 8) st.tau_f = INFINITY;         // timing experiment: screening only (nothing is ever listed)
+            if ((dbg & 32) && valid) {                // timing experiment: start from the PREVIOUS call's final filters (perfect thresholds)
                 float t = -INFINITY;
 #pragma unroll
                 for (int x = 0; x < ST; ++x) t = fmaxf(t, p.row_tau[row * MAX_ST + x]);
@@ -925,13 +928,13 @@ __global__ void __launch_bounds__(threads_for(ST), 1) rank_tc_kernel(const RankT
                 const int32_t item0 = it * TN + half * STRIP_N;
                 const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN + half * STRIP_N);
                 uint32_t r0[32], r1[32];
-                if (p.debug & 1) {                 // timing experiment: MMA / TMA feed rate without the screening
+                if (dbg & 1) {                 // timing experiment: MMA / TMA feed rate without the screening
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) { if (CG == 2) mbar_arrive_remote_relaxed(r_acc_empty + 8 * acc); else mbar_arrive(acc_empty + acc); }
                     continue;
                 }
-                if (p.debug & 2) {                 // timing experiment: TMEM drain rate (tcgen05.ld only, no screening)
+                if (dbg & 2) {                 // timing experiment: TMEM drain rate (tcgen05.ld only, no screening)
                     uint32_t acc_or = 0;
 #pragma unroll
                     for (int c0 = 0; c0 < STRIP_N; c0 += 32) {
@@ -986,16 +989,16 @@ __global__ void __launch_bounds__(threads_for(ST), 1) rank_tc_kernel(const RankT
                     // ... and once more after the LAST stage: the lists then hold ~K ln(n_it / last raise) entries above a
                     // stale threshold, every one of which the finish kernel would re-score exactly (a 512-byte gather from V
                     // per candidate: the finish is HBM-bound on those gathers)
-                    const bool scheduled = (done == next_sched && !(p.debug & 64)) || done == p.n_it;      // bit 64: timing experiment, final raise only
+                    const bool scheduled = (done == next_sched && !(dbg & 64)) || done == p.n_it;      // bit 64: timing experiment, final raise only
                     if (scheduled) {               // geometric schedule, ratio 2 (or ~1.41 with debug bit 4)
-                        const int grown = (p.debug & 4) ? (done * 181) >> 7 : done * 2;
+                        const int grown = (dbg & 4) ? (done * 181) >> 7 : done * 2;
                         next_sched = grown > done ? grown : done + 1;
                     }
                     int* share = pair_share + ((q * 32 + lane) << 2);
                     unsigned short* hist = hist_share + q * 32 + lane;
                     unsigned long long* tau_row = tau_share + q * 32 + lane;
                     if (scheduled)
-                        raise_threshold<true, ST>(st, p.topk, eps2, (uint32_t)ut, half, CAP_T, tau_row, share, hist, 1 + q, (p.debug & 16) != 0);
+                        raise_threshold<true, ST>(st, p.topk, eps2, (uint32_t)ut, half, CAP_T, tau_row, share, hist, 1 + q, (dbg & 16) != 0);
                     else if (__any_sync(0xffffffffu, st.cnt >= TRIGGER))
                         raise_threshold<false, ST>(st, p.topk, eps2, (uint32_t)ut, half, CAP_T, tau_row, share, hist, 1 + q);
                     if (st.cnt > CAP_T - STRIP_N) { flag = 1; st.cnt = 0; st.checked = 0; st.tau_f = INFINITY; }
@@ -1434,10 +1437,10 @@ static int rank_cta_group()
     return 2;
 }
 
-template <bool DUMP, int ST, int CG>
+template <bool DUMP, int ST, int CG, bool DBG = false>
 static int launch_rank_tc_t(const RankTcParams& p, cudaStream_t st)
 {
-    auto kern = rank_tc_kernel<DUMP, ST, CG>;
+    auto kern = rank_tc_kernel<DUMP, ST, CG, DBG>;
     const size_t smem = smem_bytes_for(p.kp, ST, CG);
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
@@ -1470,6 +1473,10 @@ static int launch_rank_tc(const RankTcParams& p, int strips, cudaStream_t st)
 {
     const int cg = rank_cta_group();
     if (DUMP) return cg == 2 ? launch_rank_tc_t<DUMP, 2, 2>(p, st) : launch_rank_tc_t<DUMP, 2, 1>(p, st);
+    if (!DUMP && p.debug != 0) {             // timing experiments: the instantiation that carries the switches
+        if (strips == 4) return cg == 2 ? launch_rank_tc_t<false, 4, 2, true>(p, st) : launch_rank_tc_t<false, 4, 1, true>(p, st);
+        return cg == 2 ? launch_rank_tc_t<false, 2, 2, true>(p, st) : launch_rank_tc_t<false, 2, 1, true>(p, st);
+    }
     if (strips == 4) return cg == 2 ? launch_rank_tc_t<DUMP, 4, 2>(p, st) : launch_rank_tc_t<DUMP, 4, 1>(p, st);
     return cg == 2 ? launch_rank_tc_t<DUMP, 2, 2>(p, st) : launch_rank_tc_t<DUMP, 2, 1>(p, st);
 }
@@ -1482,11 +1489,11 @@ static int rank_strips(int k, int topk)
         if (e[0] == '4') return 4;
         if (e[0] == '2') return 2;
     }
-    // 64-column strips: a warp holds its whole strip in registers, so the accumulator is handed back before any
-    // screening (the data-dependent appends leave the MMA's critical path), and four warps per scheduler hide the
-    // latency of the append path (measured: profiles/r02_rank_tc.md)
-    (void)k;
-    return 4;
+    // 64-column strips (16 epilogue warps): a warp holds its whole strip in registers, so the accumulator is handed back before
+    // any screening; best where a stage is short (k <= 64: 17.0 vs M users/s at 100 K items).  128-column strips (8 warps,
+    // 168 registers, no spills, fewer instructions per score) win once the MMA of a stage takes longer: k = 128 at 1 M items
+    // 5.63 vs 5.82 ms per 18 944 users (profiles/r02_rank_tc.md, trip X)
+    return k > 64 ? 2 : 4;
 }
 
 }  // namespace tc
