@@ -72,7 +72,7 @@ SIGNATURES = {
     "b200_ipc_open": (_int, [_vp, _i64, _vp]),
     "b200_ipc_close": (_int, [_vp, _i64]),
     "b200_item_exchange_slice": (_int, [_int, _int, _i64, _vp, _vp]),
-    "b200_item_exchange": (_int, [_int, _int, _vp, _vp, _vp, _i64, _u32, _vp]),
+    "b200_item_exchange": (_int, [_int, _int, _vp, _vp, _vp, _i64, _u32, _int, _vp]),
 }
 
 SGD_ATOMIC = 1

@@ -63,8 +63,13 @@ __device__ bool wait_all(const unsigned int* my_flags, int phase, int world, uns
     return true;
 }
 
+// mean_touched: new = snap + (sum_r d_r) / #{r : d_r != 0}  (d_r = x_r - snap) instead of snap + sum_r d_r.  The plain sum is the
+// single-process step count only while the ranks change DIFFERENT rows; a row every rank trains (a popular item) is moved
+// `world` times too far and the epochs oscillate with growing amplitude from 4 ranks on (tools/sim_localsgd.py).  The mean over
+// the ranks that changed an element is a convex combination of their local results: stable at any world size, and equal to the
+// sum wherever one rank alone touched the element.
 __global__ void __launch_bounds__(THREADS) item_exchange_kernel(const Peers P, int rank, int world, float* __restrict__ snap,
-                                                                int64_t n, int64_t lo, int64_t hi, unsigned int seq)
+                                                                int64_t n, int64_t lo, int64_t hi, unsigned int seq, int mean_touched)
 {
     unsigned int* my_flags = P.flags[rank];
     __shared__ int ok_s;
@@ -91,12 +96,22 @@ __global__ void __launch_bounds__(THREADS) item_exchange_kernel(const Peers P, i
 #pragma unroll
             for (int r = 0; r < MAX_WORLD; ++r)
                 if (r < world) v[r] = ld_volatile_f4(P.x[r] + lo + 4 * i);       // all peers' loads in flight together
+            float4 d = make_float4(0.f, 0.f, 0.f, 0.f), c = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int r = 0; r < MAX_WORLD; ++r) {
                 if (r < world) {
-                    acc.x += v[r].x - s.x; acc.y += v[r].y - s.y; acc.z += v[r].z - s.z; acc.w += v[r].w - s.w;
+                    const float dx = v[r].x - s.x, dy = v[r].y - s.y, dz = v[r].z - s.z, dw = v[r].w - s.w;
+                    d.x += dx; d.y += dy; d.z += dz; d.w += dw;
+                    c.x += dx != 0.f ? 1.f : 0.f; c.y += dy != 0.f ? 1.f : 0.f; c.z += dz != 0.f ? 1.f : 0.f; c.w += dw != 0.f ? 1.f : 0.f;
                 }
             }
+            if (mean_touched) {
+                if (c.x > 1.f) d.x /= c.x;
+                if (c.y > 1.f) d.y /= c.y;
+                if (c.z > 1.f) d.z /= c.z;
+                if (c.w > 1.f) d.w /= c.w;
+            }
+            acc.x += d.x; acc.y += d.y; acc.z += d.z; acc.w += d.w;
 #pragma unroll
             for (int r = 0; r < MAX_WORLD; ++r)
                 if (r < world) *reinterpret_cast<float4*>(P.x[r] + lo + 4 * i) = acc;
@@ -104,8 +119,14 @@ __global__ void __launch_bounds__(THREADS) item_exchange_kernel(const Peers P, i
         }
         for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * THREADS + threadIdx.x; i < len; i += stride) {
             const float s = snap[i];
-            float acc = s;
-            for (int r = 0; r < world; ++r) acc += ld_volatile_f(P.x[r] + lo + i) - s;
+            float d = 0.f, c = 0.f;
+            for (int r = 0; r < world; ++r) {
+                const float dx = ld_volatile_f(P.x[r] + lo + i) - s;
+                d += dx;
+                c += dx != 0.f ? 1.f : 0.f;
+            }
+            if (mean_touched && c > 1.f) d /= c;
+            const float acc = s + d;
             for (int r = 0; r < world; ++r) P.x[r][lo + i] = acc;
             snap[i] = acc;
         }
@@ -175,7 +196,7 @@ extern "C" int b200_ipc_close(void* mapped, int64_t offset)
 }
 
 extern "C" int b200_item_exchange(int rank, int world, void* const* x_peers, void* const* flag_peers, float* snapshot_slice,
-                                  int64_t n, uint32_t seq, void* stream)
+                                  int64_t n, uint32_t seq, int mean_touched, void* stream)
 {
     B200_REQUIRE(world >= 1 && world <= p2p::MAX_WORLD && rank >= 0 && rank < world, "b200_item_exchange: rank %d / world %d", rank, world);
     B200_REQUIRE(x_peers && flag_peers && snapshot_slice && n >= 0 && seq != 0, "b200_item_exchange: bad argument");
@@ -194,7 +215,7 @@ extern "C" int b200_item_exchange(int rank, int world, void* const* x_peers, voi
     const int64_t cap = (int64_t)sm_count() * 4;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    p2p::item_exchange_kernel<<<(unsigned)blocks, p2p::THREADS, 0, (cudaStream_t)stream>>>(P, rank, world, snapshot_slice, n, lo, hi, seq);
+    p2p::item_exchange_kernel<<<(unsigned)blocks, p2p::THREADS, 0, (cudaStream_t)stream>>>(P, rank, world, snapshot_slice, n, lo, hi, seq, mean_touched);
     ::b200::count_launch();
     B200_CUDA(cudaGetLastError());
     return B200_OK;

@@ -3,9 +3,19 @@
 The reference is a single process: nothing here has a reference
 counterpart.  Users are cut into contiguous ranges balanced by interaction count; every
 rank trains its range against a full replica of V / B; at the epoch boundary the ranks
-exchange what they changed:   V <- V_start + sum_r (V_r - V_start)   (one NCCL all-reduce
-of the deltas over NVLink; U is never communicated).  One process per GPU, torch.distributed
-for the collective, our own kernels (b200_delta_make / b200_delta_apply) around it.
+exchange what they changed:   V <- V_start + mean over the ranks that changed the row of
+(V_r - V_start)   (U is never communicated).  One process per GPU; the exchange is one fused
+kernel over NVLink peer memory (PeerItemExchange, csrc/p2p.cu) or our delta kernels around a
+torch.distributed all-reduce (ItemReplicaSync).
+
+Why a mean and not the sum (SURVEY 8(e) proposed the sum "to match the single-GPU step count"): the sum is right
+only while the ranks change DIFFERENT rows.  A popular item is trained by every rank; each rank alone moves it
+most of the way to its local optimum within the epoch, so the sum overshoots `world`-fold and the epochs oscillate
+with growing amplitude from 4 ranks on -- tools/sim_localsgd.py reproduces it on the CPU with the reference loop
+(pairwise accuracy 0.81 -> 0.30 at 4 ranks, |B| 3 -> 1e5 at 8), and on the GPU box the 8-rank MF check went to NaN
+and the 8-rank bench model broke the rank leg.  The mean over the ranks that changed an element is a convex
+combination of their results: stable at any world size, identical to the sum where one rank alone touched the
+row (reduce="sum" keeps the old rule for A/B runs).
 """
 import numpy as np
 
@@ -50,16 +60,19 @@ class ItemReplicaSync:
         sync = ItemReplicaSync([V, B])          # after the replicas were initialised identically
         for epoch ...:
             run_local_epoch()
-            sync.exchange()                      # V, B now hold start + sum of all ranks' changes
+            sync.exchange()                      # V, B now hold start + the ranks' changes (mean over the ranks that changed a row)
 
     `ops` is the pair of element-wise kernels (defaults to the CUDA ones); tests inject a
     torch-CPU stand-in to exercise the collective logic over gloo."""
 
-    def __init__(self, tensors, group=None, ops=None):
+    def __init__(self, tensors, group=None, ops=None, reduce="mean_touched"):
         import torch
+        if reduce not in ("mean_touched", "sum"):
+            raise ValueError("reduce must be 'mean_touched' or 'sum'")
         self.tensors = list(tensors)
         self.group = group
         self.ops = ops or _CudaDeltaOps
+        self.reduce = reduce
         self.snapshots = [t.clone() for t in self.tensors]
         self.deltas = [torch.empty_like(t) for t in self.tensors]
 
@@ -70,7 +83,12 @@ class ItemReplicaSync:
             self.ops.make(t, s, d)
         if not single:
             for d in self.deltas:
+                if self.reduce == "mean_touched":
+                    touched = (d != 0).to(d.dtype)              # which elements this rank changed
+                    dist.all_reduce(touched, op=dist.ReduceOp.SUM, group=self.group)
                 dist.all_reduce(d, op=dist.ReduceOp.SUM, group=self.group)
+                if self.reduce == "mean_touched":
+                    d.div_(touched.clamp_(min=1))
         for t, s, d in zip(self.tensors, self.snapshots, self.deltas):
             self.ops.apply(t, s, d)
 
@@ -79,14 +97,17 @@ class PeerItemExchange:
     """ItemReplicaSync's exchange as ONE kernel per tensor over NVLink peer memory (b200_item_exchange, csrc/p2p.cu):
     the ranks map each other's replicas with CUDA IPC at construction (handles travel through torch.distributed); every
     exchange() then launches, per tensor, a kernel in which this rank reduces and rewrites its slice of every replica.
-    No NCCL collective and no delta buffers on the data path; the result is V <- V_start + sum_r (V_r - V_start), summed in
-    rank order, bit-equal on all ranks.  One process per GPU, all GPUs of one NVLink domain."""
+    No NCCL collective and no delta buffers on the data path; the result is V <- V_start + mean over the ranks that changed the
+    element of (V_r - V_start) (reduce="sum": the plain sum), formed in rank order, bit-equal on all ranks.  One process per GPU, all GPUs of one NVLink domain."""
 
-    def __init__(self, tensors, group=None):
+    def __init__(self, tensors, group=None, reduce="mean_touched"):
         import ctypes
         import torch
         import torch.distributed as dist
         from . import _lib
+        if reduce not in ("mean_touched", "sum"):
+            raise ValueError("reduce must be 'mean_touched' or 'sum'")
+        self.reduce = reduce
         self._L = _lib.load()
         self._check = _lib.check
         self.group = group
@@ -134,7 +155,8 @@ class PeerItemExchange:
         self.seq += 1
         for st in self._state:
             self._check(self._L.b200_item_exchange(self.rank, self.world, st["x_ptrs"], st["f_ptrs"], st["snap"].data_ptr(),
-                                                   st["t"].numel(), self.seq, current_stream()), "b200_item_exchange")
+                                                   st["t"].numel(), self.seq, int(self.reduce == "mean_touched"), current_stream()),
+                        "b200_item_exchange")
 
     def failed(self):
         """True when a peer did not show up in some exchange (bounded wait expired); synchronises."""
@@ -150,7 +172,7 @@ class PeerItemExchange:
             self._opened = {}
 
 
-def make_item_sync(tensors, group=None, kind="auto"):
+def make_item_sync(tensors, group=None, kind="auto", reduce="mean_touched"):
     """The per-epoch item exchange for `tensors` ([V, B]): 'p2p' = PeerItemExchange (one fused NVLink kernel per tensor),
     'nccl' = ItemReplicaSync (delta kernels around a torch.distributed all-reduce; also the gloo / CPU test seam),
     'auto' = p2p on CUDA tensors with the NCCL backend, else nccl."""
@@ -159,8 +181,8 @@ def make_item_sync(tensors, group=None, kind="auto"):
         on_gpu = all(getattr(t, "is_cuda", False) for t in tensors)
         kind = "p2p" if (on_gpu and dist.is_initialized() and dist.get_backend(group) == "nccl") else "nccl"
     if kind == "p2p":
-        return PeerItemExchange(tensors, group=group)
-    return ItemReplicaSync(tensors, group=group)
+        return PeerItemExchange(tensors, group=group, reduce=reduce)
+    return ItemReplicaSync(tensors, group=group, reduce=reduce)
 
 
 def bpr_fit_sharded(indptr, indices, n_items, U, V, B, lr, reg, use_bias, max_iter, key=0, atomic=True):
@@ -168,7 +190,7 @@ def bpr_fit_sharded(indptr, indices, n_items, U, V, B, lr, reg, use_bias, max_it
     group initialised, torch.cuda.set_device done) with the FULL host CSR matrix and factor arrays.
 
     Rank r trains users [bounds[r], bounds[r+1]) (equal interaction counts) against its replica of
-    V / B; item-side changes are all-reduced once per epoch.  On return every rank's V and B hold
+    V / B; item-side changes are exchanged once per epoch (make_item_sync: mean over the ranks that changed a row).  On return every rank's V and B hold
     the shared result and U[bounds[r]:bounds[r+1]] holds this rank's trained rows (other rows of U
     are untouched on this rank; gather them with torch.distributed if one process needs all)."""
     import torch.distributed as dist
@@ -236,7 +258,7 @@ def mf_fit_sharded(rid, cid, val, U, V, Bu, Bi, lr, reg, mu, use_bias, max_iter,
 
     Rank r owns the users [bounds[r], bounds[r+1]) -- equal rating counts -- and all their ratings: U and Bu rows of
     those users are trained locally and never communicated; V and Bi are replicated and, once per epoch, every
-    replica becomes  start + sum over ranks of the local changes  (one all-reduce of the deltas).  The epoch loss
+    replica becomes  start + the ranks' local changes averaged over the ranks that changed the element  (make_item_sync).  The epoch loss
     is all-reduced too, so `early_stop` takes the same decision on every rank (backend_cpu.pyx:85-93).
     On return V, Bi hold the shared result on every rank; U[lo:hi], Bu[lo:hi] hold this rank's rows.
     Returns (bounds, losses)."""

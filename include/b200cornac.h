@@ -331,7 +331,12 @@ B200_API int b200_rank_counts(float* scores, int64_t n_q, int64_t n_items,
  * boundary   b200_delta_make:  delta[i] = x[i] - snapshot[i]
  * the caller all-reduces (sum) `delta` over NCCL, then
  *            b200_delta_apply: x[i] = snapshot[i] + delta[i];  snapshot[i] = x[i]
- * so every replica ends the epoch with x_start + sum over ranks of the local changes.     */
+ * so every replica ends the epoch with x_start + sum over ranks of the local changes -- or, the default of the Python layer,
+ * x_start + (sum of the changes) / (number of ranks that changed the element): the caller also all-reduces the indicator
+ * (delta != 0) and divides.  The plain sum is the single-process step count only while the ranks change different rows; a row
+ * every rank trains (a popular item) moves `world` times too far and the epochs oscillate with growing amplitude from 4 ranks
+ * on (tools/sim_localsgd.py: pairwise accuracy 0.81 -> 0.30 at 4 ranks); the mean over the ranks that changed an element is a
+ * convex combination of their local results: stable at any world size, equal to the sum where one rank alone touched it.   */
 B200_API int b200_delta_make(const float* x, const float* snapshot, float* delta, int64_t n, void* stream);
 B200_API int b200_delta_apply(float* x, float* snapshot, const float* delta, int64_t n, void* stream);
 
@@ -346,6 +351,7 @@ B200_API int b200_delta_apply(float* x, float* snapshot, const float* delta, int
  *                     (u32[32], zeroed once by its owner before the first exchange), own pointers at [rank]
  *   snapshot_slice    device f32[hi - lo]: the epoch-start values of the owned slice (= the replica's after each exchange)
  *   seq               1, 2, 3, ... : the same value on every rank for the same exchange
+ *   mean_touched      1: snapshot + (sum_r d_r) / #{r : d_r != 0} per element (see above; the default of the Python layer); 0: the sum
  * Every rank must call it once per exchange; the kernel returns when all peers have finished writing this rank's
  * replica.  A peer that never arrives sets flag word [17] after ~4 s instead of hanging the GPU. */
 B200_API int b200_ipc_export(const void* dev_ptr, void* handle64_out, int64_t* offset_out);
@@ -353,7 +359,7 @@ B200_API int b200_ipc_open(const void* handle64, int64_t offset, void** mapped_o
 B200_API int b200_ipc_close(void* mapped, int64_t offset);
 B200_API int b200_item_exchange_slice(int rank, int world, int64_t n, int64_t* lo_out, int64_t* hi_out);
 B200_API int b200_item_exchange(int rank, int world, void* const* x_peers, void* const* flag_peers, float* snapshot_slice,
-                                int64_t n, uint32_t seq, void* stream);
+                                int64_t n, uint32_t seq, int mean_touched, void* stream);
 
 #ifdef __cplusplus
 }

@@ -47,19 +47,34 @@ def _worker(rank, world, port, out):
     V = torch.randn(50, 8, generator=g)
     B = torch.randn(50, generator=g)
     V0, B0 = V.clone(), B.clone()
+    # default rule: every element moves by the MEAN of the changes of the ranks that changed it (rows r, r + 3, ... are left
+    # alone by rank r here, so the count differs from row to row); reduce="sum" is the plain sum
     sync = ItemReplicaSync([V, B], ops=_CpuOps)
-    total_dv = torch.zeros_like(V)
+    Vs = V.clone()
+    sync_sum = ItemReplicaSync([Vs], ops=_CpuOps, reduce="sum")
+    want, want_sum = V0.clone(), V0.clone()
+
+    def change(epoch, r):
+        gr = torch.Generator().manual_seed(100 * epoch + r)
+        dv, db = torch.randn(50, 8, generator=gr) * 0.01, torch.randn(50, generator=gr) * 0.01
+        dv[r::3] = 0
+        return dv, db
+
     for epoch in range(3):
-        gl = torch.Generator().manual_seed(100 * epoch + rank)
-        dv, db = torch.randn(50, 8, generator=gl) * 0.01, torch.randn(50, generator=gl) * 0.01
+        dv, db = change(epoch, rank)
         V += dv
+        Vs += dv
         B += db
         sync.exchange()
+        sync_sum.exchange()
+        tot, cnt = torch.zeros_like(V), torch.zeros_like(V)
         for r in range(world):
-            gr = torch.Generator().manual_seed(100 * epoch + r)
-            total_dv += torch.randn(50, 8, generator=gr) * 0.01
-            torch.randn(50, generator=gr)
-    ok = torch.allclose(V, V0 + total_dv, atol=1e-6)
+            d, _ = change(epoch, r)
+            tot += d
+            cnt += (d != 0).float()
+        want += tot / cnt.clamp(min=1)
+        want_sum += tot
+    ok = torch.allclose(V, want, atol=1e-6) and torch.allclose(Vs, want_sum, atol=1e-6) and not torch.allclose(want, want_sum, atol=1e-4)
     gathered = [torch.empty_like(V) for _ in range(world)]
     dist.all_gather(gathered, V)
     same = all(torch.equal(gathered[0], t) for t in gathered)
@@ -133,8 +148,10 @@ def _mf_worker(rank, world, port, out):
     U0, V0, Bu0, Bi0 = U.copy(), V.copy(), Bu.copy(), Bi.copy()
     bounds, losses = mf_fit_sharded(rid, cid, val, U, V, Bu, Bi, 0.01, 0.02, 3.0, True, max_iter=1, _device=_OracleMf())
     lo, hi = int(bounds[rank]), int(bounds[rank + 1])
-    # expectation for one epoch: every shard trained from the SAME start; V, Bi = start + sum of the shards' changes
+    # expectation for one epoch: every shard trained from the SAME start; V, Bi = start + the shards' changes averaged over the
+    # shards that changed the element (parallel.py: why not the sum)
     dV, dBi, tot = np.zeros_like(V0), np.zeros_like(Bi0), 0.0
+    cV, cBi = np.zeros_like(V0), np.zeros_like(Bi0)
     for r in range(world):
         rr, cc, vv = shard_ratings(rid, cid, val, bounds, r)
         a, b = int(bounds[r]), int(bounds[r + 1])
@@ -142,9 +159,11 @@ def _mf_worker(rank, world, port, out):
         tot += O.mf_epoch(rr, cc, vv, Ur, Vr, Bur, Bir, 0.01, 0.02, 3.0, True)
         dV += Vr - V0
         dBi += Bir - Bi0
+        cV += (Vr - V0 != 0)
+        cBi += (Bir - Bi0 != 0)
         if r == rank:
             mine = (Ur, Bur)
-    ok = (np.allclose(V, V0 + dV, atol=1e-6) and np.allclose(Bi, Bi0 + dBi, atol=1e-6)
+    ok = (np.allclose(V, V0 + dV / np.maximum(cV, 1), atol=1e-6) and np.allclose(Bi, Bi0 + dBi / np.maximum(cBi, 1), atol=1e-6)
           and np.array_equal(U[lo:hi], mine[0]) and np.array_equal(Bu[lo:hi], mine[1])
           and np.array_equal(np.delete(U, np.s_[lo:hi], axis=0), np.delete(U0, np.s_[lo:hi], axis=0))
           and abs(losses[0] - tot) <= 1e-3 * tot)
