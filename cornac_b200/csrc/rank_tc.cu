@@ -1649,7 +1649,25 @@ int rank_tc(const float* U, const int64_t* user_idx, int64_t n_q, const float* V
         int n_over = 0;
         B200_CUDA(cudaMemcpyAsync(&n_over, ws + L.off_over, 4, cudaMemcpyDeviceToHost, st));
         B200_CUDA(cudaStreamSynchronize(st));
-        if (n_over > 0) {
+        // Many overflowed rows = a degenerate score distribution (a diverged model: inf / NaN factors; thousands of exact ties):
+        // row-by-row repair would cost a host round trip per user.  Redo the whole chunk on the exact path instead, in slabs
+        // of score rows cut from the (now idle) candidate-list area -- same ids and scores, bounded time.
+        const int64_t list_bytes = (int64_t)L.chunk_ut * 8 * CAP * 32 * 8;
+        const int64_t slab_rows = list_bytes / (n_items * (int64_t)sizeof(float));
+        if (n_over > 256 && slab_rows >= 8) {
+            float* slab = reinterpret_cast<float*>(ws + L.off_lists);
+            for (int64_t r0 = 0; r0 < rows; r0 += slab_rows) {
+                const int64_t nq = rows - r0 < slab_rows ? rows - r0 : slab_rows;
+                const int64_t g0 = q0 + r0;
+                const float* Uq = user_idx ? U : U + (size_t)g0 * k;
+                rc = b200_score_batch(Uq, user_idx ? user_idx + g0 : nullptr, nq, V, n_items, k, item_base,
+                                      user_off ? user_off + g0 : nullptr, slab, st);
+                if (!rc) rc = b200_topk_rows(slab, nq, n_items, excl_indptr ? excl_indptr + g0 : nullptr, excl_indices, topk,
+                                             out_ids + (size_t)g0 * topk, out_scores + (size_t)g0 * topk, st);
+                if (rc) return rc;
+            }
+            B200_CUDA(cudaStreamSynchronize(st));
+        } else if (n_over > 0) {
             int* rows_h = new int[n_over];
             cudaError_t e = cudaMemcpy(rows_h, ws + L.off_over + 4, (size_t)n_over * 4, cudaMemcpyDeviceToHost);
             if (e != cudaSuccess) { delete[] rows_h; return cuda_fail(e, "cudaMemcpy overflow rows", __FILE__, __LINE__); }
