@@ -1490,10 +1490,12 @@ static int rank_strips(int k, int topk)
         if (e[0] == '2') return 2;
     }
     // 64-column strips (16 epilogue warps): a warp holds its whole strip in registers, so the accumulator is handed back before
-    // any screening; best where a stage is short (k <= 64: 17.0 vs M users/s at 100 K items).  128-column strips (8 warps,
-    // 168 registers, no spills, fewer instructions per score) win once the MMA of a stage takes longer: k = 128 at 1 M items
-    // 5.63 vs 5.82 ms per 18 944 users (profiles/r02_rank_tc.md, trip X)
-    return k > 64 ? 2 : 4;
+    // any screening: 17.1 vs 14.4 M users/s at 100 K items, k = 64.  At k = 128 / 1 M items 128-column strips (8 warps, 168
+    // registers, no spills) are 3 % faster (5.63 vs 5.82 ms per 18 944 users, profiles/r02_rank_tc.md), but that variant's parity
+    // tests last ran BEFORE the batched list scans and the split of the debug branches (the round's GPU budget ended), so it
+    // stays opt-in (B200_RANK_STRIPS=2) until `pytest -m gpu` has run with it.
+    (void)k;
+    return 4;
 }
 
 }  // namespace tc
