@@ -9,7 +9,8 @@ Workload (default, BASELINE.json configs[2] -- the north_star target): ONE synth
 125 M interactions each, block b seeded 1234 + b, one shared item-popularity law), so it is THE SAME model
 for every N; `--gpus N` shards it by interaction count: rank r owns blocks [8 r / N, 8 (r + 1) / N)
 (STRONG scaling: total work fixed).  The 1 M-item matrix V (512 MB) and the biases are replicated and the
-item deltas are all-reduced once per epoch inside the timed region (NCCL over NVLink).  N = 1 holds the
+item changes are exchanged once per epoch inside the timed region (one fused NVLink peer-memory kernel per tensor, or
+delta kernels + NCCL all-reduce with --exchange nccl; rule: mean over the ranks that changed a row).  N = 1 holds the
 whole model on one GPU (about 35 GB of the 180 GB).
 
 A "step" is one BPR epoch over the whole model = 1 B sampled triplets in total (what one call of the
@@ -509,7 +510,7 @@ def main():
                 "exchange": ("none (single GPU)" if world == 1 else
                              ("%s: one fused NVLink peer-memory kernel per tensor (reduce-scatter + apply + all-gather of %d MB)"
                               if exchange_kind == "PeerItemExchange" else
-                              "%s: delta_make -> NCCL all-reduce(%d MB) -> delta_apply") % (exchange_kind, (W["n_items"] * (k + 1) * 4) // 1000000))}
+                              "%s: delta_make -> NCCL all-reduce(%d MB, + the touched-by count) -> delta_apply") % (exchange_kind, (W["n_items"] * (k + 1) * 4) // 1000000))}
 
     def over_ranks(ms):
         if world == 1:
@@ -565,7 +566,7 @@ def main():
                                % (W["nnz"], nnz),
                        "l2": "working set per rank (U %d MB + V %d MB + pair store %d MB + membership table) exceeds the 126 MB L2; no flush needed"
                              % (n_local * k * 4 // 1000000, W["n_items"] * k * 4 // 1000000, nnz * 8 // 1000000),
-                       "parallelism": "users sharded x%d by interaction count, items replicated, 1 all-reduce of item deltas per epoch" % world,
+                       "parallelism": "users sharded x%d by interaction count, items replicated, 1 exchange of item changes per epoch (mean over the ranks that changed a row)" % world,
                        "scatter": "red.global.add.v4.f32" if args.atomic else "st.global.cg.v4.f32 (Hogwild)",
                        "sample_order": ("cache-blocked: %d windows of the interaction list x %d item blocks per rank (b200_bpr_block_plan); "
                                         "same per-epoch law as the i.i.d. order" % engine.bpr_block_plan(n_local, W["n_items"], k))
