@@ -190,3 +190,32 @@ def test_host_samplers_reproduce_the_oracle_streams():
         assert L.b200_sbpr_draw_host(gens[0]._h, gens[1]._h, nnz, int(g["num_items"]), coo.ctypes.data, sp_.ctypes.data, nnz,
                                      oi.ctypes.data, oj.ctypes.data, ok.ctypes.data) == 0
         assert np.array_equal(oi, r["i_index"][e]) and np.array_equal(oj, r["j_id"][e]) and np.array_equal(ok, r["k_index"][e])
+
+
+def test_sbpr_social_item_lists_match_the_reference_fixture():
+    """cornac_b200.recom_bprx.prepare_social_data (vectorised) == SBPR._prepare_social_data of the compiled reference
+    (recom_sbpr.pyx:119-145; arrays stored in the fixture) == the oracle's per-user restatement.  Host code only."""
+    pytest.importorskip("cornac")
+    import scipy.sparse as sp
+    from cornac_b200.recom_bprx import check_tri_factor_width, prepare_social_data
+    g = golden("sbpr_mid_k16")
+    n_users, n_items = int(g["num_users"]), int(g["num_items"])
+    X = sp.csr_matrix((g["data"], g["indices"], g["indptr"]), shape=(n_users, n_items))
+    Y = sp.csr_matrix((np.ones(len(g["graph_indices"])), g["graph_indices"], g["graph_indptr"]), shape=(n_users, n_users))
+    ids, cnts, ptr_ = prepare_social_data(X, Y)
+    assert ids.dtype == X.indices.dtype
+    assert np.array_equal(ids, g["social_item_ids"]) and np.array_equal(cnts, g["social_item_counts"])
+    assert np.array_equal(ptr_, g["social_indptr"])
+    o_ids, o_cnts, o_ptr = O.sbpr_social_items(g["indptr"], g["indices"], g["graph_indptr"], g["graph_indices"])
+    assert np.array_equal(ids, o_ids) and np.array_equal(cnts, o_cnts) and np.array_equal(ptr_, o_ptr)
+    # a user who is her own friend, and friends listed twice, change nothing / count twice like the reference's row selection
+    Y2 = sp.csr_matrix((np.ones(3), ([0, 0, 1], [0, 1, 0])), shape=(n_users, n_users))
+    ids2, cnts2, ptr2 = prepare_social_data(X, Y2)
+    own0 = set(X[0].indices.tolist())
+    want0 = sorted(set(X[1].indices.tolist()) - own0)
+    assert ids2[ptr2[0]:ptr2[1]].tolist() == want0 and set(cnts2[ptr2[0]:ptr2[1]].tolist()) <= {1}
+    for k in (1, 126, 128, 512):
+        assert check_tri_factor_width(k) == k
+    for k in (0, 130, 516, 1024):
+        with pytest.raises(ValueError):
+            check_tri_factor_width(k)

@@ -1,5 +1,5 @@
 #!/usr/bin/env bash
-# One-GPU trip used during development:  gpurun --timeout 2400 -- bash tools/trip_n1.sh
+# One-GPU trip used during development:  gpurun --timeout 2400 -- bash tools/trips/trip_n1.sh
 # full GPU test suite, smoke, default bench, rank sweep; everything lands in gpurun_out/.
 mkdir -p gpurun_out
 python -c "

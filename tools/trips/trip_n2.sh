@@ -1,5 +1,5 @@
 #!/usr/bin/env bash
-# 2-GPU trip used during development:  gpurun --gpus 2 --timeout 1500 -- bash tools/trip_n2.sh
+# 2-GPU trip used during development:  gpurun --gpus 2 --timeout 1500 -- bash tools/trips/trip_n2.sh
 # NCCL path of the bench + sharded-fit functional check (BPR and MF) + the GPU test suite
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name --format=csv > gpurun_out/gpus.txt 2>&1

@@ -1,5 +1,5 @@
 #!/usr/bin/env bash
-# round-2 trip A (1 GPU):  gpurun --timeout 1500 -- bash tools/trip_r2_a.sh
+# round-2 trip A (1 GPU):  gpurun --timeout 1500 -- bash tools/trips/trip_r2_a.sh
 # GPU test suite, smoke, the new default bench (configs[2] on one GPU), reference arm, ncu baselines of the timed kernels
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name,memory.total --format=csv > gpurun_out/gpu.txt 2>&1

@@ -1,5 +1,5 @@
 #!/usr/bin/env bash
-# round-2 2-GPU trip:  gpurun --gpus 2 --timeout 1500 -- bash tools/trip_r2_n2.sh
+# round-2 2-GPU trip:  gpurun --gpus 2 --timeout 1500 -- bash tools/trips/trip_r2_n2.sh
 # sharded-fit functional check (BPR + MF, NVLink peer exchange), the bench at N = 2 (default = p2p exchange; then NCCL for A/B), reference arm
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name --format=csv > gpurun_out/gpus.txt 2>&1

@@ -1,5 +1,5 @@
 #!/usr/bin/env bash
-# round-2 8-GPU trip:  gpurun --gpus 8 --timeout 900 -- bash tools/trip_r2_n8.sh      (also used with --gpus 4: N follows the visible GPUs)
+# round-2 8-GPU trip:  gpurun --gpus 8 --timeout 900 -- bash tools/trips/trip_r2_n8.sh      (also used with --gpus 4: N follows the visible GPUs)
 mkdir -p gpurun_out
 N=$(nvidia-smi --query-gpu=index --format=csv,noheader | wc -l)
 nvidia-smi --query-gpu=index,name --format=csv > gpurun_out/gpus_n$N.txt 2>&1
