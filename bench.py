@@ -343,6 +343,27 @@ def time_cpu_epochs(run, nnz, min_seconds=8.0, max_epochs=6):
 
 
 # --------------------------------------------------------------------------------------
+def checked_item_sync(sync, tensors, world):
+    """After the warm-up exchanges: if the peer-memory exchange reported a missing peer on ANY rank (its bounded waits expired),
+    every rank drops it, the replicas are re-synchronised from rank 0 and the delta-kernel + NCCL path takes over; the JSON line
+    says so.  Returns (sync, note)."""
+    import torch
+    import torch.distributed as dist
+    if sync is None or not hasattr(sync, "failed"):
+        return sync, None
+    bad = torch.tensor([1 if sync.failed() else 0], device=tensors[0].device)
+    dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+    if int(bad.item()) == 0:
+        return sync, None
+    from cornac_b200.parallel import ItemReplicaSync
+    torch.cuda.synchronize()
+    sync.close()
+    for t in tensors:
+        dist.broadcast(t, 0)
+    log("[bench] the peer-memory exchange timed out on some rank during the warm-up: falling back to delta kernels + NCCL all-reduce")
+    return ItemReplicaSync(tensors), "peer-memory exchange timed out during the warm-up; timed region ran delta kernels + NCCL all-reduce"
+
+
 def workload_text(W, world):
     return ("%s: ONE model of %d users x %d items x %d interactions, BPR k=%d, lr=%g reg=%g use_bias; user activity "
             "log-normal, item popularity Zipf(1.0), unique pairs; generated as %d user blocks, rank r owns blocks "
@@ -440,6 +461,8 @@ def main():
         if sync is not None:
             sync.exchange()
     barrier()
+    sync, exchange_note = checked_item_sync(sync, [V, B], world)
+    exchange_kind = type(sync).__name__ if sync is not None else None
     stats.zero_()
     clocks = ClockSampler(local_rank)
     if rank == 0:
@@ -511,6 +534,9 @@ def main():
                              ("%s: one fused NVLink peer-memory kernel per tensor (reduce-scatter + apply + all-gather of %d MB)"
                               if exchange_kind == "PeerItemExchange" else
                               "%s: delta_make -> NCCL all-reduce(%d MB, + the touched-by count) -> delta_apply") % (exchange_kind, (W["n_items"] * (k + 1) * 4) // 1000000))}
+
+    if world > 1 and exchange_note:
+        per_rank["exchange_note"] = exchange_note
 
     def over_ranks(ms):
         if world == 1:
@@ -799,6 +825,7 @@ def run_mf(W, engine, data, dev, world=1, over_ranks=lambda ms: ms, exchange="au
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    sync, _ = checked_item_sync(sync, [V, Bi], world)
     steps = 3
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
