@@ -219,3 +219,26 @@ def test_sbpr_social_item_lists_match_the_reference_fixture():
     for k in (0, 130, 516, 1024):
         with pytest.raises(ValueError):
             check_tri_factor_width(k)
+
+
+def test_block_plan_of_the_cache_blocked_order_is_host_arithmetic():
+    """b200_bpr_block_plan (no CUDA): 1 x 1 while the rows fit two 40 MB parts, else ceil(bytes / 40 MB) windows / item blocks --
+    the configs[2] whole-model plan the bench reports (123 x 13) -- and the dev knob B200_BPR_PART_MB rescales it."""
+    from cornac_b200 import _lib
+    L = _lib.load()
+    wn, bn = ctypes.c_uint32(), ctypes.c_uint32()
+
+    def plan(n_users, n_items, k):
+        assert L.b200_bpr_block_plan(n_users, n_items, k, ctypes.byref(wn), ctypes.byref(bn)) == 0
+        return wn.value, bn.value
+
+    os.environ.pop("B200_BPR_PART_MB", None)
+    assert plan(943, 1682, 10) == (1, 1)
+    assert plan(10_000_000, 1_000_000, 128) == (123, 13)
+    assert plan(1_250_000, 1_000_000, 128) == (16, 13)
+    os.environ["B200_BPR_PART_MB"] = "80"
+    try:
+        assert plan(10_000_000, 1_000_000, 128) == (62, 7)
+    finally:
+        os.environ.pop("B200_BPR_PART_MB", None)
+    assert L.b200_bpr_block_plan(0, 10, 8, ctypes.byref(wn), ctypes.byref(bn)) != 0      # bad argument -> error code, no crash
